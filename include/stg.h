@@ -1,0 +1,228 @@
+/* stg.h — C-ABI of the B200-native batched LLGS hot path (libstg.so).
+ *
+ * The reference (danieleschmidt/spin-torque-rl-gym) is pure Python and has no FFI; these entry points are what a
+ * ctypes binding in the reference would call in place of its per-env NumPy loops. Each entry point names the reference
+ * interface it replaces (paths relative to /root/reference/spin_torque_gym/).
+ *
+ * Conventions
+ *   - Plain C: pointers + sizes only. All `d_*` pointers are DEVICE pointers owned by the caller (PyTorch tensors in the
+ *     host layer). The library allocates nothing persistent and keeps no state between calls (re-entrant).
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream). No hidden
+ *     synchronisation.
+ *   - Return value: 0 ok; <0 bad argument (STG_E_*); >0 a cudaError_t from the launch. Numerical failures of individual
+ *     envs are reported per env in status[] and never as an error code.
+ *   - State is kept in FP64 struct-of-arrays planes regardless of the arithmetic type; `_f32` / `_f64` select the type the
+ *     RHS / integrator stages are computed in.
+ */
+#ifndef STG_H_
+#define STG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STG_ABI_VERSION 1
+
+/* error codes */
+#define STG_OK 0
+#define STG_E_NULL (-1)      /* required pointer is NULL        */
+#define STG_E_SIZE (-2)      /* negative / inconsistent size    */
+#define STG_E_ENUM (-3)      /* unknown enum / flag combination */
+#define STG_E_ALIGN (-4)     /* pointer not aligned as required */
+
+/* device kinds: which compute_resistance() formula the env uses (devices/stt_mram.py:78-94,
+ * devices/sot_mram.py:196-228, devices/vcma_mram.py:236-257) */
+#define STG_DEV_STT 0
+#define STG_DEV_SOT 1
+#define STG_DEV_VCMA 2
+
+/* integrators of SimpleLLGSSolver (physics/simple_solver.py:254-295) */
+#define STG_INT_RK4 0
+#define STG_INT_EULER 1
+
+/* step flags */
+#define STG_F_THERMAL_PHILOX 0x01u   /* thermal field from the in-kernel Philox4x32-10 stream                     */
+#define STG_F_THERMAL_INJECT 0x02u   /* thermal field from the caller's noise tensor (parity / debugging)          */
+#define STG_F_AUTORESET 0x04u        /* envs that terminate/truncate are reset in the same call (SB3 VecEnv rule)  */
+#define STG_F_EULER 0x08u            /* SimpleLLGSSolver(method='euler') instead of 'rk4'                          */
+#define STG_F_SORTED 0x10u           /* d_perm holds an env permutation (e.g. sorted by substep count)             */
+#define STG_F_AXIS_Z 0x20u           /* caller asserts stg_stt_all_axis_z(): kernels drop structurally-zero terms   */
+
+/* Raw physical parameters of one device parameter set (FP64, SI units). Mirrors the `device_params` dict read by
+ * SimpleLLGSSolver._compute_dmdt/_compute_effective_field (physics/simple_solver.py:310-315, 358-380) plus the env
+ * configuration of SpinTorqueEnv.__init__ (envs/spin_torque_env.py:36-53). */
+typedef struct StgSttParams {
+    double damping;                  /* alpha                                                     */
+    double saturation_magnetization; /* Ms  [A/m]                                                 */
+    double uniaxial_anisotropy;      /* Ku  [J/m^3]                                               */
+    double volume;                   /* V   [m^3]                                                 */
+    double polarization;             /* P                                                         */
+    double easy_axis[3];             /* normalised by the library like the solver does (:319)     */
+    double reference_magnetization[3];
+    double resistance_parallel;      /* R_P  [Ohm]                                                */
+    double resistance_antiparallel;  /* R_AP [Ohm]                                                */
+    double area;                     /* A [m^2], default 1e-14 (envs/spin_torque_env.py:476)      */
+    double series_resistance;        /* SOT: 0.1*rho/(t_HM*A*1e-12) (devices/sot_mram.py:219-226) */
+    double temperature;              /* K                                                         */
+    double applied_field[3];         /* constant H_app [A/m] (env passes 0)                       */
+    double max_current;              /* A/m^2 (env clip, :430)                                    */
+    double max_duration;             /* s     (env clip, :431)                                    */
+    double success_threshold;        /* alignment threshold (:353)                                */
+    double energy_penalty_weight;    /* w_E (:193)                                                */
+    double max_step;                 /* SimpleLLGSSolver.max_step, 1e-12 (:29)                    */
+    int32_t max_steps;               /* episode length (:372)                                     */
+    int32_t device_kind;             /* STG_DEV_*                                                 */
+    int32_t thermal;                 /* include_thermal_fluctuations                              */
+    int32_t solver_valid;            /* 0: RobustLLGSSolver input validation fails => m never moves
+                                        (utils/robust_solver.py:152-190)               */
+} StgSttParams;
+
+/* Folded per-parameter-set constants consumed by the kernels (produced on the host by stg_stt_fold, uploaded once by the
+ * caller). Opaque to callers: treat as STG_FOLDED_BYTES bytes. */
+#define STG_FOLDED_DOUBLES 40
+#define STG_FOLDED_BYTES (STG_FOLDED_DOUBLES * 8)
+typedef struct StgSttFolded {
+    double v[STG_FOLDED_DOUBLES];
+} StgSttFolded;
+
+/* Per-env state, FP64 SoA planes of length n_envs (device pointers). Mirrors SpinTorqueEnv's instance state
+ * (envs/spin_torque_env.py:133-139). */
+typedef struct StgSttState {
+    double* m;           /* [3][n]  current_magnetization (plane-major: mx[n], my[n], mz[n]) */
+    double* target;      /* [3][n]  target_magnetization                                    */
+    double* total_energy;/* [n]                                                             */
+    double* last_action; /* [2][n]  (J, T) after clipping                                   */
+    int32_t* step_count; /* [n]                                                             */
+    int32_t* episode;    /* [n]     episodes completed (advances the Philox reset stream)   */
+} StgSttState;
+
+/* Outputs of one env step (device pointers; any may be NULL except obs/reward/terminated/truncated). */
+typedef struct StgSttStepOut {
+    float* obs;          /* [n][12] f32, _get_observation (envs/spin_torque_env.py:500-520)           */
+    double* reward;      /* [n]     CompositeReward default + clip (envs/spin_torque_env.py:184-207)    */
+    uint8_t* terminated; /* [n]                                                                        */
+    uint8_t* truncated;  /* [n]                                                                        */
+    double* step_energy; /* [n]     energy_consumed (:474-480)                                         */
+    int32_t* n_sub;      /* [n]     substeps integrated (physics/simple_solver.py:137-139)              */
+    int32_t* status;     /* [n]     0 ok; bit0 non-finite/zero-norm guard fired (m kept); bit1 solver
+                                    validation failed (solver_valid==0)                               */
+    float* final_obs;    /* [n][12] with STG_F_AUTORESET: observation before the reset (terminal_observation) */
+    double* stats;       /* [STG_NSTATS] accumulated with atomics (episode statistics, K5 input)       */
+} StgSttStepOut;
+
+/* stats vector layout (all doubles, SUM-reducible across ranks) */
+#define STG_STAT_STEPS 0        /* env-steps executed                */
+#define STG_STAT_SUBSTEPS 1     /* LLGS substeps integrated          */
+#define STG_STAT_TERMINATED 2   /* episodes ended by success         */
+#define STG_STAT_TRUNCATED 3    /* episodes ended by max_steps       */
+#define STG_STAT_ENERGY 4       /* sum of step energies [J]          */
+#define STG_STAT_REWARD 5       /* sum of rewards                    */
+#define STG_STAT_GUARD 6        /* env-steps whose guard fired       */
+#define STG_STAT_EPLEN 7        /* sum of lengths of ended episodes  */
+#define STG_NSTATS 8
+
+/* Argument block of one batched env step. Host struct (passed by pointer, copied into the kernel's parameter space);
+ * every d_* member is a device pointer.
+ *   d_table        [n_sets] folded parameter sets; d_param_index [n] int32 or NULL (all envs use set 0)
+ *   d_action       [n][2] f32 (J, T) as produced by the policy; clipped like SafetyWrapper + _parse_action
+ *   d_noise        STG_F_THERMAL_INJECT: [n][noise_stride][S][3] f64 N(0,1) samples, S=4 (rk4) or 1 (euler), in the order
+ *                  the reference draws them: (substep, stage, xyz) (physics/simple_solver.py:381)
+ *   d_perm         STG_F_SORTED: [n] int32 env indices processed by consecutive threads (stg_stt_sort_by_substeps)
+ *   d_target_table STG_F_AUTORESET: [n_targets][3] f64 target_states (envs/spin_torque_env.py:117-120)
+ *   seed, env_offset: Philox key / global env id of local env 0 (rank sharding keeps streams independent of #GPUs) */
+typedef struct StgSttStepArgs {
+    const StgSttFolded* d_table;
+    const int32_t* d_param_index;
+    StgSttState state;
+    const float* d_action;
+    StgSttStepOut out;
+    const double* d_noise;
+    int64_t noise_stride;
+    const int32_t* d_perm;
+    const double* d_target_table;
+    uint64_t seed;
+    uint64_t env_offset;
+    int64_t n_envs;
+    int32_t n_sets;
+    int32_t n_targets;
+    uint32_t flags;
+    uint32_t reserved;
+} StgSttStepArgs;
+
+/* Argument block of a batched reset (envs/spin_torque_env.py:250-308) of the envs with d_mask[i]!=0 (all if NULL).
+ *   d_m0 / d_target0: optional [n][3] f64 explicit options['initial_state'] / ['target_state'] (normalised here);
+ *   NULL => m0 = normalise(N(0,1)^3) from Philox, target drawn uniformly from d_target_table [n_targets][3].
+ *   d_obs: [n][12] f32, rows of the reset envs are overwritten with the reset observation (may be NULL). */
+typedef struct StgSttResetArgs {
+    const StgSttFolded* d_table;
+    const int32_t* d_param_index;
+    StgSttState state;
+    const uint8_t* d_mask;
+    const double* d_m0;
+    const double* d_target0;
+    const double* d_target_table;
+    float* d_obs;
+    uint64_t seed;
+    uint64_t env_offset;
+    int64_t n_envs;
+    int32_t n_sets;
+    int32_t n_targets;
+} StgSttResetArgs;
+
+/* Argument block of a batched SimpleLLGSSolver.solve for rectangular pulses (physics/simple_solver.py:71-191):
+ *   d_m0 [n][3] f64; d_pulse [n][3] f64 rows (J, t_pulse, t_end): current_func(t) = J if t <= t_pulse else 0 on (0, t_end);
+ *   d_m_out [n][3] f64 last trajectory row; d_traj NULL or [n][traj_stride][3] f64 (rows 0..n_sub);
+ *   d_n_sub [n] int32 out (may be NULL); d_guard [n] int32 out (may be NULL): 1 if the non-finite guard fired. */
+typedef struct StgSttSolveArgs {
+    const StgSttFolded* d_table;
+    const int32_t* d_param_index;
+    const double* d_m0;
+    const double* d_pulse;
+    double* d_m_out;
+    double* d_traj;
+    int64_t traj_stride;
+    int32_t* d_n_sub;
+    int32_t* d_guard;
+    const double* d_noise;
+    int64_t noise_stride;
+    uint64_t seed;
+    uint64_t env_offset;
+    int64_t n_envs;
+    int32_t n_sets;
+    uint32_t flags;
+} StgSttSolveArgs;
+
+int stg_abi_version(void);
+const char* stg_error_string(int code);
+
+/* Host-side: fold n raw parameter sets into kernel constants (pure CPU, no CUDA call). Replaces the per-RHS-call
+ * dict lookups + constant recomputation of physics/simple_solver.py:310-319, 358-380. */
+int stg_stt_fold(const StgSttParams* params, int32_t n_sets, StgSttFolded* out);
+/* 1 if every folded set has easy_axis == (0,0,1) and zero applied field (then STG_F_AXIS_Z may be passed). */
+int stg_stt_all_axis_z(const StgSttFolded* folded_host, int32_t n_sets);
+
+/* One SpinTorqueEnv.step for n_envs envs. Replaces envs/spin_torque_env.py:310-407 together with
+ * utils/robust_solver.py:75 -> physics/simple_solver.py:71-191, devices/*:compute_resistance,
+ * rewards/composite_reward.py:65-126 and the SafetyWrapper clamps (utils/monitoring.py:288-348). */
+int stg_stt_step_f32(const StgSttStepArgs* args, void* stream);
+int stg_stt_step_f64(const StgSttStepArgs* args, void* stream);
+
+int stg_stt_reset(const StgSttResetArgs* args, void* stream);
+
+/* Counting sort of envs by substep count (descending) so that warps are homogeneous when pulse durations differ
+ * (physics/simple_solver.py:137-139 gives n in [10, 5000]). d_perm [n] int32 out; d_work >= STG_SORT_WORK_INTS int32
+ * scratch (zeroed by the call). */
+#define STG_SORT_BINS 8192
+#define STG_SORT_WORK_INTS STG_SORT_BINS
+int stg_stt_sort_by_substeps(const StgSttFolded* d_table, int32_t n_sets, const int32_t* d_param_index,
+                             const float* d_action, int32_t* d_perm, int32_t* d_work, int64_t n_envs, void* stream);
+
+int stg_stt_solve_f32(const StgSttSolveArgs* args, void* stream);
+int stg_stt_solve_f64(const StgSttSolveArgs* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STG_H_ */

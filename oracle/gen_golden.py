@@ -1,0 +1,194 @@
+"""Generate golden vectors by running the LIVE reference (/root/reference) in this container.
+
+TEST INFRASTRUCTURE ONLY. Usage (build container only; /root/reference does not exist on the GPU box):
+
+    python oracle/gen_golden.py [stt] [array] [rk45] [devices]      # default: all
+
+The reference is imported through oracle/shims (gymnasium / matplotlib are not installed) and sanitised as
+SURVEY.md §8c prescribes: wall-clock timeout off, memo caches off, global NumPy RNG seeded immediately
+before each thermal step. Outputs land in tests/golden/*.npz (small, committed).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = os.environ.get("STG_REFERENCE", "/root/reference")
+
+
+def _import_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit(f"reference checkout not found at {REF}; goldens can only be generated in the build container")
+    sys.path.insert(0, os.path.join(HERE, "shims"))
+    sys.path.insert(0, REF)
+    import logging
+    logging.disable(logging.CRITICAL)
+    warnings.filterwarnings("ignore")
+    import spin_torque_gym  # noqa: F401
+    from spin_torque_gym.envs import SpinTorqueEnv, SpinTorqueArrayEnv
+    return SpinTorqueEnv, SpinTorqueArrayEnv
+
+
+def _sanitise(env):
+    """no RK4->Euler wall-clock switch, no stale caches."""
+    env.solver.timeout = 1e9
+    env.optimizer.cache.ttl = -1
+    env.cache_observations = False
+    return env
+
+
+def _stt_params(**over):
+    from spin_torque_gym.devices import DeviceFactory
+    p = DeviceFactory().get_default_parameters('stt_mram')
+    p.update(over)
+    return p
+
+
+def _run_stt_episode(env, m0, target, actions, seeds=None):
+    obs0, _ = env.reset(seed=0, options={'initial_state': m0, 'target_state': target})
+    out = dict(obs=[obs0], reward=[], terminated=[], truncated=[], m=[env.current_magnetization.copy()],
+               energy=[], total_energy=[], sim_ok=[])
+    for k, a in enumerate(actions):
+        if seeds is not None:
+            np.random.seed(int(seeds[k]))
+        obs, r, term, trunc, info = env.step(a.copy())
+        out['obs'].append(obs)
+        out['reward'].append(r)
+        out['terminated'].append(term)
+        out['truncated'].append(trunc)
+        out['m'].append(env.current_magnetization.copy())
+        out['energy'].append(info['energy_consumed'])
+        out['total_energy'].append(env.total_energy)
+        out['sim_ok'].append(info['simulation_success'])
+    return {k: np.array(v) for k, v in out.items()}
+
+
+def gen_stt():
+    SpinTorqueEnv, _ = _import_reference()
+    cases = {}
+
+    # ---- C1: N=1, thermal off, 100 steps of random pulses, well-conditioned regime ----------
+    rng = np.random.default_rng(0)
+    jm = 1.1e-6
+    m0 = rng.normal(0, 1, 3)
+    m0 /= np.linalg.norm(m0)
+    acts = np.stack([rng.uniform(-jm, jm, 100), rng.uniform(1e-12, 5e-9, 100)], axis=1).astype(np.float32)
+    env = _sanitise(SpinTorqueEnv(device_type='stt_mram', device_params=_stt_params(), max_current=jm,
+                                  include_thermal_fluctuations=False, seed=0))
+    res = _run_stt_episode(env, m0, np.array([0.0, 0.0, 1.0]), acts)
+    cases['c1_det'] = dict(res, m0=m0, target=np.array([0.0, 0.0, 1.0]), actions=acts, max_current=jm,
+                           thermal=0, method='rk4')
+    print("c1_det done", res['m'][-1], flush=True)
+
+    # ---- same regime reached through a scaled volume and action-scale currents ---------------------------
+    rng = np.random.default_rng(1)
+    m0 = rng.normal(0, 1, 3)
+    m0 /= np.linalg.norm(m0)
+    vol = 1e-23 * 1e12
+    acts = np.stack([rng.uniform(-2e6, 2e6, 24), rng.uniform(1e-12, 1.2e-9, 24)], axis=1).astype(np.float32)
+    acts[3, 0] = 0.0          # zero-current step
+    acts[5] = [3e6, 7e-9]     # clipped by max_current / max_duration
+    acts[7, 1] = 0.0          # duration below the 1e-12 floor
+    env = _sanitise(SpinTorqueEnv(device_type='stt_mram', device_params=_stt_params(volume=vol),
+                                  include_thermal_fluctuations=False, max_steps=20, seed=0))
+    res = _run_stt_episode(env, m0, np.array([0.0, 0.0, -1.0]), acts)
+    cases['bigvol_det'] = dict(res, m0=m0, target=np.array([0.0, 0.0, -1.0]), actions=acts, max_current=2e6,
+                               volume=vol, thermal=0, method='rk4', max_steps=20)
+    print("bigvol_det done", flush=True)
+
+    # ---- tilted easy axis / reference layer, Euler integrator ---------------------------------------------
+    rng = np.random.default_rng(2)
+    m0 = rng.normal(0, 1, 3)
+    m0 /= np.linalg.norm(m0)
+    e = np.array([1.0, 2.0, 2.0])
+    refm = np.array([0.0, 1.0, 1.0])
+    tgt = np.array([1.0, 2.0, 2.0])
+    acts = np.stack([rng.uniform(-jm, jm, 16), rng.uniform(1e-12, 8e-10, 16)], axis=1).astype(np.float32)
+    for method in ('rk4', 'euler'):
+        env = _sanitise(SpinTorqueEnv(device_type='stt_mram',
+                                      device_params=_stt_params(easy_axis=e, reference_magnetization=refm,
+                                                                damping=0.05, polarization=0.55,
+                                                                resistance_parallel=1500.0,
+                                                                resistance_antiparallel=4000.0),
+                                      max_current=jm, include_thermal_fluctuations=False, seed=0))
+        env.solver.method = method
+        res = _run_stt_episode(env, m0, tgt, acts)
+        cases[f'tilted_{method}'] = dict(res, m0=m0, target=tgt, actions=acts, max_current=jm, thermal=0,
+                                         method=method, easy_axis=e, reference_magnetization=refm, damping=0.05,
+                                         polarization=0.55, resistance_parallel=1500.0,
+                                         resistance_antiparallel=4000.0)
+        print(f"tilted_{method} done", flush=True)
+
+    # ---- thermal on, noise stream pinned by seeding the global NumPy RNG before every step -----------------
+    rng = np.random.default_rng(3)
+    m0 = rng.normal(0, 1, 3)
+    m0 /= np.linalg.norm(m0)
+    acts = np.stack([rng.uniform(-jm, jm, 12), rng.uniform(1e-12, 6e-10, 12)], axis=1).astype(np.float32)
+    seeds = np.arange(100, 112)
+    env = _sanitise(SpinTorqueEnv(device_type='stt_mram', device_params=_stt_params(), max_current=jm,
+                                  temperature=300.0, include_thermal_fluctuations=True, seed=0))
+    res = _run_stt_episode(env, m0, np.array([0.0, 0.0, 1.0]), acts, seeds)
+    cases['thermal_injected'] = dict(res, m0=m0, target=np.array([0.0, 0.0, 1.0]), actions=acts, max_current=jm,
+                                     thermal=1, method='rk4', seeds=seeds, temperature=300.0)
+    print("thermal_injected done", flush=True)
+
+    # ---- thermal at the unstable equilibrium (m_z = 0): the only place the noise is dynamically visible ----
+    acts = np.tile(np.array([[0.0, 1e-10]], dtype=np.float32), (6, 1))
+    seeds = np.arange(200, 206)
+    outs = []
+    for s in seeds:
+        env = _sanitise(SpinTorqueEnv(device_type='stt_mram', device_params=_stt_params(), max_current=jm,
+                                      temperature=300.0, include_thermal_fluctuations=True, seed=0))
+        r = _run_stt_episode(env, np.array([1.0, 0.0, 0.0]), np.array([0.0, 0.0, 1.0]), acts[:1], [s])
+        outs.append(r['m'][-1])
+    cases['thermal_equator'] = dict(m_final=np.array(outs), seeds=seeds, actions=acts[:1], max_current=jm,
+                                    temperature=300.0)
+    print("thermal_equator done", flush=True)
+
+    flat = {}
+    for cname, c in cases.items():
+        for k, v in c.items():
+            flat[f"{cname}/{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(GOLD, "stt_env.npz"), **flat)
+    print("wrote stt_env.npz")
+
+
+def gen_multi():
+    """64 independent well-conditioned single steps: fresh random m0 / target / action each (what an RL rollout with
+    resets looks like), thermal off. Avoids the deep-pole regime a long reset-free episode collapses into."""
+    SpinTorqueEnv, _ = _import_reference()
+    rng = np.random.default_rng(7)
+    jm = 1.1e-6
+    n = 64
+    m0 = rng.normal(0, 1, (n, 3))
+    m0 /= np.linalg.norm(m0, axis=1, keepdims=True)
+    tgt = np.where(rng.integers(2, size=(n, 1)) == 0, 1.0, -1.0) * np.array([[0.0, 0.0, 1.0]])
+    acts = np.stack([rng.uniform(-jm, jm, n), rng.uniform(1e-12, 2e-9, n)], axis=1).astype(np.float32)
+    env = _sanitise(SpinTorqueEnv(device_type='stt_mram', device_params=_stt_params(), max_current=jm,
+                                  include_thermal_fluctuations=False, seed=0))
+    out = dict(obs0=[], obs=[], reward=[], terminated=[], truncated=[], m=[], energy=[])
+    for k in range(n):
+        o0, _ = env.reset(seed=0, options={'initial_state': m0[k], 'target_state': tgt[k]})
+        o, r, te, tr, info = env.step(acts[k].copy())
+        out['obs0'].append(o0); out['obs'].append(o); out['reward'].append(r); out['terminated'].append(te)
+        out['truncated'].append(tr); out['m'].append(env.current_magnetization.copy())
+        out['energy'].append(info['energy_consumed'])
+    np.savez_compressed(os.path.join(GOLD, "stt_multi.npz"), m0=m0, target=tgt, actions=acts, max_current=jm,
+                        **{k: np.array(v) for k, v in out.items()})
+    print("wrote stt_multi.npz")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["stt", "multi", "array", "rk45", "devices"]
+    os.makedirs(GOLD, exist_ok=True)
+    for w in what:
+        fn = globals().get(f"gen_{w}")
+        if fn is None:
+            raise SystemExit(f"unknown golden set {w}")
+        fn()

@@ -1,0 +1,145 @@
+"""ctypes binding of libstg.so (include/stg.h). The product path has NO CPU fallback: if the library is missing or
+CUDA is unavailable, calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+from . import build as _build
+
+c_double3 = C.c_double * 3
+
+# flags / enums (include/stg.h)
+F_THERMAL_PHILOX = 0x01
+F_THERMAL_INJECT = 0x02
+F_AUTORESET = 0x04
+F_EULER = 0x08
+F_SORTED = 0x10
+F_AXIS_Z = 0x20
+DEV_STT, DEV_SOT, DEV_VCMA = 0, 1, 2
+NSTATS = 8
+STAT_NAMES = ("steps", "substeps", "terminated", "truncated", "energy", "reward", "guard", "episode_length")
+FOLDED_DOUBLES = 40
+SORT_WORK_INTS = 8192
+OBS_DIM = 12
+
+
+class StgSttParams(C.Structure):
+    _fields_ = [
+        ("damping", C.c_double), ("saturation_magnetization", C.c_double), ("uniaxial_anisotropy", C.c_double),
+        ("volume", C.c_double), ("polarization", C.c_double), ("easy_axis", c_double3),
+        ("reference_magnetization", c_double3), ("resistance_parallel", C.c_double),
+        ("resistance_antiparallel", C.c_double), ("area", C.c_double), ("series_resistance", C.c_double),
+        ("temperature", C.c_double), ("applied_field", c_double3), ("max_current", C.c_double),
+        ("max_duration", C.c_double), ("success_threshold", C.c_double), ("energy_penalty_weight", C.c_double),
+        ("max_step", C.c_double), ("max_steps", C.c_int32), ("device_kind", C.c_int32), ("thermal", C.c_int32),
+        ("solver_valid", C.c_int32),
+    ]
+
+
+class StgSttFolded(C.Structure):
+    _fields_ = [("v", C.c_double * FOLDED_DOUBLES)]
+
+
+class StgSttState(C.Structure):
+    _fields_ = [("m", C.c_void_p), ("target", C.c_void_p), ("total_energy", C.c_void_p), ("last_action", C.c_void_p),
+                ("step_count", C.c_void_p), ("episode", C.c_void_p)]
+
+
+class StgSttStepOut(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("truncated", C.c_void_p),
+                ("step_energy", C.c_void_p), ("n_sub", C.c_void_p), ("status", C.c_void_p), ("final_obs", C.c_void_p),
+                ("stats", C.c_void_p)]
+
+
+class StgSttStepArgs(C.Structure):
+    _fields_ = [("d_table", C.c_void_p), ("d_param_index", C.c_void_p), ("state", StgSttState),
+                ("d_action", C.c_void_p), ("out", StgSttStepOut), ("d_noise", C.c_void_p),
+                ("noise_stride", C.c_int64), ("d_perm", C.c_void_p), ("d_target_table", C.c_void_p),
+                ("seed", C.c_uint64), ("env_offset", C.c_uint64), ("n_envs", C.c_int64), ("n_sets", C.c_int32),
+                ("n_targets", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class StgSttResetArgs(C.Structure):
+    _fields_ = [("d_table", C.c_void_p), ("d_param_index", C.c_void_p), ("state", StgSttState),
+                ("d_mask", C.c_void_p), ("d_m0", C.c_void_p), ("d_target0", C.c_void_p),
+                ("d_target_table", C.c_void_p), ("d_obs", C.c_void_p), ("seed", C.c_uint64),
+                ("env_offset", C.c_uint64), ("n_envs", C.c_int64), ("n_sets", C.c_int32), ("n_targets", C.c_int32)]
+
+
+class StgSttSolveArgs(C.Structure):
+    _fields_ = [("d_table", C.c_void_p), ("d_param_index", C.c_void_p), ("d_m0", C.c_void_p),
+                ("d_pulse", C.c_void_p), ("d_m_out", C.c_void_p), ("d_traj", C.c_void_p), ("traj_stride", C.c_int64),
+                ("d_n_sub", C.c_void_p), ("d_guard", C.c_void_p), ("d_noise", C.c_void_p),
+                ("noise_stride", C.c_int64), ("seed", C.c_uint64), ("env_offset", C.c_uint64), ("n_envs", C.c_int64),
+                ("n_sets", C.c_int32), ("flags", C.c_uint32)]
+
+
+# every symbol include/stg.h declares: (name, restype, argtypes)
+SYMBOLS = {
+    "stg_abi_version": (C.c_int, []),
+    "stg_error_string": (C.c_char_p, [C.c_int]),
+    "stg_stt_fold": (C.c_int, [C.POINTER(StgSttParams), C.c_int32, C.POINTER(StgSttFolded)]),
+    "stg_stt_all_axis_z": (C.c_int, [C.POINTER(StgSttFolded), C.c_int32]),
+    "stg_stt_step_f32": (C.c_int, [C.POINTER(StgSttStepArgs), C.c_void_p]),
+    "stg_stt_step_f64": (C.c_int, [C.POINTER(StgSttStepArgs), C.c_void_p]),
+    "stg_stt_reset": (C.c_int, [C.POINTER(StgSttResetArgs), C.c_void_p]),
+    "stg_stt_sort_by_substeps": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int64, C.c_void_p]),
+    "stg_stt_solve_f32": (C.c_int, [C.POINTER(StgSttSolveArgs), C.c_void_p]),
+    "stg_stt_solve_f64": (C.c_int, [C.POINTER(StgSttSolveArgs), C.c_void_p]),
+}
+
+_LIB: Optional[C.CDLL] = None
+
+
+class StgError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load libstg.so (building it in-tree with nvcc first if it is missing or stale). Raises if impossible."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build()
+        except Exception as exc:  # a stale but present library is still usable on a box without nvcc
+            if not os.path.exists(path):
+                raise StgError(f"libstg.so is missing and could not be built: {exc}") from exc
+    if not os.path.exists(path):
+        raise StgError(f"{path} not found: the CUDA extension is required (no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.stg_abi_version() != 1:
+        raise StgError("libstg.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, what: str = "stg call") -> None:
+    if rc != 0:
+        msg = load().stg_error_string(rc).decode()
+        raise StgError(f"{what} failed with code {rc}: {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise StgError("CUDA device required: spin_torque_rl_gym_b200 has no CPU fallback for the LLGS hot path")
+    return torch
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,338 @@
+// stt_env_core.cuh — per-env body of the SpinTorque-v0 step (action parse -> integrate -> energy/reward/obs -> auto-reset).
+// Shared by the CUDA kernels (stt_kernels.cu) and by the host build used for CPU-side arithmetic checks (tests/hostsim).
+#pragma once
+
+#include "../../include/stg.h"
+#include "llgs_core.cuh"
+
+namespace stg {
+
+constexpr int kObs = 12;
+
+// ---- action -> (J, T) ------------------------------------------------------------------------------------------------
+// utils/monitoring.py:288-315 (float32 clips, NaN/Inf -> (0, 1e-12)) then envs/spin_torque_env.py:409-433 (FP64 clips)
+STG_HD void parse_action(float a0, float a1, double max_current, double max_duration, double& J,
+                                             double& T) {
+    // np.clip keeps NaN (and clips +-Inf), so only NaN reaches the reference's NaN/Inf test; fminf/fmaxf would drop it
+    const bool bad = (a0 != a0) || (a1 != a1);
+    a0 = fminf(fmaxf(a0, -1e8f), 1e8f);
+    a1 = fminf(fmaxf(a1, 1e-12f), 1e-6f);
+    if (bad) {
+        a0 = 0.0f;
+        a1 = 1e-12f;
+    }
+    J = fmin(fmax((double)a0, -max_current), max_current);
+    T = fmin(fmax((double)a1, 1e-12), max_duration);
+}
+
+template <typename R>
+STG_HD void make_consts(const double* f, double dt, double J, StepConsts<R>& c) {
+    double G = -f[FI_GEFF] * dt;
+    c.ck = (R)(G * f[FI_HK]);
+    c.cd = (R)(-G * f[FI_MS]);
+    c.cth = (R)(G * f[FI_HTH]);
+    c.alpha = (R)f[FI_ALPHA];
+    c.a_on = (fabs(J) > 1e-12) ? (R)(f[FI_AJ_PER_J] * J * dt) : R(0);   // physics/simple_solver.py:327-331
+    c.ex = (R)f[FI_EX]; c.ey = (R)f[FI_EY]; c.ez = (R)f[FI_EZ];
+    c.bax = (R)(G * f[FI_HAX]); c.bay = (R)(G * f[FI_HAY]); c.baz = (R)(G * f[FI_HAZ]);
+}
+
+// Integrate n substeps of size dt from (mx,my,mz); pulse of density J on while t <= t_pulse.
+// NOISE: 0 none, 1 Philox, 2 injected tensor. Traj: optional [n+1][3] FP64 rows.
+template <typename R, bool AXIS_Z, int NOISE, bool EULER>
+STG_HD void integrate(const StepConsts<R>& c, double& mx, double& my, double& mz, int n, double dt,
+                                          double t_pulse, double t_end, const Philox& ph, uint64_t gid, uint32_t step_id,
+                                          const double* noise_row, double* traj, int& guard) {
+    constexpr bool TH = NOISE != 0;
+    // substeps whose four stage times are certainly inside the pulse run with constant a_on; the few around the pulse edge
+    // evaluate current_func(t) exactly in FP64 (the k4 stage of the LAST substep sees t_i+dt > T for ~16 % of f32 durations)
+    int i_safe;
+    if (t_pulse >= t_end) {
+        i_safe = n - 1;
+    } else {
+        double q = t_pulse / dt - 2.0;
+        i_safe = q < 0.0 ? 0 : (q > (double)n ? n : (int)q);
+    }
+    if (traj) { traj[0] = mx; traj[1] = my; traj[2] = mz; }
+    if constexpr (sizeof(R) == 4 && AXIS_Z && NOISE == 0) {
+        // FP32 stages, no noise: block-scaled transverse pair (llgs_core.cuh: ScaledState)
+        ScaledState st{mx, my, mz, 1.0, 1.0, 1.0f};
+        rescale(st);
+        for (int i = 0; i < n; ++i) {
+            float a1 = c.a_on, a2 = c.a_on, a3 = c.a_on, a4 = c.a_on;
+            if (i >= i_safe) {
+                a1 = pulse_on(i, 0, dt, t_pulse) ? c.a_on : 0.0f;
+                a2 = pulse_on(i, 1, dt, t_pulse) ? c.a_on : 0.0f;
+                a3 = a2;
+                a4 = pulse_on(i, 2, dt, t_pulse) ? c.a_on : 0.0f;
+            }
+            substep_scaled<EULER>(c, st, a1, a2, a3, a4, guard);
+            if ((i & 15) == 15) rescale(st);
+            if (traj) {
+                traj[3 * (i + 1) + 0] = st.sx * st.inv_s; traj[3 * (i + 1) + 1] = st.sy * st.inv_s;
+                traj[3 * (i + 1) + 2] = st.z;
+            }
+        }
+        mx = st.sx * st.inv_s; my = st.sy * st.inv_s; mz = st.z;
+        return;
+    }
+    for (int i = 0; i < n; ++i) {
+        R a1 = c.a_on, a2 = c.a_on, a3 = c.a_on, a4 = c.a_on;
+        if (i >= i_safe) {
+            a1 = pulse_on(i, 0, dt, t_pulse) ? c.a_on : R(0);
+            a2 = pulse_on(i, 1, dt, t_pulse) ? c.a_on : R(0);
+            a3 = a2;
+            a4 = pulse_on(i, 2, dt, t_pulse) ? c.a_on : R(0);
+        }
+        R xi[EULER ? 3 : 12];
+        if (NOISE == 1) {
+            if (EULER) {
+                float z[4];
+                philox_normals4(ph, gid, step_id, (uint32_t)i, 0u, z);
+                xi[0] = (R)z[0]; xi[1] = (R)z[1]; xi[2] = (R)z[2];
+            } else {
+                float z[12];
+                philox_normals12(ph, gid, step_id, (uint32_t)i, z);
+#pragma unroll
+                for (int q = 0; q < 12; ++q) xi[q] = (R)z[q];
+            }
+        } else if (NOISE == 2) {
+            constexpr int S = EULER ? 3 : 12;
+#pragma unroll
+            for (int q = 0; q < S; ++q) xi[q] = (R)noise_row[(int64_t)i * S + q];
+        }
+        substep<R, AXIS_Z, TH, EULER>(c, mx, my, mz, a1, a2, a3, a4, TH ? xi : nullptr, guard);
+        if (traj) {
+            traj[3 * (i + 1) + 0] = mx; traj[3 * (i + 1) + 1] = my; traj[3 * (i + 1) + 2] = mz;
+        }
+    }
+}
+
+// observation row (envs/spin_torque_env.py:500-520) + SafetyWrapper.validate_observation (utils/monitoring.py:317-330)
+STG_HD void make_obs(const double* f, double mx, double my, double mz, double tx, double ty, double tz,
+                                         int step, double total_e, double J, double T, float* o) {
+    double r = resistance(f, mx, my, mz);
+    double max_steps = f[FI_MAXSTEPS];
+    o[0] = (float)mx; o[1] = (float)my; o[2] = (float)mz;
+    o[3] = (float)tx; o[4] = (float)ty; o[5] = (float)tz;
+    o[6] = (float)(r / f[FI_RP]);
+    o[7] = (float)(f[FI_TEMP] / 300.0);
+    o[8] = (float)((max_steps - (double)step) / max_steps);
+    o[9] = (float)(total_e / 1e-12);
+    o[10] = (float)(J / f[FI_MAXCUR]);
+    o[11] = (float)(T / f[FI_MAXDUR]);
+    bool bad = false;
+#pragma unroll
+    for (int q = 0; q < kObs; ++q) bad |= !(fabsf(o[q]) <= 3.4028234e38f);
+    if (bad) {
+#pragma unroll
+        for (int q = 0; q < kObs; ++q) {
+            float v = o[q];
+            o[q] = (v != v) ? 0.0f : (v > 3.4028234e38f ? 1e6f : (v < -3.4028234e38f ? -1e6f : v));
+        }
+    }
+}
+
+// normalise(N(0,1)^3) start state + uniform target pick from the Philox reset stream (envs/spin_torque_env.py:286-299)
+STG_HD void draw_reset(const Philox& ph, uint64_t gid, uint32_t episode, const double* target_table,
+                                           int n_targets, double& mx, double& my, double& mz, double& tx, double& ty,
+                                           double& tz) {
+    uint32_t o[4];
+    float z0, z1, z2, z3;
+    uint32_t attempt = 0;
+    do {
+        ph((uint32_t)gid, (uint32_t)(gid >> 32), episode, 0xFFFF0000u + attempt, o);
+        box_muller(o[0], o[1], z0, z1);
+        box_muller(o[2], o[3], z2, z3);
+        ++attempt;
+    } while (z0 * z0 + z1 * z1 + z2 * z2 < 1e-12f && attempt < 8);
+    double n = sqrt((double)z0 * z0 + (double)z1 * z1 + (double)z2 * z2);
+    mx = z0 / n; my = z1 / n; mz = z2 / n;
+    ph((uint32_t)gid, (uint32_t)(gid >> 32), episode, 0xFFFF8000u, o);
+    int k = (int)(((uint64_t)o[0] * (uint64_t)n_targets) >> 32);
+    tx = target_table[3 * k + 0]; ty = target_table[3 * k + 1]; tz = target_table[3 * k + 2];
+}
+
+
+// Everything one env-step produces besides the state update (kept in registers until the block-level store phase).
+struct EnvStepResult {
+    float obs[kObs];
+    float final_obs[kObs];
+    double reward, energy;
+    int n_sub, status;
+    bool terminated, truncated, did_reset, valid;
+    int step_after;     // step count of the finished step (episode length if it ended)
+};
+
+// One env (index e of a.n_envs): reads and updates the FP64 state planes, returns the outputs in `r`.
+template <typename R, bool AXIS_Z, int NOISE, bool EULER>
+STG_HD void env_step_body(const StgSttStepArgs& a, int64_t e, EnvStepResult& r) {
+    const int64_t n = a.n_envs;
+    const bool autoreset = (a.flags & STG_F_AUTORESET) != 0;
+    const double* f = a.d_table[a.d_param_index ? a.d_param_index[e] : 0].v;
+    double mx = a.state.m[e], my = a.state.m[n + e], mz = a.state.m[2 * n + e];
+    double tx = a.state.target[e], ty = a.state.target[n + e], tz = a.state.target[2 * n + e];
+    double total_e = a.state.total_energy[e];
+    int step = a.state.step_count[e];
+    const float a0 = a.d_action[2 * e], a1 = a.d_action[2 * e + 1];
+
+    double J, T;
+    parse_action(a0, a1, f[FI_MAXCUR], f[FI_MAXDUR], J, T);
+    const double prev_align = mx * tx + my * ty + mz * tz;                     // envs/spin_torque_env.py:338-339
+    const StepPlan plan = substep_plan(T, f[FI_MAXSTEP_DT]);
+
+    // ---- integrate (utils/robust_solver.py:75 -> physics/simple_solver.py:147-179) ---------------------------------
+    double nx = mx, ny = my, nz = mz;
+    int guard = 0;
+    int status = 0;
+    const bool valid = f[FI_VALID] != 0.0 && (!AXIS_Z || f[FI_AXISZ] != 0.0);
+    if (valid) {
+        guard_normalise<R>(nx, ny, nz, guard);                                 // SimpleLLGSSolver.solve :119
+        StepConsts<R> c;
+        make_consts<R>(f, plan.dt, J, c);
+        Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+        const uint64_t gid = a.env_offset + (uint64_t)e;
+        const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
+        // Philox stream position: (episode, step) packed so that every env-step of every episode is distinct
+        const uint32_t step_id = ((uint32_t)a.state.episode[e] << 12) ^ (uint32_t)step;
+        if (f[FI_HTH] > 0.0 || NOISE == 0) {
+            integrate<R, AXIS_Z, NOISE, EULER>(c, nx, ny, nz, plan.n, plan.dt, T, T, ph, gid, step_id, nrow, nullptr, guard);
+        } else {
+            integrate<R, AXIS_Z, 0, EULER>(c, nx, ny, nz, plan.n, plan.dt, T, T, ph, gid, step_id, nullptr, nullptr, guard);
+        }
+        // env-level renormalisation of the last trajectory row (envs/spin_torque_env.py:464)
+        const double inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+        nx *= inv; ny *= inv; nz *= inv;
+        if (guard) {   // A3: a trajectory row failed validation => solver result discarded, m unchanged
+            nx = mx; ny = my; nz = mz;
+            status |= 1;
+        }
+    } else {
+        status |= 2;
+    }
+
+    // ---- Joule energy with the PRE-step m (envs/spin_torque_env.py:474-480) ------------------------------------------
+    double energy = 0.0;
+    if (fabs(J) > 1e-12) {
+        const double res = resistance(f, mx, my, mz);
+        const double v = J * res * f[FI_AREA];
+        energy = v * v / res * T;
+    }
+    total_e += energy;
+    step += 1;
+    const double align = nx * tx + ny * ty + nz * tz;                           // :350-353
+    const bool success = align >= f[FI_SUCC];
+    // CompositeReward default components in dict order (:184-207), then validate_reward (utils/monitoring.py:332-348)
+    double reward = 0.0;
+    reward += 10.0 * (success ? 10.0 : 0.0);
+    reward += (-f[FI_WE]) * (-energy / 1e-12);
+    reward += 1.0 * (align - prev_align);
+    if (!(fabs(reward) <= 1.7e308)) reward = -1.0;
+    reward = fmin(fmax(reward, -1e6), 1e6);
+    const bool truncated = step >= (int)f[FI_MAXSTEPS];                          // :371-372
+
+    make_obs(f, nx, ny, nz, tx, ty, tz, step, total_e, J, T, r.obs);
+    r.reward = reward; r.energy = energy; r.n_sub = plan.n; r.status = status;
+    r.terminated = success; r.truncated = truncated; r.valid = valid; r.step_after = step;
+    r.did_reset = false;
+
+    double lj = J, lt = T;
+    if (autoreset && (success || truncated)) {
+        // same-call reset (SB3 VecEnv convention): the returned obs is the first obs of the next episode; the last obs of the
+        // finished one goes to final_obs
+        r.did_reset = true;
+        for (int q = 0; q < kObs; ++q) r.final_obs[q] = r.obs[q];
+        const uint32_t ep = (uint32_t)a.state.episode[e] + 1u;
+        a.state.episode[e] = (int32_t)ep;
+        Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+        draw_reset(ph, a.env_offset + (uint64_t)e, ep, a.d_target_table, a.n_targets, nx, ny, nz, tx, ty, tz);
+        a.state.target[e] = tx; a.state.target[n + e] = ty; a.state.target[2 * n + e] = tz;
+        step = 0; total_e = 0.0; lj = 0.0; lt = 0.0;
+        make_obs(f, nx, ny, nz, tx, ty, tz, step, total_e, lj, lt, r.obs);
+    }
+    a.state.m[e] = nx; a.state.m[n + e] = ny; a.state.m[2 * n + e] = nz;
+    a.state.total_energy[e] = total_e;
+    a.state.step_count[e] = step;
+    a.state.last_action[e] = lj;
+    a.state.last_action[n + e] = lt;
+
+    a.out.reward[e] = reward;
+    a.out.terminated[e] = success ? 1 : 0;
+    a.out.truncated[e] = truncated ? 1 : 0;
+    if (a.out.step_energy) a.out.step_energy[e] = energy;
+    if (a.out.n_sub) a.out.n_sub[e] = plan.n;
+    if (a.out.status) a.out.status[e] = status;
+}
+
+// SpinTorqueEnv.reset for one env (envs/spin_torque_env.py:250-308)
+STG_HD void env_reset_body(const StgSttResetArgs& a, int64_t e) {
+    const int64_t n = a.n_envs;
+    const double* f = a.d_table[a.d_param_index ? a.d_param_index[e] : 0].v;
+    const uint32_t ep = (uint32_t)a.state.episode[e] + 1u;
+    a.state.episode[e] = (int32_t)ep;
+    double mx, my, mz, tx, ty, tz;
+    Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+    if (a.d_target_table && a.n_targets > 0) {
+        draw_reset(ph, a.env_offset + (uint64_t)e, ep, a.d_target_table, a.n_targets, mx, my, mz, tx, ty, tz);
+    } else {
+        const double zt[3] = {0.0, 0.0, 1.0};
+        draw_reset(ph, a.env_offset + (uint64_t)e, ep, zt, 1, mx, my, mz, tx, ty, tz);
+    }
+    if (a.d_m0) {   // options['initial_state'] -> device.validate_magnetization (devices/base_device.py:94-116)
+        const double x = a.d_m0[3 * e], y = a.d_m0[3 * e + 1], z = a.d_m0[3 * e + 2];
+        const double nn = sqrt(x * x + y * y + z * z);
+        mx = x / nn; my = y / nn; mz = z / nn;
+    }
+    if (a.d_target0) {
+        const double x = a.d_target0[3 * e], y = a.d_target0[3 * e + 1], z = a.d_target0[3 * e + 2];
+        const double nn = sqrt(x * x + y * y + z * z);
+        tx = x / nn; ty = y / nn; tz = z / nn;
+    }
+    a.state.m[e] = mx; a.state.m[n + e] = my; a.state.m[2 * n + e] = mz;
+    a.state.target[e] = tx; a.state.target[n + e] = ty; a.state.target[2 * n + e] = tz;
+    a.state.total_energy[e] = 0.0;
+    a.state.step_count[e] = 0;
+    a.state.last_action[e] = 0.0;
+    a.state.last_action[n + e] = 0.0;
+    if (a.d_obs) make_obs(f, mx, my, mz, tx, ty, tz, 0, 0.0, 0.0, 0.0, a.d_obs + e * kObs);
+}
+
+// Batched SimpleLLGSSolver.solve for one env (physics/simple_solver.py:71-191)
+template <typename R, bool AXIS_Z, int NOISE, bool EULER>
+STG_HD void solve_body(const StgSttSolveArgs& a, int64_t e) {
+    const double* f = a.d_table[a.d_param_index ? a.d_param_index[e] : 0].v;
+    double mx = a.d_m0[3 * e], my = a.d_m0[3 * e + 1], mz = a.d_m0[3 * e + 2];
+    const double J = a.d_pulse[3 * e], t_pulse = a.d_pulse[3 * e + 1], t_end = a.d_pulse[3 * e + 2];
+    int guard = 0;
+    guard_normalise<R>(mx, my, mz, guard);                       // :119
+    int nsub = 0;
+    if (t_end > 0.0 && (!AXIS_Z || f[FI_AXISZ] != 0.0)) {        // t_end <= t_start: trivial solution (:122-123)
+        const StepPlan plan = substep_plan(t_end, f[FI_MAXSTEP_DT]);
+        nsub = plan.n;
+        StepConsts<R> c;
+        make_consts<R>(f, plan.dt, J, c);
+        Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+        const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
+        double* traj = a.d_traj ? a.d_traj + (int64_t)e * a.traj_stride * 3 : nullptr;
+        if (f[FI_HTH] > 0.0 || NOISE == 0)
+            integrate<R, AXIS_Z, NOISE, EULER>(c, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph, a.env_offset + (uint64_t)e,
+                                               0u, nrow, traj, guard);
+        else
+            integrate<R, AXIS_Z, 0, EULER>(c, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph, a.env_offset + (uint64_t)e, 0u,
+                                           nullptr, traj, guard);
+    }
+    a.d_m_out[3 * e] = mx; a.d_m_out[3 * e + 1] = my; a.d_m_out[3 * e + 2] = mz;
+    if (a.d_n_sub) a.d_n_sub[e] = nsub;
+    if (a.d_guard) a.d_guard[e] = guard;
+}
+
+// substep-count bin of an env's action for the counting sort (descending n_sub)
+STG_HD int action_bin(const StgSttFolded* table, const int32_t* pidx, const float* action, int64_t e) {
+    const double* f = table[pidx ? pidx[e] : 0].v;
+    double J, T;
+    parse_action(action[2 * e], action[2 * e + 1], f[FI_MAXCUR], f[FI_MAXDUR], J, T);
+    const int n = substep_plan(T, f[FI_MAXSTEP_DT]).n;
+    return STG_SORT_BINS - 1 - (n < STG_SORT_BINS ? n : STG_SORT_BINS - 1);
+}
+
+}  // namespace stg

@@ -1,0 +1,357 @@
+// stt_kernels.cu — K1: fused SpinTorque-v0 env step / reset / solver kernels + their C-ABI entry points (sm_100a).
+//
+// Thread mapping: one env per thread. Per env-step a thread (stt_env_core.cuh: env_step_body)
+//   1. loads its state (FP64 SoA planes, coalesced) and its action,
+//   2. sanitises the action (SafetyWrapper.validate_action + _parse_action), derives the substep plan in FP64,
+//   3. integrates n_sub fixed RK4/Euler substeps entirely in registers (stage arithmetic in R = float/double, state FP64),
+//   4. evaluates Joule energy, alignment, reward, flags, observation in FP64, optionally resets finished episodes (Philox),
+// then the block
+//   5. stages the 12-float observation rows through shared memory so [n][12] f32 is written as coalesced float4s,
+//   6. accumulates episode statistics (warp shuffle + one atomic per warp and statistic).
+// Reference lines are cited next to each block; the CPU restatement lives in oracle/stt_oracle.py.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/stg.h"
+#include "llgs_core.cuh"
+#include "stt_env_core.cuh"
+
+namespace stg {
+
+constexpr int kBlock = 64;      // 65,536 envs -> 1024 CTAs = 6.9 per SM: balanced to 1.2 % on 148 SMs
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+using StepArgs = StgSttStepArgs;
+using ResetArgs = StgSttResetArgs;
+using SolveArgs = StgSttSolveArgs;
+
+__device__ __forceinline__ void store_row(float* dst, const float* o) {
+    float4* d = reinterpret_cast<float4*>(dst);
+    d[0] = make_float4(o[0], o[1], o[2], o[3]);
+    d[1] = make_float4(o[4], o[5], o[6], o[7]);
+    d[2] = make_float4(o[8], o[9], o[10], o[11]);
+}
+
+template <typename R, bool AXIS_Z, int NOISE, bool EULER>
+__global__ void __launch_bounds__(kBlock) stt_env_step_kernel(const __grid_constant__ StepArgs a) {
+    __shared__ __align__(16) float s_obs[kBlock * kObs];
+    const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const bool active = slot < a.n_envs;
+    const bool sorted = (a.flags & STG_F_SORTED) != 0;
+    const bool want_fin = (a.flags & STG_F_AUTORESET) != 0 && a.out.final_obs != nullptr;
+    const int64_t e = active ? (sorted ? (int64_t)a.d_perm[slot] : slot) : 0;
+
+    EnvStepResult r;
+    r.did_reset = false;
+    if (active) env_step_body<R, AXIS_Z, NOISE, EULER>(a, e, r);
+
+    // ---- observation rows ------------------------------------------------------------------------------------------------
+    if (!sorted) {
+        // consecutive slots are consecutive envs: stage rows in shared memory, write the block's rows as coalesced float4s
+        const int64_t base = (int64_t)blockIdx.x * kBlock;
+        const int64_t rows = (a.n_envs - base) < kBlock ? (a.n_envs - base) : kBlock;
+        const int n4 = (int)(rows * kObs / 4);   // rows*12 floats is always a multiple of 4
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < kObs; ++q) s_obs[threadIdx.x * kObs + q] = r.obs[q];
+        }
+        __syncthreads();
+        {
+            float4* dst = reinterpret_cast<float4*>(a.out.obs + base * kObs);
+            const float4* src = reinterpret_cast<const float4*>(s_obs);
+            for (int q = threadIdx.x; q < n4; q += kBlock) dst[q] = src[q];
+        }
+        if (want_fin) {   // rows of envs that did not reset are written as zeros
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < kObs; ++q) s_obs[threadIdx.x * kObs + q] = r.did_reset ? r.final_obs[q] : 0.0f;
+            }
+            __syncthreads();
+            float4* dst = reinterpret_cast<float4*>(a.out.final_obs + base * kObs);
+            const float4* src = reinterpret_cast<const float4*>(s_obs);
+            for (int q = threadIdx.x; q < n4; q += kBlock) dst[q] = src[q];
+        }
+    } else if (active) {
+        store_row(a.out.obs + e * kObs, r.obs);
+        if (want_fin) {
+            if (!r.did_reset) {
+#pragma unroll
+                for (int q = 0; q < kObs; ++q) r.final_obs[q] = 0.0f;
+            }
+            store_row(a.out.final_obs + e * kObs, r.final_obs);
+        }
+    }
+
+    // ---- episode statistics: warp shuffle reduction, one atomic per warp and statistic (K5 input) ---------------------
+    if (a.out.stats) {
+        double v[STG_NSTATS];
+#pragma unroll
+        for (int q = 0; q < STG_NSTATS; ++q) v[q] = 0.0;
+        if (active) {
+            const bool ended = r.terminated || r.truncated;
+            v[STG_STAT_STEPS] = 1.0;
+            v[STG_STAT_SUBSTEPS] = r.valid ? (double)r.n_sub : 0.0;
+            v[STG_STAT_TERMINATED] = r.terminated ? 1.0 : 0.0;
+            v[STG_STAT_TRUNCATED] = (!r.terminated && r.truncated) ? 1.0 : 0.0;
+            v[STG_STAT_ENERGY] = r.energy;
+            v[STG_STAT_REWARD] = r.reward;
+            v[STG_STAT_GUARD] = (r.status & 1) ? 1.0 : 0.0;
+            v[STG_STAT_EPLEN] = ended ? (double)r.step_after : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < STG_NSTATS; ++q) {
+            const double s = warp_sum(v[q]);
+            if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(a.out.stats + q, s);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) stt_env_reset_kernel(const __grid_constant__ ResetArgs a) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n_envs) return;
+    if (a.d_mask && !a.d_mask[e]) return;
+    env_reset_body(a, e);
+}
+
+// ---- counting sort of envs by substep count (descending) -------------------------------------------------------------
+__global__ void sort_hist_kernel(const StgSttFolded* table, const int32_t* pidx, const float* action, int32_t* hist,
+                                 int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) atomicAdd(hist + action_bin(table, pidx, action, e), 1);
+}
+__global__ void sort_scan_kernel(int32_t* hist) {   // one block of 1024 threads, 8 bins each: exclusive scan in place
+    __shared__ int32_t s[1024];
+    const int t = threadIdx.x;
+    int32_t loc[8];
+    int32_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { loc[q] = hist[t * 8 + q]; sum += loc[q]; }
+    s[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int32_t v = (t >= off) ? s[t - off] : 0;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
+    }
+    int32_t run = s[t] - sum;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { hist[t * 8 + q] = run; run += loc[q]; }
+}
+__global__ void sort_scatter_kernel(const StgSttFolded* table, const int32_t* pidx, const float* action, int32_t* hist,
+                                    int32_t* perm, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) {
+        const int pos = atomicAdd(hist + action_bin(table, pidx, action, e), 1);
+        perm[pos] = (int32_t)e;
+    }
+}
+
+template <typename R, bool AXIS_Z, int NOISE, bool EULER>
+__global__ void __launch_bounds__(kBlock) stt_solve_kernel(const __grid_constant__ SolveArgs a) {
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e >= a.n_envs) return;
+    solve_body<R, AXIS_Z, NOISE, EULER>(a, e);
+}
+
+// ---- dispatch --------------------------------------------------------------------------------------------------------
+template <typename R, bool AXIS_Z, int NOISE>
+static cudaError_t launch_step2(const StepArgs& a, cudaStream_t s) {
+    const unsigned grid = (unsigned)((a.n_envs + kBlock - 1) / kBlock);
+    if (a.flags & STG_F_EULER)
+        stt_env_step_kernel<R, AXIS_Z, NOISE, true><<<grid, kBlock, 0, s>>>(a);
+    else
+        stt_env_step_kernel<R, AXIS_Z, NOISE, false><<<grid, kBlock, 0, s>>>(a);
+    return cudaGetLastError();
+}
+template <typename R>
+static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
+    const int noise = (a.flags & STG_F_THERMAL_INJECT) ? 2 : ((a.flags & STG_F_THERMAL_PHILOX) ? 1 : 0);
+    if (axis_z) {
+        if (noise == 0) return launch_step2<R, true, 0>(a, s);
+        if (noise == 1) return launch_step2<R, true, 1>(a, s);
+        return launch_step2<R, true, 2>(a, s);
+    }
+    if (noise == 0) return launch_step2<R, false, 0>(a, s);
+    if (noise == 1) return launch_step2<R, false, 1>(a, s);
+    return launch_step2<R, false, 2>(a, s);
+}
+
+template <typename R, bool AXIS_Z, int NOISE>
+static cudaError_t launch_solve2(const SolveArgs& a, uint32_t flags, cudaStream_t s) {
+    const unsigned grid = (unsigned)((a.n_envs + kBlock - 1) / kBlock);
+    if (flags & STG_F_EULER)
+        stt_solve_kernel<R, AXIS_Z, NOISE, true><<<grid, kBlock, 0, s>>>(a);
+    else
+        stt_solve_kernel<R, AXIS_Z, NOISE, false><<<grid, kBlock, 0, s>>>(a);
+    return cudaGetLastError();
+}
+template <typename R>
+static cudaError_t launch_solve(const SolveArgs& a, uint32_t flags, bool axis_z, cudaStream_t s) {
+    const int noise = (flags & STG_F_THERMAL_INJECT) ? 2 : ((flags & STG_F_THERMAL_PHILOX) ? 1 : 0);
+    if (axis_z) {
+        if (noise == 0) return launch_solve2<R, true, 0>(a, flags, s);
+        if (noise == 1) return launch_solve2<R, true, 1>(a, flags, s);
+        return launch_solve2<R, true, 2>(a, flags, s);
+    }
+    if (noise == 0) return launch_solve2<R, false, 0>(a, flags, s);
+    if (noise == 1) return launch_solve2<R, false, 1>(a, flags, s);
+    return launch_solve2<R, false, 2>(a, flags, s);
+}
+
+}  // namespace stg
+
+// =====================================================================================================================
+// C-ABI
+// =====================================================================================================================
+using namespace stg;
+
+extern "C" int stg_abi_version(void) { return STG_ABI_VERSION; }
+
+extern "C" const char* stg_error_string(int code) {
+    switch (code) {
+        case STG_OK: return "ok";
+        case STG_E_NULL: return "required pointer is NULL";
+        case STG_E_SIZE: return "negative or inconsistent size";
+        case STG_E_ENUM: return "unknown enum value or flag combination";
+        case STG_E_ALIGN: return "pointer not aligned as required";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown stg error";
+    }
+}
+
+extern "C" int stg_stt_fold(const StgSttParams* params, int32_t n_sets, StgSttFolded* out) {
+    if (!params || !out) return STG_E_NULL;
+    if (n_sets <= 0) return STG_E_SIZE;
+    for (int i = 0; i < n_sets; ++i) {
+        const StgSttParams& p = params[i];
+        if (p.device_kind < STG_DEV_STT || p.device_kind > STG_DEV_VCMA) return STG_E_ENUM;
+        double* v = out[i].v;
+        memset(v, 0, sizeof(out[i].v));
+        const double alpha = p.damping, ms = p.saturation_magnetization, vol = p.volume;
+        v[FI_ALPHA] = alpha;
+        v[FI_GEFF] = kGamma / (1.0 + alpha * alpha);                               // physics/simple_solver.py:338
+        v[FI_HK] = (2.0 * p.uniaxial_anisotropy) / (kMu0 * ms);                    // :368
+        v[FI_MS] = ms;
+        v[FI_AJ_PER_J] = p.polarization / (ms * vol);                              // :330
+        v[FI_HTH] = (p.thermal && p.temperature > 0.0)
+                        ? sqrt(2.0 * alpha * kKbSolver * p.temperature / (kMu0 * ms * vol * kGamma))   // :375-380
+                        : 0.0;
+        const double en = sqrt(p.easy_axis[0] * p.easy_axis[0] + p.easy_axis[1] * p.easy_axis[1] +
+                               p.easy_axis[2] * p.easy_axis[2]);
+        const double rn = sqrt(p.reference_magnetization[0] * p.reference_magnetization[0] +
+                               p.reference_magnetization[1] * p.reference_magnetization[1] +
+                               p.reference_magnetization[2] * p.reference_magnetization[2]);
+        if (!(en > 0.0) || !(rn > 0.0)) return STG_E_SIZE;
+        for (int k = 0; k < 3; ++k) {
+            v[FI_EX + k] = p.easy_axis[k] / en;                                    // :319
+            v[FI_REFX + k] = p.reference_magnetization[k] / rn;
+            v[FI_HAX + k] = p.applied_field[k];
+        }
+        v[FI_RP] = p.resistance_parallel;
+        v[FI_RAP] = p.resistance_antiparallel;
+        v[FI_TMR] = (p.resistance_antiparallel - p.resistance_parallel) / p.resistance_parallel;
+        v[FI_AREA] = p.area;
+        v[FI_RSERIES] = p.series_resistance;
+        v[FI_TEMP] = p.temperature;
+        v[FI_MAXCUR] = p.max_current;
+        v[FI_MAXDUR] = p.max_duration;
+        v[FI_SUCC] = p.success_threshold;
+        v[FI_WE] = p.energy_penalty_weight;
+        v[FI_MAXSTEP_DT] = p.max_step > 0.0 ? p.max_step : 1e-12;
+        v[FI_MAXSTEPS] = (double)p.max_steps;
+        v[FI_KIND] = (double)p.device_kind;
+        v[FI_THERMAL] = (double)p.thermal;
+        v[FI_VALID] = (double)p.solver_valid;
+        const bool axis_z = v[FI_EX] == 0.0 && v[FI_EY] == 0.0 && v[FI_EZ] == 1.0 && p.applied_field[0] == 0.0 &&
+                            p.applied_field[1] == 0.0 && p.applied_field[2] == 0.0;
+        v[FI_AXISZ] = axis_z ? 1.0 : 0.0;
+    }
+    return STG_OK;
+}
+
+extern "C" int stg_stt_all_axis_z(const StgSttFolded* folded_host, int32_t n_sets) {
+    if (!folded_host || n_sets <= 0) return 0;
+    for (int i = 0; i < n_sets; ++i)
+        if (folded_host[i].v[FI_AXISZ] == 0.0) return 0;
+    return 1;
+}
+
+static int check_step_args(const StgSttStepArgs& a) {
+    if (a.n_envs < 0 || a.n_sets <= 0) return STG_E_SIZE;
+    const StgSttState& st = a.state;
+    if (!a.d_table || !st.m || !st.target || !st.total_energy || !st.last_action || !st.step_count || !st.episode ||
+        !a.d_action || !a.out.obs || !a.out.reward || !a.out.terminated || !a.out.truncated)
+        return STG_E_NULL;
+    if ((a.flags & STG_F_THERMAL_PHILOX) && (a.flags & STG_F_THERMAL_INJECT)) return STG_E_ENUM;
+    if ((a.flags & STG_F_THERMAL_INJECT) && (!a.d_noise || a.noise_stride <= 0)) return STG_E_NULL;
+    if ((a.flags & STG_F_SORTED) && !a.d_perm) return STG_E_NULL;
+    if ((a.flags & STG_F_AUTORESET) && (!a.d_target_table || a.n_targets <= 0)) return STG_E_NULL;
+    if (((uintptr_t)a.d_action & 7u) || ((uintptr_t)a.out.obs & 15u) ||
+        (a.out.final_obs && ((uintptr_t)a.out.final_obs & 15u)))
+        return STG_E_ALIGN;
+    return STG_OK;
+}
+
+template <typename R>
+static int stt_step_impl(const StgSttStepArgs* args, void* stream) {
+    if (!args) return STG_E_NULL;
+    int rc = check_step_args(*args);
+    if (rc != STG_OK) return rc;
+    if (args->n_envs == 0) return STG_OK;
+    return (int)launch_step<R>(*args, (args->flags & STG_F_AXIS_Z) != 0, (cudaStream_t)stream);
+}
+extern "C" int stg_stt_step_f32(const StgSttStepArgs* args, void* stream) { return stt_step_impl<float>(args, stream); }
+extern "C" int stg_stt_step_f64(const StgSttStepArgs* args, void* stream) { return stt_step_impl<double>(args, stream); }
+
+extern "C" int stg_stt_reset(const StgSttResetArgs* args, void* stream) {
+    if (!args) return STG_E_NULL;
+    const StgSttResetArgs& a = *args;
+    if (a.n_envs < 0 || a.n_sets <= 0) return STG_E_SIZE;
+    const StgSttState& st = a.state;
+    if (!a.d_table || !st.m || !st.target || !st.total_energy || !st.last_action || !st.step_count || !st.episode)
+        return STG_E_NULL;
+    if (!a.d_target0 && (!a.d_target_table || a.n_targets <= 0)) return STG_E_NULL;
+    if (a.d_obs && ((uintptr_t)a.d_obs & 15u)) return STG_E_ALIGN;
+    if (a.n_envs == 0) return STG_OK;
+    const unsigned grid = (unsigned)((a.n_envs + 127) / 128);
+    stt_env_reset_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int stg_stt_sort_by_substeps(const StgSttFolded* d_table, int32_t n_sets, const int32_t* d_param_index,
+                                        const float* d_action, int32_t* d_perm, int32_t* d_work, int64_t n_envs,
+                                        void* stream) {
+    if (!d_table || !d_action || !d_perm || !d_work) return STG_E_NULL;
+    if (n_envs < 0 || n_sets <= 0 || n_envs > 2147483647LL) return STG_E_SIZE;
+    if (n_envs == 0) return STG_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t err = cudaMemsetAsync(d_work, 0, sizeof(int32_t) * STG_SORT_BINS, s);
+    if (err != cudaSuccess) return (int)err;
+    const unsigned grid = (unsigned)((n_envs + 255) / 256);
+    sort_hist_kernel<<<grid, 256, 0, s>>>(d_table, d_param_index, d_action, d_work, n_envs);
+    sort_scan_kernel<<<1, 1024, 0, s>>>(d_work);
+    sort_scatter_kernel<<<grid, 256, 0, s>>>(d_table, d_param_index, d_action, d_work, d_perm, n_envs);
+    return (int)cudaGetLastError();
+}
+
+template <typename R>
+static int stt_solve_impl(const StgSttSolveArgs* args, void* stream) {
+    if (!args) return STG_E_NULL;
+    const StgSttSolveArgs& a = *args;
+    if (a.n_envs < 0 || a.n_sets <= 0) return STG_E_SIZE;
+    if (!a.d_table || !a.d_m0 || !a.d_pulse || !a.d_m_out) return STG_E_NULL;
+    if ((a.flags & STG_F_THERMAL_PHILOX) && (a.flags & STG_F_THERMAL_INJECT)) return STG_E_ENUM;
+    if ((a.flags & STG_F_THERMAL_INJECT) && (!a.d_noise || a.noise_stride <= 0)) return STG_E_NULL;
+    if (a.d_traj && a.traj_stride <= 0) return STG_E_SIZE;
+    if (a.n_envs == 0) return STG_OK;
+    return (int)launch_solve<R>(a, a.flags, (a.flags & STG_F_AXIS_Z) != 0, (cudaStream_t)stream);
+}
+extern "C" int stg_stt_solve_f32(const StgSttSolveArgs* args, void* stream) { return stt_solve_impl<float>(args, stream); }
+extern "C" int stg_stt_solve_f64(const StgSttSolveArgs* args, void* stream) { return stt_solve_impl<double>(args, stream); }

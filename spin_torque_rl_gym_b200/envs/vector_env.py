@@ -1,0 +1,378 @@
+"""SpinTorqueVectorEnv — N SpinTorque-v0 environments stepped by ONE kernel launch on a B200.
+
+Host-side mirror of the reference's SpinTorqueEnv (spin_torque_gym/envs/spin_torque_env.py:26-554) with the same
+constructor kwargs, spaces, reset options and step outputs, batched over `num_envs` and backed by the C-ABI in
+include/stg.h (libstg.so). State, actions, observations, rewards and flags are torch tensors resident in HBM; numpy in /
+numpy out is supported for drop-in use (pinned staging buffers).
+
+There is no CPU fallback: constructing the env without CUDA or without libstg.so raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, List, Optional, Sequence, Union
+
+import numpy as np
+
+from .. import _lib, params as _params
+from ..spaces import Box, batch_box
+
+
+class SpinTorqueVectorEnv:
+    """Batched drop-in for `gym.make('SpinTorque-v0', ...)` (gymnasium.vector.VectorEnv-style API).
+
+    Reference kwargs (envs/spin_torque_env.py:36-53) are accepted unchanged. Extra kwargs:
+      num_envs, device ('cuda:k'), dtype (torch.float32 | torch.float64: arithmetic of the integrator stages),
+      integrator ('rk4' | 'euler'), rng_seed (Philox key), env_offset (global id of env 0: multi-GPU sharding),
+      autoreset (same-step reset of finished episodes, SB3 VecEnv convention), param_index (per-env index into a list of
+      device_params dicts = device mix), sort_by_substeps ('auto' | True | False).
+    """
+
+    metadata = {"render_modes": [], "autoreset_mode": "same_step"}
+
+    def __init__(
+        self,
+        num_envs: int = 1,
+        device_type: Union[str, Sequence[str]] = "stt_mram",
+        device_params: Optional[Union[Dict[str, Any], Sequence[Dict[str, Any]]]] = None,
+        target_states: Optional[List[np.ndarray]] = None,
+        max_steps: int = 100,
+        max_current: float = 2e6,
+        max_duration: float = 5e-9,
+        temperature: float = 300.0,
+        include_thermal_fluctuations: bool = True,
+        reward_components: Optional[Dict[str, Dict]] = None,
+        action_mode: str = "continuous",
+        observation_mode: str = "vector",
+        success_threshold: float = 0.9,
+        energy_penalty_weight: float = 0.1,
+        render_mode: Optional[str] = None,
+        seed: Optional[int] = None,
+        *,
+        device: Union[str, Any] = "cuda",
+        dtype: Any = None,
+        integrator: str = "rk4",
+        rng_seed: Optional[int] = None,
+        env_offset: int = 0,
+        autoreset: bool = True,
+        param_index: Optional[Any] = None,
+        sort_by_substeps: Union[str, bool] = "auto",
+        collect_stats: bool = True,
+    ):
+        torch = _lib.require_cuda()
+        self._torch = torch
+        self._lib = _lib.load()
+        if action_mode != "continuous":
+            # the reference's discrete mode raises inside step() and returns the error tuple; not supported
+            raise ValueError("only action_mode='continuous' is implemented (the reference's 'discrete' mode is non-functional)")
+        if observation_mode != "vector":
+            raise ValueError("only observation_mode='vector' is implemented (the reference's 'dict' mode is non-functional)")
+        if reward_components is not None:
+            raise ValueError("custom reward_components are Python callables and cannot run in the kernel; "
+                             "the default CompositeReward (envs/spin_torque_env.py:184-207) is fused")
+        if integrator not in ("rk4", "euler"):
+            raise ValueError(f"unknown integrator {integrator!r}")
+        self.num_envs = int(num_envs)
+        if self.num_envs <= 0:
+            raise ValueError("num_envs must be positive")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.StgError("SpinTorqueVectorEnv requires a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dtype = torch.float32 if dtype is None else dtype
+        if self.dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be torch.float32 or torch.float64")
+        self.integrator = integrator
+        self.max_steps = int(max_steps)
+        self.max_current = float(max_current)
+        self.max_duration = float(max_duration)
+        self.temperature = float(temperature)
+        self.include_thermal = bool(include_thermal_fluctuations)
+        self.action_mode = action_mode
+        self.observation_mode = observation_mode
+        self.success_threshold = float(success_threshold)
+        self.energy_penalty_weight = float(energy_penalty_weight)
+        self.render_mode = render_mode
+        self.autoreset = bool(autoreset)
+        self.env_offset = int(env_offset)
+        self.collect_stats = bool(collect_stats)
+        if rng_seed is None:
+            rng_seed = 0 if seed is None else int(seed)
+        self.rng_seed = int(rng_seed) & 0xFFFFFFFFFFFFFFFF
+
+        # ---- device parameter sets ---------------------------------------------------------------------------------
+        types = [device_type] if isinstance(device_type, str) else list(device_type)
+        if device_params is None or isinstance(device_params, dict):
+            plist = [device_params] * len(types)
+        else:
+            plist = list(device_params)
+            if len(types) == 1:
+                types = types * len(plist)
+        if len(types) != len(plist):
+            raise ValueError("device_type and device_params lists must have the same length")
+        self.device_types = types
+        self.device_type = types[0]
+        self.device_params_list = []
+        structs = []
+        for t, p in zip(types, plist):
+            if p is None:
+                p = _params.env_default_device_params(t)          # envs/spin_torque_env.py:112-114
+            _params.check_device_constructible(t, p)
+            self.device_params_list.append(dict(p))
+            structs.append(_params.make_param_struct(
+                t, p, max_steps=self.max_steps, max_current=self.max_current, max_duration=self.max_duration,
+                temperature=self.temperature, thermal=self.include_thermal, success_threshold=self.success_threshold,
+                energy_penalty_weight=self.energy_penalty_weight))
+        self.device_params = self.device_params_list[0]
+        self._folded_host = _params.fold(structs)
+        self._axis_z = _params.all_axis_z(self._folded_host)
+        self._n_sets = len(structs)
+
+        N = self.num_envs
+        dev = self.device
+        with torch.cuda.device(dev):
+            self._table = torch.from_numpy(self._folded_host).to(dev)
+            if param_index is not None:
+                pi = torch.as_tensor(param_index, dtype=torch.int32).to(dev).contiguous()
+                if pi.shape != (N,):
+                    raise ValueError("param_index must have shape (num_envs,)")
+                if int(pi.min()) < 0 or int(pi.max()) >= self._n_sets:
+                    raise ValueError("param_index out of range")
+                self._param_index = pi
+            else:
+                if self._n_sets != 1:
+                    raise ValueError("several device parameter sets need a param_index")
+                self._param_index = None
+
+            # ---- target states (envs/spin_torque_env.py:117-120) ----------------------------------------------------
+            if target_states is None:
+                tt = np.array([[0.0, 0.0, 1.0], [0.0, 0.0, -1.0]])
+            else:
+                tt = np.array([np.asarray(t, dtype=float) / np.linalg.norm(np.asarray(t, dtype=float))
+                               for t in target_states])
+            self.target_states = [t.copy() for t in tt]
+            self._target_table = torch.from_numpy(np.ascontiguousarray(tt)).to(dev)
+
+            # ---- state planes (FP64 SoA) and step outputs -----------------------------------------------------------
+            f64, i32 = torch.float64, torch.int32
+            self._m = torch.zeros(3, N, dtype=f64, device=dev)
+            self._m[2] = 1.0
+            self._target = torch.zeros(3, N, dtype=f64, device=dev)
+            self._target[2] = 1.0
+            self._total_energy = torch.zeros(N, dtype=f64, device=dev)
+            self._last_action = torch.zeros(2, N, dtype=f64, device=dev)
+            self._step_count = torch.zeros(N, dtype=i32, device=dev)
+            self._episode = torch.zeros(N, dtype=i32, device=dev)
+            self._obs = torch.zeros(N, _lib.OBS_DIM, dtype=torch.float32, device=dev)
+            self._final_obs = torch.zeros(N, _lib.OBS_DIM, dtype=torch.float32, device=dev)
+            self._reward = torch.zeros(N, dtype=f64, device=dev)
+            self._terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
+            self._truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
+            self._step_energy = torch.zeros(N, dtype=f64, device=dev)
+            self._n_sub = torch.zeros(N, dtype=i32, device=dev)
+            self._status = torch.zeros(N, dtype=i32, device=dev)
+            self._stats = torch.zeros(_lib.NSTATS, dtype=f64, device=dev)
+            self._action_dev = torch.zeros(N, 2, dtype=torch.float32, device=dev)
+            self._perm = torch.zeros(N, dtype=i32, device=dev)
+            self._sort_work = torch.zeros(_lib.SORT_WORK_INTS, dtype=i32, device=dev)
+            self._action_pinned = torch.zeros(N, 2, dtype=torch.float32).pin_memory()
+
+        self._sort_mode = sort_by_substeps
+        self._needs_reset = True
+        self.gpu_launches = 0     # kernels of libstg launched so far (bench.py reports it)
+
+        # ---- spaces (envs/spin_torque_env.py:209-248) ------------------------------------------------------------------
+        self.single_action_space = Box(low=np.array([-self.max_current, 0.0]),
+                                       high=np.array([self.max_current, self.max_duration]), dtype=np.float32)
+        self.single_observation_space = Box(low=-np.inf, high=np.inf, shape=(_lib.OBS_DIM,), dtype=np.float32)
+        self.action_space = batch_box(self.single_action_space, N)
+        self.observation_space = batch_box(self.single_observation_space, N)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _state_struct(self) -> _lib.StgSttState:
+        s = _lib.StgSttState()
+        s.m = self._m.data_ptr()
+        s.target = self._target.data_ptr()
+        s.total_energy = self._total_energy.data_ptr()
+        s.last_action = self._last_action.data_ptr()
+        s.step_count = self._step_count.data_ptr()
+        s.episode = self._episode.data_ptr()
+        return s
+
+    def _stream(self) -> int:
+        return self._torch.cuda.current_stream(self.device).cuda_stream
+
+    def _as_device_f64(self, x, shape):
+        torch = self._torch
+        t = torch.as_tensor(x, dtype=torch.float64) if not isinstance(x, torch.Tensor) else x.to(torch.float64)
+        t = t.to(self.device)
+        if t.dim() == len(shape) - 1:
+            t = t.unsqueeze(0).expand(*shape)
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {shape} (or one row), got {tuple(t.shape)}")
+        return t.contiguous()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def reset(self, *, seed: Optional[int] = None, options: Optional[Dict[str, Any]] = None, mask=None):
+        """Reset all envs (or the envs selected by `mask`). options: 'initial_state', 'target_state' ([3] or [N,3]),
+        'temperature' (accepted and ignored like the reference, which only forwards it to an unused thermal model:
+        envs/spin_torque_env.py:301-303)."""
+        torch = self._torch
+        options = options or {}
+        if seed is not None:
+            self.rng_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            self._episode.zero_()
+        N = self.num_envs
+        a = _lib.StgSttResetArgs()
+        a.d_table = self._table.data_ptr()
+        a.d_param_index = _lib.ptr(self._param_index)
+        a.state = self._state_struct()
+        keep = []
+        if mask is not None:
+            mk = torch.as_tensor(mask).to(self.device).to(torch.uint8).contiguous()
+            keep.append(mk)
+            a.d_mask = mk.data_ptr()
+        if "initial_state" in options:
+            m0 = self._as_device_f64(options["initial_state"], (N, 3))
+            keep.append(m0)
+            a.d_m0 = m0.data_ptr()
+        if "target_state" in options:
+            t0 = self._as_device_f64(options["target_state"], (N, 3))
+            keep.append(t0)
+            a.d_target0 = t0.data_ptr()
+        a.d_target_table = self._target_table.data_ptr()
+        a.n_targets = self._target_table.shape[0]
+        a.d_obs = self._obs.data_ptr()
+        a.seed = self.rng_seed
+        a.env_offset = self.env_offset
+        a.n_envs = N
+        a.n_sets = self._n_sets
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.stg_stt_reset(C.byref(a), self._stream()), "stg_stt_reset")
+        self.gpu_launches += 1
+        self._needs_reset = False
+        self._keep = keep
+        return self._obs, {}
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _stage_actions(self, actions):
+        torch = self._torch
+        N = self.num_envs
+        if isinstance(actions, torch.Tensor):
+            if actions.device == self.device and actions.dtype == torch.float32 and actions.is_contiguous() \
+                    and tuple(actions.shape) == (N, 2):
+                return actions
+            act = actions.to(device=self.device, dtype=torch.float32).reshape(N, 2)
+            self._action_dev.copy_(act)
+            return self._action_dev
+        arr = np.asarray(actions, dtype=np.float32).reshape(N, 2)
+        self._action_pinned.numpy()[...] = arr
+        self._action_dev.copy_(self._action_pinned, non_blocking=True)
+        return self._action_dev
+
+    def step(self, actions, noise=None):
+        """One env step for all envs. `actions`: [N,2] (J [A/m^2], T [s]) torch (device or host) or numpy.
+        `noise`: optional [N, n_max, S, 3] float64 N(0,1) tensor (S=4 rk4 / 1 euler) replacing the in-kernel Philox stream.
+        Returns (obs [N,12] f32, reward [N] f64, terminated [N] bool, truncated [N] bool, info dict of tensors)."""
+        torch = self._torch
+        if self._needs_reset:
+            raise RuntimeError("Environment must be reset before calling step")
+        N = self.num_envs
+        act = self._stage_actions(actions)
+        flags = 0
+        if self.integrator == "euler":
+            flags |= _lib.F_EULER
+        if self._axis_z:
+            flags |= _lib.F_AXIS_Z
+        if self.autoreset:
+            flags |= _lib.F_AUTORESET
+        a = _lib.StgSttStepArgs()
+        if noise is not None:
+            nz = torch.as_tensor(noise, dtype=torch.float64).to(self.device).contiguous()
+            S = 1 if self.integrator == "euler" else 4
+            if nz.dim() != 4 or nz.shape[0] != N or nz.shape[2] != S or nz.shape[3] != 3:
+                raise ValueError(f"noise must have shape [N, n_max, {S}, 3]")
+            self._noise_keep = nz
+            flags |= _lib.F_THERMAL_INJECT
+            a.d_noise = nz.data_ptr()
+            a.noise_stride = nz.shape[1]
+        elif self.include_thermal and self.temperature > 0:
+            flags |= _lib.F_THERMAL_PHILOX
+        stream = self._stream()
+        with torch.cuda.device(self.device):
+            do_sort = self._sort_mode is True
+            if do_sort:
+                _lib.check(self._lib.stg_stt_sort_by_substeps(
+                    self._table.data_ptr(), self._n_sets, _lib.ptr(self._param_index), act.data_ptr(),
+                    self._perm.data_ptr(), self._sort_work.data_ptr(), N, stream), "stg_stt_sort_by_substeps")
+                self.gpu_launches += 3
+                flags |= _lib.F_SORTED
+                a.d_perm = self._perm.data_ptr()
+            a.d_table = self._table.data_ptr()
+            a.d_param_index = _lib.ptr(self._param_index)
+            a.state = self._state_struct()
+            a.d_action = act.data_ptr()
+            o = a.out
+            o.obs = self._obs.data_ptr()
+            o.reward = self._reward.data_ptr()
+            o.terminated = self._terminated.data_ptr()
+            o.truncated = self._truncated.data_ptr()
+            o.step_energy = self._step_energy.data_ptr()
+            o.n_sub = self._n_sub.data_ptr()
+            o.status = self._status.data_ptr()
+            o.final_obs = self._final_obs.data_ptr() if self.autoreset else None
+            o.stats = self._stats.data_ptr() if self.collect_stats else None
+            a.d_target_table = self._target_table.data_ptr()
+            a.n_targets = self._target_table.shape[0]
+            a.seed = self.rng_seed
+            a.env_offset = self.env_offset
+            a.n_envs = N
+            a.n_sets = self._n_sets
+            a.flags = flags
+            fn = self._lib.stg_stt_step_f32 if self.dtype == torch.float32 else self._lib.stg_stt_step_f64
+            _lib.check(fn(C.byref(a), stream), "stg_stt_step")
+        self.gpu_launches += 1
+        info = {
+            "step_energy": self._step_energy, "n_sub": self._n_sub, "status": self._status,
+            "total_energy": self._total_energy, "step_count": self._step_count,
+        }
+        if self.autoreset:
+            info["final_observation"] = self._final_obs
+        return self._obs, self._reward, self._terminated.bool(), self._truncated.bool(), info
+
+    # ------------------------------------------------------------------------------------------------------------------
+    @property
+    def magnetization(self):
+        """[N,3] float64 view-copy of the current magnetisation."""
+        return self._m.t().contiguous()
+
+    @property
+    def target(self):
+        return self._target.t().contiguous()
+
+    def episode_stats(self, reset: bool = False) -> Dict[str, float]:
+        """Accumulated episode statistics of this rank (dict of python floats; one D2H of 64 bytes)."""
+        vals = self._stats.cpu().tolist()
+        if reset:
+            self._stats.zero_()
+        return dict(zip(_lib.STAT_NAMES, vals))
+
+    def stats_tensor(self):
+        return self._stats
+
+    def state_dict(self) -> Dict[str, Any]:
+        return {"m": self._m.clone(), "target": self._target.clone(), "total_energy": self._total_energy.clone(),
+                "last_action": self._last_action.clone(), "step_count": self._step_count.clone(),
+                "episode": self._episode.clone(), "rng_seed": self.rng_seed, "stats": self._stats.clone()}
+
+    def load_state_dict(self, sd: Dict[str, Any]) -> None:
+        for k, t in (("m", self._m), ("target", self._target), ("total_energy", self._total_energy),
+                     ("last_action", self._last_action), ("step_count", self._step_count),
+                     ("episode", self._episode), ("stats", self._stats)):
+            t.copy_(sd[k])
+        self.rng_seed = int(sd["rng_seed"])
+        self._needs_reset = False
+
+    def close(self):
+        pass

@@ -1,0 +1,92 @@
+// hostsim.cpp — HOST build of the per-env bodies in spin_torque_rl_gym_b200/csrc/stt_env_core.cuh.
+//
+// TEST INFRASTRUCTURE ONLY (lives under tests/, never imported by the product package). It lets the CPU test-suite run the
+// exact arithmetic the CUDA kernels execute (same templates, same folded constants) against the NumPy oracle and the golden
+// vectors in a container without a GPU. It is not a fallback: the product path always calls libstg.so's CUDA kernels.
+#include <stdint.h>
+#include <xmmintrin.h>
+
+#include "../../include/stg.h"
+#include "../../spin_torque_rl_gym_b200/csrc/llgs_core.cuh"
+#include "../../spin_torque_rl_gym_b200/csrc/stt_env_core.cuh"
+
+using namespace stg;
+
+template <typename R, bool AXIS_Z, int NOISE>
+static void step_all(const StgSttStepArgs& a) {
+    for (int64_t s = 0; s < a.n_envs; ++s) {
+        const int64_t e = (a.flags & STG_F_SORTED) ? a.d_perm[s] : s;
+        EnvStepResult r;
+        if (a.flags & STG_F_EULER)
+            env_step_body<R, AXIS_Z, NOISE, true>(a, e, r);
+        else
+            env_step_body<R, AXIS_Z, NOISE, false>(a, e, r);
+        for (int q = 0; q < kObs; ++q) a.out.obs[e * kObs + q] = r.obs[q];
+        if ((a.flags & STG_F_AUTORESET) && a.out.final_obs)
+            for (int q = 0; q < kObs; ++q) a.out.final_obs[e * kObs + q] = r.did_reset ? r.final_obs[q] : 0.0f;
+    }
+}
+template <typename R, bool AXIS_Z>
+static void step_noise(const StgSttStepArgs& a) {
+    if (a.flags & STG_F_THERMAL_INJECT) step_all<R, AXIS_Z, 2>(a);
+    else if (a.flags & STG_F_THERMAL_PHILOX) step_all<R, AXIS_Z, 1>(a);
+    else step_all<R, AXIS_Z, 0>(a);
+}
+
+// x86 handles denormal operands in microcode (~100x slower); the GPU does not care. Flush them on the host for the f32 runs:
+// they are < 1e-38, far below every tolerance.
+struct FtzScope {
+    unsigned old;
+    explicit FtzScope(bool on) : old(_mm_getcsr()) { if (on) _mm_setcsr(old | 0x8040u); }
+    ~FtzScope() { _mm_setcsr(old); }
+};
+
+extern "C" int hostsim_stt_step(const StgSttStepArgs* a, int f64) {
+    FtzScope ftz(!f64);
+    const bool z = (a->flags & STG_F_AXIS_Z) != 0;
+    if (f64) { if (z) step_noise<double, true>(*a); else step_noise<double, false>(*a); }
+    else     { if (z) step_noise<float, true>(*a);  else step_noise<float, false>(*a); }
+    return 0;
+}
+
+extern "C" int hostsim_stt_reset(const StgSttResetArgs* a) {
+    for (int64_t e = 0; e < a->n_envs; ++e)
+        if (!a->d_mask || a->d_mask[e]) env_reset_body(*a, e);
+    return 0;
+}
+
+template <typename R, bool AXIS_Z, int NOISE>
+static void solve_all(const StgSttSolveArgs& a) {
+    for (int64_t e = 0; e < a.n_envs; ++e) {
+        if (a.flags & STG_F_EULER) solve_body<R, AXIS_Z, NOISE, true>(a, e);
+        else solve_body<R, AXIS_Z, NOISE, false>(a, e);
+    }
+}
+template <typename R, bool AXIS_Z>
+static void solve_noise(const StgSttSolveArgs& a) {
+    if (a.flags & STG_F_THERMAL_INJECT) solve_all<R, AXIS_Z, 2>(a);
+    else if (a.flags & STG_F_THERMAL_PHILOX) solve_all<R, AXIS_Z, 1>(a);
+    else solve_all<R, AXIS_Z, 0>(a);
+}
+extern "C" int hostsim_stt_solve(const StgSttSolveArgs* a, int f64) {
+    FtzScope ftz(!f64);
+    const bool z = (a->flags & STG_F_AXIS_Z) != 0;
+    if (f64) { if (z) solve_noise<double, true>(*a); else solve_noise<double, false>(*a); }
+    else     { if (z) solve_noise<float, true>(*a);  else solve_noise<float, false>(*a); }
+    return 0;
+}
+
+extern "C" void hostsim_sort_bins(const StgSttFolded* table, const int32_t* pidx, const float* action, int32_t* bins,
+                                  int64_t n) {
+    for (int64_t e = 0; e < n; ++e) bins[e] = action_bin(table, pidx, action, e);
+}
+
+// Philox known-answer access for tests
+extern "C" void hostsim_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out) {
+    Philox ph{k0, k1};
+    ph(c0, c1, c2, c3, out);
+}
+extern "C" void hostsim_normals12(uint64_t seed, uint64_t gid, uint32_t step, uint32_t sub, float* out) {
+    Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    philox_normals12(ph, gid, step, sub, out);
+}

@@ -1,0 +1,197 @@
+"""CPU-side check of the exact arithmetic the CUDA kernels run: the per-env bodies of csrc/stt_env_core.cuh compiled for the
+host (tests/hostsim) against the golden vectors of the live reference and against the C oracle.
+
+Tolerances are the north-star ones: 1e-6 relative (FP64 stage arithmetic), 1e-4 (FP32 stage arithmetic, FP64 state).
+The GPU tests (-m gpu) repeat the same comparisons through libstg.so's CUDA kernels."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import GOLDEN, load_case, noise_for_step, rel_err, stt_params_for
+from tests.hostsim.harness import HostSimEnv
+from oracle.c_oracle import COracleEnv
+
+TOL = {True: 1e-6, False: 1e-4}
+
+
+def _env(c, f64, **kw):
+    return HostSimEnv(1, device_params=stt_params_for(c), max_current=float(c["max_current"]),
+                      include_thermal_fluctuations=bool(c["thermal"]), integrator=str(c["method"]),
+                      max_steps=int(c.get("max_steps", 100)), f64=f64, **kw)
+
+
+@pytest.mark.parametrize("f64", [True, False])
+@pytest.mark.parametrize("name", ["bigvol_det", "tilted_rk4", "thermal_injected"])
+def test_free_running_episode(name, f64):
+    c = load_case("stt_env.npz", name)
+    env = _env(c, f64)
+    obs = env.reset(c["m0"], c["target"])
+    assert np.array_equal(obs[0], c["obs"][0])
+    for k, a in enumerate(c["actions"]):
+        noise = noise_for_step(c["seeds"][k], a, float(c["max_current"]))[None] if "seeds" in c else None
+        o, r, te, tr = env.step(a[None], noise)
+        assert np.abs(env.m[:, 0] - c["m"][k + 1]).max() < TOL[f64], k
+        assert np.abs(o[0] - c["obs"][k + 1]).max() < TOL[f64]
+        assert abs(r[0] - c["reward"][k]) < TOL[f64] * max(1.0, abs(c["reward"][k]))
+        e_ref = c["energy"][k]
+        assert abs(env.step_energy[0] - e_ref) <= TOL[f64] * e_ref
+        assert te[0] == c["terminated"][k] and tr[0] == c["truncated"][k]
+
+
+@pytest.mark.parametrize("f64,general", [(True, False), (True, True), (False, False), (False, True)])
+def test_c1_teacher_forced(f64, general):
+    """Config C1: every step from the golden's own pre-step state (see test_oracle_golden for why)."""
+    c = load_case("stt_env.npz", "c1_det")
+    env = _env(c, f64, force_general=general)
+    env.reset(c["m0"], c["target"])
+    for k, a in enumerate(c["actions"]):
+        t_in = np.hypot(*c["m"][k][:2])
+        if not f64 and general and t_in < 1e-30:
+            continue   # only the axis-z FP32 path block-scales the transverse pair (llgs_core.cuh: ScaledState)
+        env.m[:, 0] = c["m"][k]
+        env.total_energy[0] = c["total_energy"][k - 1] if k else 0.0
+        env.step_count[0] = k
+        o, r, te, tr = env.step(a[None])
+        if t_in > 1e-200 and (f64 or not general):
+            # relative agreement even of the exponentially small transverse components (FP32: 2e-3 of 1e-257)
+            assert rel_err(env.m[:, 0], c["m"][k + 1]) < (1e-6 if f64 else 5e-3), k
+        assert np.abs(env.m[:, 0] - c["m"][k + 1]).max() < TOL[f64], k
+        assert abs(r[0] - c["reward"][k]) < TOL[f64] * max(1.0, abs(c["reward"][k]))
+        assert te[0] == c["terminated"][k] and tr[0] == c["truncated"][k]
+
+
+@pytest.mark.parametrize("f64", [True, False])
+def test_c1_free_running_prefix(f64):
+    """C1 free-running for as long as the golden itself is well-conditioned (transverse above the denormal range)."""
+    c = load_case("stt_env.npz", "c1_det")
+    env = _env(c, f64)
+    env.reset(c["m0"], c["target"])
+    for k, a in enumerate(c["actions"]):
+        o, r, te, tr = env.step(a[None])
+        if np.hypot(*c["m"][k + 1][:2]) < 1e-300:
+            break
+        assert rel_err(env.m[:, 0], c["m"][k + 1]) < (1e-6 if f64 else 5e-2), k
+        assert np.abs(env.m[:, 0] - c["m"][k + 1]).max() < TOL[f64]
+        assert abs(r[0] - c["reward"][k]) < TOL[f64] * max(1.0, abs(c["reward"][k]))
+        assert te[0] == c["terminated"][k] and tr[0] == c["truncated"][k]
+    assert k >= 8
+
+
+@pytest.mark.parametrize("f64", [True, False])
+def test_multi_episode_golden(f64):
+    g = np.load(os.path.join(GOLDEN, "stt_multi.npz"))
+    n = len(g["actions"])
+    env = HostSimEnv(n, max_current=float(g["max_current"]), include_thermal_fluctuations=False, f64=f64)
+    obs0 = env.reset(g["m0"], g["target"])
+    assert np.array_equal(obs0, g["obs0"])
+    o, r, te, tr = env.step(g["actions"])
+    assert np.abs(env.m.T - g["m"]).max() < TOL[f64]
+    assert np.abs(o - g["obs"]).max() < TOL[f64]
+    assert np.allclose(r, g["reward"], rtol=TOL[f64], atol=TOL[f64])
+    assert np.array_equal(te, g["terminated"]) and np.array_equal(tr, g["truncated"])
+
+
+def test_euler_teacher_forced_f32():
+    """The explicit-Euler map with 0.35 rad/substep amplifies rounding differences over an episode (FP64: 1e-11 after 16
+    steps); in FP32 the comparison is therefore per step from the golden's pre-step state."""
+    c = load_case("stt_env.npz", "tilted_euler")
+    env = _env(c, False)
+    env.reset(c["m0"], c["target"])
+    worst = 0.0
+    for k, a in enumerate(c["actions"]):
+        env.m[:, 0] = c["m"][k]
+        env.step(a[None])
+        worst = max(worst, np.abs(env.m[:, 0] - c["m"][k + 1]).max())
+    assert worst < 5e-3
+    env64 = _env(c, True)
+    env64.reset(c["m0"], c["target"])
+    for k, a in enumerate(c["actions"]):
+        env64.step(a[None])
+        assert np.abs(env64.m[:, 0] - c["m"][k + 1]).max() < 1e-6
+
+
+@pytest.mark.parametrize("f64", [True, False])
+def test_random_batch_vs_c_oracle(f64):
+    """256 envs, random states/targets/actions incl. edge actions, 3 steps, against the C oracle."""
+    rng = np.random.default_rng(11)
+    n, jm = 256, 1.1e-6
+    m0 = rng.normal(size=(n, 3))
+    tgt = np.where(rng.integers(2, size=(n, 1)) == 0, 1.0, -1.0) * np.array([[0, 0, 1.0]])
+    h = HostSimEnv(n, max_current=jm, include_thermal_fluctuations=False, f64=f64)
+    o = COracleEnv(n, max_current=jm, include_thermal=False, nthreads=4)
+    assert np.array_equal(h.reset(m0, tgt), o.reset(m0, tgt))
+    for s in range(3):
+        act = np.stack([rng.uniform(-jm, jm, n), rng.uniform(0, 1.5e-9, n)], 1).astype(np.float32)
+        act[0] = [np.nan, 1e-9]; act[1] = [jm, np.inf]; act[2] = [0.0, 5e-10]; act[3] = [-1.0, 1e-13]
+        act[4] = [1e-13, 1e-9]
+        ho, hr, hte, htr = h.step(act)
+        oo, orr, ote, otr = o.step(act)
+        assert np.array_equal(h.n_sub, o.n_sub)
+        assert np.abs(h.m.T - o.m).max() < TOL[f64]
+        assert np.abs(ho - oo).max() < TOL[f64]
+        assert np.allclose(hr, orr, rtol=TOL[f64], atol=TOL[f64])
+        assert np.array_equal(hte, ote) and np.array_equal(htr, otr)
+        assert np.allclose(h.step_energy, o.step_energy, rtol=TOL[f64], atol=0)
+
+
+def test_substep_plan_matches_numpy_quirks():
+    """float32 durations floor to 999/4999/... substeps and tiny durations give 99 or 100."""
+    from oracle.stt_oracle import substep_plan
+    durs = np.array([1e-9, 5e-9, 2e-9, 5e-10, 1e-10, 7.3e-11, 1e-12, 3.3e-12, 9.99e-11], dtype=np.float32)
+    h = HostSimEnv(len(durs), include_thermal_fluctuations=False, f64=True)
+    h.reset(np.array([0.3, 0.2, 0.9]), [0, 0, 1.0])
+    h.step(np.stack([np.zeros(len(durs), np.float32), durs], 1))
+    assert list(h.n_sub) == [substep_plan(float(d))[0] for d in durs]
+    assert h.n_sub[0] == 999 and h.n_sub[1] == 4999
+
+
+def test_autoreset_and_truncation_semantics():
+    h = HostSimEnv(8, max_steps=3, include_thermal_fluctuations=False, f64=True, autoreset=True, rng_seed=5)
+    h.reset()
+    m_start = h.m.copy()
+    assert np.allclose(np.linalg.norm(m_start, axis=0), 1.0)
+    act = np.tile(np.array([[0.0, 1e-11]], np.float32), (8, 1))
+    ends = 0
+    for s in range(3):
+        o, r, te, tr = h.step(act)
+        done = te | tr
+        ends += done.sum()
+        # envs that ended were reset in the same call: fresh counters, obs of the new episode, final_obs kept
+        assert np.all(h.step_count[done] == 0) and np.all(h.total_energy[done] == 0)
+        assert np.all(o[done, 8] == 1.0)
+        assert np.all(h.final_obs[~done] == 0)
+        if done.any():
+            assert np.all(np.abs(h.final_obs[done][:, :3]).sum(1) > 0)
+    assert np.all(h.episode >= 1 + 1)   # reset() + at least one auto-reset within 3 steps (max_steps=3)
+    assert ends >= 8
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors from the Random123 distribution (kat_vectors)."""
+    import ctypes as C
+    from tests.hostsim.harness import lib
+    out = (C.c_uint32 * 4)()
+    lib().hostsim_philox(0, 0, 0, 0, 0, 0, out)
+    assert list(out) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    lib().hostsim_philox(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, out)
+    assert list(out) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    lib().hostsim_philox(0xa4093822, 0x299f31d0, 0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, out)
+    assert list(out) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_normals_moments():
+    import ctypes as C
+    from tests.hostsim.harness import lib
+    buf = (C.c_float * 12)()
+    xs = []
+    for g in range(4000):
+        lib().hostsim_normals12(C.c_uint64(1234), C.c_uint64(g), 3, 7, buf)
+        xs.append(np.array(buf[:]))
+    x = np.concatenate(xs)
+    assert abs(x.mean()) < 4 / np.sqrt(x.size)
+    assert abs(x.var() - 1) < 0.03
+    assert abs((x ** 4).mean() - 3) < 0.15
+    pairs = np.stack(xs)
+    c = np.corrcoef(pairs.T)
+    assert np.abs(c - np.eye(12)).max() < 0.08
