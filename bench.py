@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — LLGS hot-path benchmark (driver contract: one JSON line on stdout from rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one env.step() of every env of the workload = one launch of the fused K1 kernel per GPU.
+Workload (config.workload): BASELINE configs[1] physics — SpinTorque-v0, stt_mram reference defaults, T = 300 K thermal
+fluctuations from the in-kernel Philox stream, RK4 fixed dt (pulse 1 ns -> 999 substeps per step), random current
+densities — at the env count the metric is quoted on: 1,048,576 envs per GPU (weak scaling: every rank owns that many).
+
+  value      LLGS substeps/s, whole job, actions/state/obs resident in HBM (device-timed, max over ranks)
+  e2e        same metric through the public API (SpinTorqueVectorEnv.step) with HOST numpy actions: pinned H2D of the
+             actions and D2H of obs/reward/flags inside the timed region
+  roofline   dominant kernel (stt_env_step_kernel) against the FP32 FMA pipe (the path is not HBM- or tensor-bound)
+  cpu_baseline  the C restatement of the reference algorithm (oracle/c, kind "port") on all host cores, bounded sample
+
+`--impl reference` times that CPU port alone (the reference is pure Python and cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ENVS_PER_GPU = 1 << 20
+PULSE_S = 1e-9                 # float32(1e-9) floors to 999 substeps (physics/simple_solver.py:137-139)
+FLOP_RK4_THERMAL = 329         # algorithmic flops per RK4 substep, thermal on
+FLOP_RK4 = 301
+BYTES_PER_ENV_STEP = 150       # algorithmic HBM bytes per env-step
+FP32_LANES_PER_SM, N_SM = 128, 148
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[1]) for r in rows]
+            out["samples"] = len(sm)
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["power_w_max"] = max(float(r[3]) for r in rows)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for k, nm in enumerate(names):
+                    if any(r[5 + k].strip().lower().startswith("active") for r in rows):
+                        out["reasons"].append(nm)
+        except Exception:  # noqa: BLE001
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+def make_actions(n, seed):
+    """Synthetic random pulse sequences: J ~ U(-Jm, Jm) in the well-conditioned regime, fixed 1 ns duration."""
+    rng = np.random.default_rng(seed)
+    a = np.empty((n, 2), np.float32)
+    a[:, 0] = rng.uniform(-1.1e-6, 1.1e-6, n)
+    a[:, 1] = PULSE_S
+    return a
+
+
+ENV_KW = dict(device_type="stt_mram", max_current=1.1e-6, temperature=300.0, include_thermal_fluctuations=True,
+              integrator="rk4", autoreset=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_port_rate(n_sample: int, steps: int, threads: int, thermal: bool = True):
+    """LLGS substeps/s of the C restatement (oracle/c) on `threads` host threads over `steps` steps of n_sample envs."""
+    from oracle.c_oracle import COracleEnv
+    env = COracleEnv(n_sample, max_current=1.1e-6, include_thermal=thermal, temperature=300.0, nthreads=threads)
+    rng = np.random.default_rng(0)
+    env.reset(rng.normal(size=(n_sample, 3)), np.array([0.0, 0.0, 1.0]))
+    act = make_actions(n_sample, 1)
+    sub = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        env.step(act)
+        sub += int(env.substeps)
+    dt = time.perf_counter() - t0
+    return sub / dt, n_sample * steps / dt, dt
+
+
+def python_port_rate(max_seconds: float = 4.0):
+    """Substeps/s of the NumPy restatement (what the reference's interpreter-bound loop costs), one core."""
+    from oracle.stt_oracle import SttOracleEnv
+    env = SttOracleEnv(max_current=1.1e-6, include_thermal=False)
+    env.reset(np.array([0.3, 0.2, 0.9]), np.array([0.0, 0.0, 1.0]))
+    t0 = time.perf_counter()
+    sub = 0
+    while time.perf_counter() - t0 < max_seconds:
+        _, _, _, _, info = env.step(np.array([5e-7, 5e-10], np.float32))
+        sub += info["n_sub"]
+    return sub / (time.perf_counter() - t0)
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the CPU implementation of the path on all host cores. Rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = 256 * threads           # ~1.0 s of CPU work per step at ~2e5 substeps/s/thread... bounded sample
+    for _ in range(args.warmup):
+        cpu_port_rate(max(threads, n_sample // 8), 1, threads)
+    t0 = time.perf_counter()
+    sub_rate, env_rate, dt = cpu_port_rate(n_sample, args.steps, threads)
+    line = {
+        "impl": "reference", "metric": "llgs_substeps_per_sec", "value": sub_rate, "unit": "LLGS substeps/s",
+        "env_steps_per_s": env_rate, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, n_sample, "bounded sample of the same workload"),
+        "cpu_baseline": {"value": sub_rate, "unit": "LLGS substeps/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_sample} envs x {args.steps} steps x 999 RK4 substeps, thermal on"},
+        "e2e": {"value": sub_rate, "unit": "LLGS substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, n_envs_per_gpu, note=""):
+    return {
+        "workload": "SpinTorque-v0 stt_mram (reference default device), T=300K thermal (Philox), RK4 fixed dt, "
+                    "1 ns pulses = 999 substeps/step, random J in the well-conditioned regime (BASELINE configs[1] physics "
+                    "at the metric's 1M envs per GPU)" + (f"; {note}" if note else ""),
+        "envs_per_gpu": n_envs_per_gpu, "total_envs": n_envs_per_gpu * n_gpus, "substeps_per_env_step": 999,
+        "parallelism": f"env-sharded x{n_gpus}, no data-path collective; stats all-reduce once per rollout",
+        "l2": "state+io per step (~200 MB at 1M envs) exceeds the 126 MB L2; kernel is FP32-pipe bound",
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=N_ENVS_PER_GPU)
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-thermal", action="store_true", help="secondary workload: thermal off (301 flop/substep)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (thermal-off, f64, probe)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from spin_torque_rl_gym_b200 import SpinTorqueVectorEnv, _lib
+    from spin_torque_rl_gym_b200.parallel import all_reduce_stats
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    n_local = args.envs_per_gpu
+    tdtype = torch.float32 if args.dtype == "f32" else torch.float64
+    thermal = not args.no_thermal
+    kw = dict(ENV_KW, include_thermal_fluctuations=thermal)
+    flop_sub = FLOP_RK4_THERMAL if thermal else FLOP_RK4
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed_device_steps(env, act, steps, warmup):
+        for _ in range(warmup):
+            env.step(act)
+        barrier()
+        l0 = env.gpu_launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            env.step(act)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, env.gpu_launches - l0
+
+    # ---- headline: device-resident ------------------------------------------------------------------------------------
+    env = SpinTorqueVectorEnv(num_envs=n_local, device=dev, dtype=tdtype, rng_seed=1234, env_offset=rank * n_local, **kw)
+    env.reset(seed=1234)
+    act_host = make_actions(n_local, 100 + rank)
+    act = torch.from_numpy(act_host).to(dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed_device_steps(env, act, args.steps, args.warmup)
+    stats = all_reduce_stats(env.stats_tensor())          # one collective per rollout (K5): episode statistics
+    clocks = sampler.stop() if rank == 0 else {}
+    sub_per_step = n_local * 999 * n_gpus
+    value = sub_per_step * args.steps / (ms * 1e-3)
+    env_steps = n_local * n_gpus * args.steps / (ms * 1e-3)
+    kernel_ms = ms / args.steps                             # one K1 launch per step per GPU
+
+    # ---- e2e: public API, host actions in, host results out ------------------------------------------------------------
+    pinned_obs = torch.empty(n_local, 12, dtype=torch.float32).pin_memory()
+    pinned_rew = torch.empty(n_local, dtype=torch.float64).pin_memory()
+    pinned_flags = torch.empty(2, n_local, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        o, r, te, tr, _ = env.step(act_host)                # numpy in: staged through pinned memory + H2D inside step()
+        pinned_obs.copy_(o, non_blocking=True)
+        pinned_rew.copy_(r, non_blocking=True)
+        pinned_flags[0].copy_(env._terminated, non_blocking=True)
+        pinned_flags[1].copy_(env._truncated, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()        # the caller reads the results every step
+        return float(pinned_rew[0])
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0])
+    e2e_value = sub_per_step * args.steps / (e2e_ms * 1e-3)
+
+    # ---- secondary measurements (rank 0, N=1 only) ---------------------------------------------------------------------
+    extras = {}
+    peaks, peaks_src = _peaks()
+    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    fp32_peak_theory = N_SM * FP32_LANES_PER_SM * 2 * sm_max_mhz * 1e6 / 1e12
+    fma_probe_tflops = None
+    if rank == 0 and not args.no_extras:
+        lib = _lib.load()
+        buf = torch.empty(N_SM * 16 * 256, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        best = 0.0
+        for it in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.stg_probe_fma(buf.data_ptr(), N_SM * 16, 4096, 0, stream))
+            e1.record()
+            torch.cuda.synchronize(dev)
+            if it:
+                best = max(best, N_SM * 16 * 256 * 4096 * 64 * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        fma_probe_tflops = best
+        if world == 1:
+            def variant(name, n, **over):
+                e = SpinTorqueVectorEnv(num_envs=n, device=dev, rng_seed=1234,
+                                        **dict(kw, **{k: v for k, v in over.items() if k != "dtype"}),
+                                        dtype=over.get("dtype", tdtype))
+                e.reset(seed=1234)
+                a = torch.from_numpy(make_actions(n, 7)).to(dev)
+                m, _ = timed_device_steps(e, a, max(3, args.steps // 2), 3)
+                extras[name] = n * 999 * max(3, args.steps // 2) / (m * 1e-3)
+                del e
+            variant("substeps_per_s_thermal_off", n_local, include_thermal_fluctuations=False)
+            variant("substeps_per_s_65536_envs", 65536)
+            variant("substeps_per_s_f64_thermal", n_local // 4, dtype=torch.float64)
+            variant("substeps_per_s_f64_thermal_off", n_local // 4, dtype=torch.float64, include_thermal_fluctuations=False)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_sample = 256 * threads
+        cpu_port_rate(max(threads, n_sample // 8), 1, threads, thermal)
+        rate, _, dt = cpu_port_rate(n_sample, 3, threads, thermal)
+        cpu_baseline = {"value": rate, "unit": "LLGS substeps/s", "cores": threads, "kind": "port",
+                        "sample": f"{n_sample} envs x 3 steps x 999 RK4 substeps (thermal {'on' if thermal else 'off'}), "
+                                  f"C restatement oracle/c on {threads} threads, {dt:.1f} s",
+                        "python_port_substeps_per_s_1core": python_port_rate(3.0)}
+
+    if rank == 0:
+        achieved = value / n_gpus * flop_sub / 1e12            # per-GPU algorithmic TFLOP/s of the dominant kernel
+        peak = fma_probe_tflops if fma_probe_tflops else fp32_peak_theory
+        line = {
+            "metric": "llgs_substeps_per_sec", "value": value, "unit": "LLGS substeps/s",
+            "env_steps_per_s": env_steps, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype + " stages, f64 state", "data": "synthetic",
+            "config": workload_config(n_gpus, n_local),
+            "e2e": {"value": e2e_value, "unit": "LLGS substeps/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": n_local * 8 * n_gpus, "d2h_bytes_per_step": n_local * (48 + 8 + 2) * n_gpus,
+                    "api": "SpinTorqueVectorEnv.step(numpy actions) + D2H of obs/reward/terminated/truncated"},
+            "gpu_launches": launches,
+            "roofline": {
+                "bound": "fp32_fma", "kernel": "stt_env_step_kernel<float, axis_z, philox, rk4>",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": ("stg_probe_fma measured in this run" if fma_probe_tflops else "theoretical"),
+                "peak_theoretical": fp32_peak_theory, "frac_of_theoretical": achieved / fp32_peak_theory,
+                "algorithmic_flop_per_substep": flop_sub, "substeps_per_launch": n_local * 999,
+                "kernel_ms": kernel_ms, "traffic": None,
+                "hbm": {"achieved_gbs": n_local * BYTES_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9,
+                        "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src},
+            },
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "episode_stats": stats,
+            "extras": extras,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

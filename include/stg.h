@@ -222,6 +222,10 @@ int stg_stt_sort_by_substeps(const StgSttFolded* d_table, int32_t n_sets, const 
 int stg_stt_solve_f32(const StgSttSolveArgs* args, void* stream);
 int stg_stt_solve_f64(const StgSttSolveArgs* args, void* stream);
 
+/* FMA-pipe throughput probe (bench.py's measured FP32/FP64 roofline denominator): blocks*256 threads x iters*64 FMAs.
+ * d_out: >= blocks*256 elements of the probed type (never written in practice). */
+int stg_probe_fma(void* d_out, int32_t blocks, int32_t iters, int32_t f64, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,29 @@ typedef struct {
     int32_t max_steps, thermal, euler, pad;
 } OracleParams;
 
+/* Stand-in for np.random.normal(0, 1, 3) (physics/simple_solver.py:381) when no noise tensor is injected: the same
+ * Marsaglia polar method NumPy's legacy generator uses (second value cached), on a splitmix64 stream per env. Only the
+ * distribution matters here (bench timing and statistics); bit-level noise parity uses the injected tensor. */
+typedef struct { uint64_t s; int has; double cached; } Rng;
+static uint64_t splitmix(uint64_t* s) {
+    uint64_t z = (*s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static double rng_gauss(Rng* r) {
+    if (r->has) { r->has = 0; return r->cached; }
+    double x1, x2, r2;
+    do {
+        x1 = 2.0 * ((splitmix(&r->s) >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+        x2 = 2.0 * ((splitmix(&r->s) >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+        r2 = x1 * x1 + x2 * x2;
+    } while (r2 >= 1.0 || r2 == 0.0);
+    double f = sqrt(-2.0 * log(r2) / r2);
+    r->cached = f * x1; r->has = 1;
+    return f * x2;
+}
+
 static void cross(const double* a, const double* b, double* c) {
     c[0] = a[1] * b[2] - a[2] * b[1];
     c[1] = a[2] * b[0] - a[0] * b[2];
@@ -107,6 +130,7 @@ typedef struct {
     const float* action; const double* noise; int64_t noise_stride;
     float* obs; double* reward; uint8_t* terminated; uint8_t* truncated; double* step_energy; int32_t* n_sub_out;
     int64_t total_sub;
+    uint64_t rng_seed;
 } Job;
 
 static void* run_range(void* arg) {
@@ -145,10 +169,17 @@ static void* run_range(void* arg) {
         int guard = 0;
         guard_normalise(mm, &guard);
         const double* nz = noise ? noise + (int64_t)i * noise_stride * S * 3 : 0;
+        Rng rng = {jb->rng_seed * 0x2545F4914F6CDD1DULL + (uint64_t)i * 0x9E3779B97F4A7C15ULL + (uint64_t)step_count[i], 0, 0.0};
+        const int own_noise = (!nz && hth > 0);
+        double drawn[12];
         for (int s = 0; s < ns; ++s) {
             double ti = (double)s * dt;
             double k1[3], k2[3], k3[3], k4[3], tmp[3], f[3], mn[3];
             const double* x = nz ? nz + (int64_t)s * S * 3 : 0;
+            if (own_noise) {
+                for (int q = 0; q < S * 3; ++q) drawn[q] = rng_gauss(&rng);
+                x = drawn;
+            }
             rhs(mm, ti <= T ? J : 0.0, p, e, hth, x, f);
             if (p->euler) {
                 for (int k = 0; k < 3; ++k) mn[k] = mm[k] + dt * f[k];
@@ -207,7 +238,7 @@ static void* run_range(void* arg) {
 int64_t stt_oracle_step(const OracleParams* p, int64_t n, double* m, const double* target, double* total_energy,
                         int32_t* step_count, double* last_action, const float* action, const double* noise,
                         int64_t noise_stride, float* obs, double* reward, uint8_t* terminated, uint8_t* truncated,
-                        double* step_energy, int32_t* n_sub_out, int32_t nthreads) {
+                        double* step_energy, int32_t* n_sub_out, int32_t nthreads, uint64_t rng_seed) {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     if ((int64_t)nthreads > n) nthreads = n > 0 ? (int32_t)n : 1;
@@ -219,7 +250,7 @@ int64_t stt_oracle_step(const OracleParams* p, int64_t n, double* m, const doubl
         jb->m = m; jb->target = target; jb->total_energy = total_energy; jb->step_count = step_count;
         jb->last_action = last_action; jb->action = action; jb->noise = noise; jb->noise_stride = noise_stride;
         jb->obs = obs; jb->reward = reward; jb->terminated = terminated; jb->truncated = truncated;
-        jb->step_energy = step_energy; jb->n_sub_out = n_sub_out; jb->total_sub = 0;
+        jb->step_energy = step_energy; jb->n_sub_out = n_sub_out; jb->total_sub = 0; jb->rng_seed = rng_seed;
     }
     for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], 0, run_range, &jobs[t]);
     run_range(&jobs[0]);

@@ -63,6 +63,7 @@ class COracleEnv:
         p.success_threshold, p.energy_weight = success_threshold, energy_penalty_weight
         p.max_steps, p.thermal, p.euler = max_steps, int(bool(include_thermal)), int(method == "euler")
         self.p, self.n, self.nthreads = p, int(n), int(nthreads)
+        self.rng_seed = 12345
         n = self.n
         self.m = np.zeros((n, 3)); self.m[:, 2] = 1
         self.target = np.zeros((n, 3)); self.target[:, 2] = 1
@@ -97,5 +98,6 @@ class COracleEnv:
         self.substeps = lib().stt_oracle_step(
             C.byref(self.p), C.c_int64(self.n), _p(self.m), _p(self.target), _p(self.total_energy), _p(self.step_count),
             _p(self.last_action), _p(act), _p(noise), C.c_int64(stride), _p(self.obs), _p(self.reward),
-            _p(self.terminated), _p(self.truncated), _p(self.step_energy), _p(self.n_sub), C.c_int32(self.nthreads))
+            _p(self.terminated), _p(self.truncated), _p(self.step_energy), _p(self.n_sub), C.c_int32(self.nthreads),
+            C.c_uint64(self.rng_seed))
         return self.obs.copy(), self.reward.copy(), self.terminated.astype(bool), self.truncated.astype(bool)

@@ -89,6 +89,7 @@ SYMBOLS = {
                                            C.c_int64, C.c_void_p]),
     "stg_stt_solve_f32": (C.c_int, [C.POINTER(StgSttSolveArgs), C.c_void_p]),
     "stg_stt_solve_f64": (C.c_int, [C.POINTER(StgSttSolveArgs), C.c_void_p]),
+    "stg_probe_fma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
 _LIB: Optional[C.CDLL] = None

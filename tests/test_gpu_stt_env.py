@@ -1,0 +1,324 @@
+"""Parity tests proper: the CUDA path (SpinTorqueVectorEnv -> C-ABI -> sm_100a kernels) against the golden vectors of the
+live reference and against the C oracle on identical inputs. Tolerances (north star): 1e-6 relative with FP64 stage
+arithmetic, 1e-4 with FP32 stage arithmetic; binomial / F-test confidence intervals with the in-kernel Philox stream."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import GOLDEN, load_case, noise_for_step, rel_err, stt_params_for
+
+pytestmark = pytest.mark.gpu
+TOL = {"f64": 1e-6, "f32": 1e-4}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dtype(name):
+    torch = _torch()
+    return torch.float64 if name == "f64" else torch.float32
+
+
+def _make(n, prec, cuda_device, **kw):
+    from spin_torque_rl_gym_b200 import SpinTorqueVectorEnv
+    kw.setdefault("autoreset", False)
+    return SpinTorqueVectorEnv(num_envs=n, device=cuda_device, dtype=_dtype(prec), **kw)
+
+
+def _case_env(c, prec, cuda_device):
+    return _make(1, prec, cuda_device, device_params=stt_params_for(c), max_current=float(c["max_current"]),
+                 include_thermal_fluctuations=bool(c["thermal"]), integrator=str(c["method"]),
+                 max_steps=int(c.get("max_steps", 100)))
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["bigvol_det", "tilted_rk4", "thermal_injected"])
+def test_golden_episode(name, prec, cuda_device):
+    c = load_case("stt_env.npz", name)
+    env = _case_env(c, prec, cuda_device)
+    obs, _ = env.reset(options={"initial_state": c["m0"], "target_state": c["target"]})
+    assert np.array_equal(obs.cpu().numpy()[0], c["obs"][0])
+    tol = TOL[prec]
+    for k, a in enumerate(c["actions"]):
+        noise = noise_for_step(c["seeds"][k], a, float(c["max_current"]))[None] if "seeds" in c else None
+        o, r, te, tr, info = env.step(a[None].copy(), noise=noise)
+        m = env.magnetization.cpu().numpy()[0]
+        assert np.abs(m - c["m"][k + 1]).max() < tol, k
+        assert np.abs(o.cpu().numpy()[0] - c["obs"][k + 1]).max() < tol
+        assert abs(float(r[0]) - c["reward"][k]) < tol * max(1.0, abs(c["reward"][k]))
+        e_ref = c["energy"][k]
+        assert abs(float(info["step_energy"][0]) - e_ref) <= tol * e_ref
+        assert bool(te[0]) == c["terminated"][k] and bool(tr[0]) == c["truncated"][k]
+        assert int(info["status"][0]) == 0
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_c1_single_env_100_pulses(prec, cuda_device):
+    """BASELINE config[0]: N=1, thermal off, 100 random pulses. Free-running while the golden is well-conditioned, then every
+    step from the golden's own pre-step state (the episode collapses onto a pole down to denormals; tests/test_oracle_golden)."""
+    torch = _torch()
+    c = load_case("stt_env.npz", "c1_det")
+    env = _case_env(c, prec, cuda_device)
+    env.reset(options={"initial_state": c["m0"], "target_state": c["target"]})
+    tol = TOL[prec]
+    for k, a in enumerate(c["actions"]):
+        if np.hypot(*c["m"][k + 1][:2]) < 1e-300:
+            break
+        o, r, te, tr, info = env.step(a[None].copy())
+        m = env.magnetization.cpu().numpy()[0]
+        assert rel_err(m, c["m"][k + 1]) < (1e-6 if prec == "f64" else 5e-2), k
+        assert np.abs(m - c["m"][k + 1]).max() < tol
+        assert abs(float(r[0]) - c["reward"][k]) < tol * max(1.0, abs(c["reward"][k]))
+        assert bool(te[0]) == c["terminated"][k]
+    assert k >= 8
+    # teacher-forced over all 100 steps
+    for k, a in enumerate(c["actions"]):
+        t_in = np.hypot(*c["m"][k][:2])
+        env._m.copy_(torch.from_numpy(c["m"][k]).to(cuda_device).reshape(3, 1))
+        env._total_energy.fill_(float(c["total_energy"][k - 1]) if k else 0.0)
+        env._step_count.fill_(k)
+        o, r, te, tr, info = env.step(a[None].copy())
+        m = env.magnetization.cpu().numpy()[0]
+        if t_in > 1e-200:
+            assert rel_err(m, c["m"][k + 1]) < (1e-6 if prec == "f64" else 5e-3), k
+        assert np.abs(m - c["m"][k + 1]).max() < tol, k
+        assert np.abs(o.cpu().numpy()[0] - c["obs"][k + 1]).max() < tol
+        assert abs(float(r[0]) - c["reward"][k]) < tol * max(1.0, abs(c["reward"][k]))
+        assert bool(te[0]) == c["terminated"][k] and bool(tr[0]) == c["truncated"][k]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_multi_episode_golden(prec, cuda_device):
+    g = np.load(os.path.join(GOLDEN, "stt_multi.npz"))
+    n = len(g["actions"])
+    env = _make(n, prec, cuda_device, max_current=float(g["max_current"]), include_thermal_fluctuations=False)
+    obs0, _ = env.reset(options={"initial_state": g["m0"], "target_state": g["target"]})
+    assert np.array_equal(obs0.cpu().numpy(), g["obs0"])
+    o, r, te, tr, info = env.step(g["actions"].copy())
+    tol = TOL[prec]
+    assert np.abs(env.magnetization.cpu().numpy() - g["m"]).max() < tol
+    assert np.abs(o.cpu().numpy() - g["obs"]).max() < tol
+    assert np.allclose(r.cpu().numpy(), g["reward"], rtol=tol, atol=tol)
+    assert np.array_equal(te.cpu().numpy(), g["terminated"]) and np.array_equal(tr.cpu().numpy(), g["truncated"])
+    assert np.allclose(info["step_energy"].cpu().numpy(), g["energy"], rtol=1e-9, atol=0)
+
+
+def _random_setup(n, seed, jm=1.1e-6, tmax=1.5e-9):
+    rng = np.random.default_rng(seed)
+    m0 = rng.normal(size=(n, 3))
+    tgt = np.where(rng.integers(2, size=(n, 1)) == 0, 1.0, -1.0) * np.array([[0, 0, 1.0]])
+    acts = [np.stack([rng.uniform(-jm, jm, n), rng.uniform(0, tmax, n)], 1).astype(np.float32) for _ in range(2)]
+    acts[0][0] = [np.nan, 1e-9]
+    acts[0][1] = [jm, np.inf]
+    acts[0][2] = [0.0, 5e-10]
+    acts[0][3] = [-1.0, 1e-13]
+    acts[0][4] = [1e-13, 1e-9]
+    return m0, tgt, acts
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("variant", ["default", "tilted", "euler"])
+def test_random_batch_vs_c_oracle(prec, variant, cuda_device):
+    """4096 envs with ragged substep counts (10..1500), edge-case actions, two consecutive steps."""
+    from oracle.c_oracle import COracleEnv
+    from oracle.stt_oracle import default_stt_params
+    n, jm = 4096, 1.1e-6
+    m0, tgt, acts = _random_setup(n, 21)
+    p = default_stt_params()
+    method = "rk4"
+    if variant == "tilted":
+        p.update(easy_axis=np.array([0.2, -0.1, 1.0]), reference_magnetization=np.array([0.0, 0.3, 1.0]), damping=0.03)
+    if variant == "euler":
+        method = "euler"
+        acts = [np.stack([a[:, 0], np.minimum(a[:, 1], 2e-10)], 1) for a in acts]   # the Euler map amplifies rounding
+    env = _make(n, prec, cuda_device, device_params=p, max_current=jm, include_thermal_fluctuations=False,
+                integrator=method)
+    ora = COracleEnv(n, device_params=p, max_current=jm, include_thermal=False, method=method,
+                     nthreads=os.cpu_count() or 1)
+    obs0, _ = env.reset(options={"initial_state": m0, "target_state": tgt})
+    assert np.array_equal(obs0.cpu().numpy(), ora.reset(m0, tgt))
+    tol = TOL[prec] * (20 if (variant == "euler" and prec == "f32") else 1)
+    for a in acts:
+        o, r, te, tr, info = env.step(a.copy())
+        oo, orr, ote, otr = ora.step(a)
+        assert np.array_equal(info["n_sub"].cpu().numpy(), ora.n_sub)
+        assert np.abs(env.magnetization.cpu().numpy() - ora.m).max() < tol
+        assert np.abs(o.cpu().numpy() - oo).max() < tol
+        assert np.allclose(r.cpu().numpy(), orr, rtol=tol, atol=tol)
+        mism = (te.cpu().numpy() != ote)
+        # an env sitting within tol of the success threshold may legitimately flip its flag
+        assert mism.sum() <= 2
+        assert np.array_equal(tr.cpu().numpy(), otr)
+        assert np.allclose(info["step_energy"].cpu().numpy(), ora.step_energy, rtol=tol, atol=0)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_injected_noise_batch_vs_c_oracle(prec, cuda_device):
+    """Thermal on, identical N(0,1) tensor fed to both sides (order: substep, stage, xyz)."""
+    from oracle.c_oracle import COracleEnv
+    n, jm = 128, 1.1e-6
+    rng = np.random.default_rng(5)
+    m0 = rng.normal(size=(n, 3))
+    m0[:16] = [1.0, 0.0, 0.0]      # unstable equilibrium: the only place the noise matters dynamically
+    tgt = np.tile([0.0, 0.0, 1.0], (n, 1))
+    act = np.stack([rng.uniform(-jm, jm, n), rng.uniform(1e-11, 3e-10, n)], 1).astype(np.float32)
+    act[:16, 0] = 0.0
+    noise = rng.normal(size=(n, 300, 4, 3))
+    env = _make(n, prec, cuda_device, max_current=jm, include_thermal_fluctuations=True, temperature=300.0)
+    ora = COracleEnv(n, max_current=jm, include_thermal=True, temperature=300.0, nthreads=4)
+    env.reset(options={"initial_state": m0, "target_state": tgt})
+    ora.reset(m0, tgt)
+    o, r, te, tr, info = env.step(act.copy(), noise=noise)
+    oo, orr, ote, otr = ora.step(act, noise)
+    m = env.magnetization.cpu().numpy()
+    assert np.abs(m - ora.m).max() < TOL[prec]
+    # at the equator m_z is O(1e-8): compare it relatively (never through 1-|m.z|)
+    mz, mz_ref = m[:16, 2], ora.m[:16, 2]
+    assert np.all(np.abs(mz_ref) < 1e-6)
+    assert np.abs(mz - mz_ref).max() < (1e-6 if prec == "f64" else 2e-3) * np.abs(mz_ref).max()
+    assert np.allclose(r.cpu().numpy(), orr, rtol=TOL[prec], atol=TOL[prec])
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_philox_switching_statistics(prec, cuda_device):
+    """In-kernel RNG: start on the equator (m_z = 0), no current, 100 substeps. The sign of m_z is decided by the noise:
+    P(m_z > 0) must sit inside the binomial 95 % CI, and Var(m_z) must match the oracle's (same experiment with NumPy noise)
+    within the F-test interval — the sign checks the symmetry of the stream, the variance checks the amplitude h_th."""
+    from oracle.c_oracle import COracleEnv
+    n_gpu, n_cpu = 65536, 4096
+    act = np.tile(np.array([[0.0, 1e-10]], np.float32), (n_gpu, 1))
+    env = _make(n_gpu, prec, cuda_device, include_thermal_fluctuations=True, temperature=300.0, rng_seed=1234)
+    env.reset(options={"initial_state": np.array([1.0, 0.0, 0.0]), "target_state": np.array([0.0, 0.0, 1.0])})
+    env.step(act)
+    mz = env.magnetization.cpu().numpy()[:, 2]
+    rng = np.random.default_rng(99)
+    ora = COracleEnv(n_cpu, include_thermal=True, temperature=300.0, nthreads=os.cpu_count() or 1)
+    ora.reset(np.array([1.0, 0.0, 0.0]), np.array([0.0, 0.0, 1.0]))
+    ora.step(act[:n_cpu], rng.normal(size=(n_cpu, 100, 4, 3)))
+    mz_ref = ora.m[:, 2]
+    p_gpu = (mz > 0).mean()
+    half = 1.96 * np.sqrt(0.25 / n_gpu)
+    assert abs(p_gpu - 0.5) < half + 1.96 * np.sqrt(0.25 / n_cpu) * 0 + 1e-12, p_gpu
+    p_ref = (mz_ref > 0).mean()
+    assert abs(p_gpu - p_ref) < 1.96 * np.sqrt(0.25 / n_gpu + 0.25 / n_cpu)
+    ratio = mz.var() / mz_ref.var()
+    ci = 1.96 * np.sqrt(2.0 / n_gpu + 2.0 / n_cpu)        # normal approx. of the F interval (both samples Gaussian)
+    assert abs(ratio - 1.0) < ci, ratio
+    assert abs(mz.mean()) < 4 * mz.std() / np.sqrt(n_gpu)
+    assert 1e-9 < mz.std() < 1e-7
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE config[1] size (65,536 envs, T=300 K, RK4, 999 substeps): size-independent properties."""
+    torch = _torch()
+    n = 65536
+    act = torch.zeros(n, 2, dtype=torch.float32, device=cuda_device)
+    act[:, 0] = torch.linspace(-2e6, 2e6, n, device=cuda_device) * 5e-13   # well-conditioned current scale
+    act[:, 1] = 1e-9
+    kw = dict(max_current=1.1e-6, include_thermal_fluctuations=True, temperature=300.0, rng_seed=7)
+    env = _make(n, "f32", cuda_device, **kw)
+    env.reset(seed=7)
+    m_before = env.magnetization.clone()
+    o, r, te, tr, info = env.step(act)
+    m = env.magnetization
+    assert torch.all(info["n_sub"] == 999)
+    assert float((m.norm(dim=1) - 1).abs().max()) < 1e-12            # renormalised in FP64
+    assert torch.isfinite(o).all() and torch.isfinite(r).all()
+    assert int(info["status"].max()) == 0
+    assert float((m - m_before).abs().max()) > 1e-3
+    # determinism: same seed, same inputs -> bit-identical
+    env2 = _make(n, "f32", cuda_device, **kw)
+    env2.reset(seed=7)
+    o2, r2, *_ = env2.step(act)
+    assert torch.equal(o, o2) and torch.equal(r, r2)
+    # sharding invariance: two half-size envs with env_offset reproduce the full batch (Philox counters use global ids)
+    h = n // 2
+    parts = []
+    for k in range(2):
+        e = _make(h, "f32", cuda_device, env_offset=k * h, **kw)
+        e.reset(seed=7)
+        ok, *_ = e.step(act[k * h:(k + 1) * h].contiguous())
+        parts.append(ok.clone())
+    assert torch.equal(torch.cat(parts), o)
+    # different seed -> different thermal stream
+    env3 = _make(n, "f32", cuda_device, **dict(kw, rng_seed=8))
+    env3.reset(seed=7)
+    env3._m.copy_(torch.as_tensor(m_before.t().contiguous()))
+    o3, *_ = env3.step(act)
+    assert not torch.equal(o3, o)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_sorted_launch_is_identical(prec, cuda_device):
+    """Sorting envs by substep count only changes the thread mapping, never the result."""
+    n, jm = 8192, 1.1e-6
+    m0, tgt, acts = _random_setup(n, 3, tmax=5e-9)
+    outs = []
+    for sort in (False, True):
+        env = _make(n, prec, cuda_device, max_current=jm, include_thermal_fluctuations=True, rng_seed=3,
+                    sort_by_substeps=sort)
+        env.reset(options={"initial_state": m0, "target_state": tgt})
+        o, r, te, tr, info = env.step(acts[0].copy())
+        outs.append((o.clone(), r.clone(), te.clone(), info["n_sub"].clone(), env.magnetization.clone()))
+        if sort:
+            perm = env._perm.cpu().numpy()
+            assert np.array_equal(np.sort(perm), np.arange(n))
+            ns = info["n_sub"].cpu().numpy()[perm]
+            assert np.all(np.diff(ns) <= 0)
+    for a, b in zip(outs[0], outs[1]):
+        assert _torch().equal(a, b)
+
+
+def test_autoreset_final_observation_and_stats(cuda_device):
+    torch = _torch()
+    n = 4096
+    env = _make(n, "f64", cuda_device, max_steps=3, include_thermal_fluctuations=False, autoreset=True, rng_seed=11,
+                max_current=1.1e-6)
+    obs, _ = env.reset(seed=11)
+    m0 = env.magnetization.cpu().numpy()
+    assert np.allclose(np.linalg.norm(m0, axis=1), 1.0, atol=1e-15)
+    assert abs(m0.mean()) < 0.03 and abs(m0[:, 2].var() - 1 / 3) < 0.03           # uniform on the sphere
+    tz = env.target.cpu().numpy()[:, 2]
+    assert set(np.unique(tz)) == {-1.0, 1.0} and abs((tz > 0).mean() - 0.5) < 0.05
+    act = torch.zeros(n, 2, dtype=torch.float32, device=cuda_device)
+    act[:, 1] = 1e-11
+    ended = 0
+    for s in range(3):
+        o, r, te, tr, info = env.step(act)
+        done = te | tr
+        ended += int(done.sum())
+        assert torch.all(info["step_count"][done] == 0)
+        assert torch.all(o[done, 8] == 1.0)
+        fin = info["final_observation"]
+        assert torch.all(fin[~done] == 0)
+        if done.any():
+            assert torch.all(fin[done][:, :3].norm(dim=1) > 0.99)
+    st = env.episode_stats()
+    assert st["steps"] == 3 * n
+    assert st["terminated"] + st["truncated"] == ended
+    assert st["substeps"] == 3 * n * 100
+    assert ended >= n                     # max_steps=3 truncates every env at the latest in step 3
+    sd = env.state_dict()
+    env2 = _make(n, "f64", cuda_device, max_steps=3, include_thermal_fluctuations=False, autoreset=True, rng_seed=11,
+                 max_current=1.1e-6)
+    env2.load_state_dict(sd)
+    o1, *_ = env.step(act)
+    o1 = o1.clone()
+    o2, *_ = env2.step(act)
+    assert torch.equal(o1, o2)
+
+
+def test_invalid_solver_params_keep_magnetisation(cuda_device):
+    """SOT dict without `polarization`: the reference's solver validation fails and m never moves."""
+    from spin_torque_rl_gym_b200 import params as P
+    p = P.default_device_parameters("sot_mram")
+    env = _make(16, "f64", cuda_device, device_type="sot_mram", device_params=p, include_thermal_fluctuations=False)
+    env.reset(seed=1)
+    m0 = env.magnetization.clone()
+    o, r, te, tr, info = env.step(np.tile(np.array([[1e6, 1e-9]], np.float32), (16, 1)))
+    assert _torch().equal(env.magnetization, m0)
+    assert int(info["status"].min()) == 2 and np.isfinite(r.cpu().numpy()).all()
+    assert float(info["step_energy"].min()) > 0
