@@ -22,6 +22,10 @@
 #define STG_HD inline
 #endif
 
+#ifndef STG_FAST_COPY_FROM_MASTER
+#define STG_FAST_COPY_FROM_MASTER 1
+#endif
+
 namespace stg {
 
 // ---- folded parameter-set layout (StgSttFolded::v) ------------------------------------------------------------------
@@ -69,112 +73,188 @@ struct Philox {
     }
 };
 
-// two uniforms -> two N(0,1) (Box-Muller, single precision; the noise only has to be statistically N(0,1))
-STG_HD void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
-    const float two_m32 = 2.3283064365386963e-10f;
-    float a = fmaf((float)u0, two_m32, 0.5f * two_m32);   // (0, 1]
-    float ang = (float)u1 * (two_m32 * 6.283185307179586f);
+// ---- fast device intrinsics (MUFU) with libm fallbacks for the host build ---------------------------------------------
+STG_HD float fast_lg2(float x) {
 #if defined(__CUDA_ARCH__)
-    float r = sqrtf(-2.0f * __logf(a));
-    float s, c;
-    __sincosf(ang, &s, &c);
+    return __log2f(x);
 #else
-    float r = sqrtf(-2.0f * logf(a));
-    float s = sinf(ang), c = cosf(ang);
+    return log2f(x);
 #endif
+}
+STG_HD float fast_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+STG_HD void fast_sincos_rev(float rev, float& s, float& c) {   // angle given in revolutions [0,1)
+    const float ang = rev * 6.283185307179586f;
+#if defined(__CUDA_ARCH__)
+    s = __sinf(ang);
+    c = __cosf(ang);
+#else
+    s = sinf(ang);
+    c = cosf(ang);
+#endif
+}
+STG_HD float bits_to_unit(uint32_t x) {   // top 23 bits -> [0,1) without an int->float conversion
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(0x3f800000u | (x >> 9)) - 1.0f;
+#else
+    union { uint32_t u; float f; } v;
+    v.u = 0x3f800000u | (x >> 9);
+    return v.f - 1.0f;
+#endif
+}
+
+// two uniforms -> two N(0, scale^2) (Box-Muller in single precision; the noise only has to be statistically Gaussian).
+// The radius uses all 32 bits of u0 (tail out to 6.66 sigma), the angle the top 23 bits of u1. `neg2ln2_scale2` is
+// -2*ln(2)*scale^2 so that scaling the field strength into the samples costs nothing.
+STG_HD void box_muller_scaled(uint32_t u0, uint32_t u1, float neg2ln2_scale2, float& n0, float& n1) {
+    const float two_m32 = 2.3283064365386963e-10f;
+    const float a = fmaf((float)u0, two_m32, 0.5f * two_m32);   // (0, 1]
+    const float r = fast_sqrt(neg2ln2_scale2 * fast_lg2(a));
+    float s, c;
+    fast_sincos_rev(bits_to_unit(u1), s, c);
     n0 = r * c;
     n1 = r * s;
 }
+STG_HD void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
+    box_muller_scaled(u0, u1, -1.3862943611198906f, n0, n1);
+}
 
-// 12 normals for the 4 stages of RK4 substep `sub` of env-step `step` of env `gid` (3 Philox calls)
-STG_HD void philox_normals12(const Philox& ph, uint64_t gid, uint32_t step, uint32_t sub, float xi[12]) {
+// 12 samples N(0, scale^2) for the 4 stages of RK4 substep `sub` of env-step `step` of env `gid` (3 Philox calls)
+STG_HD void philox_normals12(const Philox& ph, uint64_t gid, uint32_t step, uint32_t sub, float neg2ln2_scale2,
+                             float xi[12]) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         uint32_t o[4];
         ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u + (uint32_t)c, o);
-        box_muller(o[0], o[1], xi[4 * c + 0], xi[4 * c + 1]);
-        box_muller(o[2], o[3], xi[4 * c + 2], xi[4 * c + 3]);
+        box_muller_scaled(o[0], o[1], neg2ln2_scale2, xi[4 * c + 0], xi[4 * c + 1]);
+        box_muller_scaled(o[2], o[3], neg2ln2_scale2, xi[4 * c + 2], xi[4 * c + 3]);
     }
 }
-STG_HD void philox_normals4(const Philox& ph, uint64_t gid, uint32_t step, uint32_t sub, uint32_t lane, float xi[4]) {
+STG_HD void philox_normals4(const Philox& ph, uint64_t gid, uint32_t step, uint32_t sub, uint32_t lane,
+                            float neg2ln2_scale2, float xi[4]) {
     uint32_t o[4];
     ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u + lane, o);
-    box_muller(o[0], o[1], xi[0], xi[1]);
-    box_muller(o[2], o[3], xi[2], xi[3]);
+    box_muller_scaled(o[0], o[1], neg2ln2_scale2, xi[0], xi[1]);
+    box_muller_scaled(o[2], o[3], neg2ln2_scale2, xi[2], xi[3]);
 }
 
-// ---- per-step constants of one env (everything the substep loop needs, in the arithmetic type R) ---------------------
+// ---- per-step constants of one env --------------------------------------------------------------------------------------
+// Every product of physical constants and dt is formed in FP64 and split into a (hi, lo) pair of R so that FP32 stages see
+// the constants to ~48 bits: a constant rounded to 24 bits is a SYSTEMATIC error of the precession / relaxation rate that
+// grows linearly (phase) or quadratically (phase through m_z) with the 10..5000 substeps of a step. For R = double lo == 0.
+// `sc` pre-scales every increment (1/6 for the RK4 fast path, so the RK4 weights become exact small integers).
 template <typename R>
 struct StepConsts {
-    R ck;        // G*hk
-    R cd;        // -G*Ms            (demag  -Ms*m_z z^)
-    R cth;       // G*h_th
-    R alpha;
-    R a_on;      // aJ*dt while the pulse is on
+    R c_hi, c_lo;       // sc * G*(hk - Ms)          axis-z:  b_z = c * m_z
+    R ac_hi, ac_lo;     // sc * alpha*G*(hk - Ms)     axis-z:  w = ac*m_z + a
+    R a_hi, a_lo;       // sc * aJ*dt (pulse on)
+    R al_hi, al_lo;     // alpha
+    R ck_hi, ck_lo;     // sc * G*hk                  general axis
+    R cd_hi, cd_lo;     // sc * -G*Ms
+    R cth;              // sc * G*h_th  (field strength folded into the noise samples)
     R ex, ey, ez;
-    R bax, bay, baz;  // G*H_app
+    R bax, bay, baz;    // sc * G*H_app
 };
 
-// One stage: k = dt*f(m). AXIS_Z: easy axis == z^ exactly and H_app == 0, so every structurally-zero term is dropped.
-template <typename R, bool AXIS_Z, bool THERMAL>
-STG_HD void stage(const StepConsts<R>& c, R mx, R my, R mz, R a, R xx, R xy, R xz, R& kx, R& ky, R& kz) {
-    if (AXIS_Z) {
-        if (!THERMAL) {
-            R bz = (c.ck + c.cd) * mz;
-            R px = my * bz;
-            R py = -(mx * bz);
-            R qx = -(mz * py);
-            R qy = mz * px;
-            R qz = mx * py - my * px;
-            R tx = mz * mx;
-            R ty = mz * my;
-            R tz = -(mx * mx + my * my);
-            kx = px + c.alpha * qx + a * tx;
-            ky = py + c.alpha * qy + a * ty;
-            kz = c.alpha * qz + a * tz;
-        } else {
-            R bx = c.cth * xx;
-            R by = c.cth * xy;
-            R bz = (c.ck + c.cd) * mz + c.cth * xz;
-            R px = my * bz - mz * by;
-            R py = mz * bx - mx * bz;
-            R pz = mx * by - my * bx;
-            R qx = my * pz - mz * py;
-            R qy = mz * px - mx * pz;
-            R qz = mx * py - my * px;
-            R tx = mz * mx;
-            R ty = mz * my;
-            R tz = -(mx * mx + my * my);
-            kx = px + c.alpha * qx + a * tx;
-            ky = py + c.alpha * qy + a * ty;
-            kz = pz + c.alpha * qz + a * tz;
-        }
+template <typename R>
+STG_HD void split_const(double x, R& hi, R& lo) {
+    hi = (R)x;
+    lo = (sizeof(R) == 4) ? (R)(x - (double)hi) : R(0);
+}
+
+template <typename R>
+STG_HD void make_consts(const double* f, double dt, double J, double sc, StepConsts<R>& c) {
+    const double G = -f[FI_GEFF] * dt * sc;
+    const double alpha = f[FI_ALPHA];
+    split_const<R>(G * (f[FI_HK] - f[FI_MS]), c.c_hi, c.c_lo);
+    split_const<R>(alpha * G * (f[FI_HK] - f[FI_MS]), c.ac_hi, c.ac_lo);
+    const double a = (fabs(J) > 1e-12) ? f[FI_AJ_PER_J] * J * dt * sc : 0.0;   // physics/simple_solver.py:327-331
+    split_const<R>(a, c.a_hi, c.a_lo);
+    split_const<R>(alpha, c.al_hi, c.al_lo);
+    split_const<R>(G * f[FI_HK], c.ck_hi, c.ck_lo);
+    split_const<R>(-G * f[FI_MS], c.cd_hi, c.cd_lo);
+    c.cth = (R)(G * f[FI_HTH]);
+    c.ex = (R)f[FI_EX]; c.ey = (R)f[FI_EY]; c.ez = (R)f[FI_EZ];
+    c.bax = (R)(G * f[FI_HAX]); c.bay = (R)(G * f[FI_HAY]); c.baz = (R)(G * f[FI_HAZ]);
+}
+
+// ---- stage derivative, easy axis == z^ and H_app == 0 (deterministic part) ------------------------------------------------
+// With e = z^ the reference's  m x b + alpha m x (m x b) + a m x (m x e),  b = (0, 0, c m_z),  collapses to
+//     w = alpha*c*m_z + a,   k_x = m_y b_z + m_x m_z w,   k_y = -m_x b_z + m_y m_z w,   k_z = -(m_x^2 + m_y^2) w
+// (13 FMA-pipe instructions). q multiplies k_z only for the block-scaled transverse state (ScaledState below).
+template <typename R, bool SCALED>
+STG_HD void stage_z(const StepConsts<R>& c, R mx, R my, R mz, R aH, R aL, R q, R& kx, R& ky, R& kz) {
+    R bz, w;
+    if (sizeof(R) == 4) {
+        bz = c.c_lo * mz + c.c_hi * mz;
+        w = (c.ac_hi * mz + aH) + (c.ac_lo * mz + aL);
     } else {
-        R s = mx * c.ex + my * c.ey + mz * c.ez;
-        R cks = c.ck * s;
-        R bx = cks * c.ex + c.bax;
-        R by = cks * c.ey + c.bay;
-        R bz = cks * c.ez + c.baz + c.cd * mz;
-        if (THERMAL) {
-            bx += c.cth * xx;
-            by += c.cth * xy;
-            bz += c.cth * xz;
-        }
-        R px = my * bz - mz * by;
-        R py = mz * bx - mx * bz;
-        R pz = mx * by - my * bx;
-        R qx = my * pz - mz * py;
-        R qy = mz * px - mx * pz;
-        R qz = mx * py - my * px;
-        R ux = my * c.ez - mz * c.ey;
-        R uy = mz * c.ex - mx * c.ez;
-        R uz = mx * c.ey - my * c.ex;
-        R tx = my * uz - mz * uy;
-        R ty = mz * ux - mx * uz;
-        R tz = mx * uy - my * ux;
-        kx = px + c.alpha * qx + a * tx;
-        ky = py + c.alpha * qy + a * ty;
-        kz = pz + c.alpha * qz + a * tz;
+        bz = c.c_hi * mz;
+        w = c.ac_hi * mz + aH;
+    }
+    const R u = mz * w;
+    const R s2 = mx * mx + my * my;
+    kx = mx * u + my * bz;
+    ky = my * u - mx * bz;
+    kz = SCALED ? (s2 * -w) * q : s2 * -w;
+}
+// thermal part for e = z^: k += m x bn + alpha m x (m x bn), bn = (scaled) noise rotation vector
+template <typename R>
+STG_HD void stage_noise(const StepConsts<R>& c, R mx, R my, R mz, R bx, R by, R bz, R& kx, R& ky, R& kz) {
+    const R px = my * bz - mz * by;
+    const R py = mz * bx - mx * bz;
+    const R pz = mx * by - my * bx;
+    const R qx = my * pz - mz * py;
+    const R qy = mz * px - mx * pz;
+    const R qz = mx * py - my * px;
+    kx += px + c.al_hi * qx;
+    ky += py + c.al_hi * qy;
+    kz += pz + c.al_hi * qz;
+}
+
+// ---- stage derivative, general easy axis / applied field (cross-product form of the reference) ----------------------------
+template <typename R, bool THERMAL>
+STG_HD void stage_general(const StepConsts<R>& c, R mx, R my, R mz, R aH, R aL, R nx, R ny, R nz, R& kx, R& ky, R& kz) {
+    const R s = mx * c.ex + my * c.ey + mz * c.ez;
+    R cks, cdz;
+    if (sizeof(R) == 4) {
+        cks = c.ck_lo * s + c.ck_hi * s;
+        cdz = c.cd_lo * mz + c.cd_hi * mz;
+    } else {
+        cks = c.ck_hi * s;
+        cdz = c.cd_hi * mz;
+    }
+    R bx = cks * c.ex + c.bax;
+    R by = cks * c.ey + c.bay;
+    R bz = cks * c.ez + c.baz + cdz;
+    if (THERMAL) { bx += nx; by += ny; bz += nz; }
+    const R px = my * bz - mz * by;
+    const R py = mz * bx - mx * bz;
+    const R pz = mx * by - my * bx;
+    const R qx = my * pz - mz * py;
+    const R qy = mz * px - mx * pz;
+    const R qz = mx * py - my * px;
+    const R ux = my * c.ez - mz * c.ey;
+    const R uy = mz * c.ex - mx * c.ez;
+    const R uz = mx * c.ey - my * c.ex;
+    const R tx = my * uz - mz * uy;
+    const R ty = mz * ux - mx * uz;
+    const R tz = mx * uy - my * ux;
+    if (sizeof(R) == 4) {
+        kx = px + (c.al_hi * qx + (aH * tx + (aL * tx + c.al_lo * qx)));
+        ky = py + (c.al_hi * qy + (aH * ty + (aL * ty + c.al_lo * qy)));
+        kz = pz + (c.al_hi * qz + (aH * tz + (aL * tz + c.al_lo * qz)));
+    } else {
+        kx = px + c.al_hi * qx + aH * tx;
+        ky = py + c.al_hi * qy + aH * ty;
+        kz = pz + c.al_hi * qz + aH * tz;
     }
 }
 
@@ -187,67 +267,23 @@ STG_HD double inv_norm<double>(double n2) {
 }
 template <>
 STG_HD double inv_norm<float>(double n2) {
-    // f32 seed + one FP64 Newton step: relative error ~1e-14, far below the f32 stage arithmetic
+    // f32 seed + two FP64 Newton steps (relative error ~1e-14 after the first)
 #if defined(__CUDA_ARCH__)
     double y = (double)rsqrtf((float)n2);
 #else
     double y = (double)(1.0f / sqrtf((float)n2));
 #endif
+    y = y * (1.5 - 0.5 * n2 * y * y);
     return y * (1.5 - 0.5 * n2 * y * y);
 }
 
-// Guard + normalise (physics/simple_solver.py:208-229): non-finite or |m| < 1e-12 -> (0,0,1) and the guard flag.
-template <typename R>
-STG_HD void guard_normalise(double& mx, double& my, double& mz, int& guard) {
-    double n2 = mx * mx + my * my + mz * mz;
-    if (n2 >= 1e-24 && n2 <= 1.0e300) {
-        double inv = inv_norm<R>(n2);
-        mx *= inv; my *= inv; mz *= inv;
-    } else {
-        mx = 0.0; my = 0.0; mz = 1.0;
-        guard = 1;
-    }
-}
-
-// One fixed-step substep on the FP64 state. a1..a4: aJ*dt seen by the four stages (pulse gating). xi: 12 (rk4) or 3 (euler)
-// N(0,1) samples in stage order.
-template <typename R, bool AXIS_Z, bool THERMAL, bool EULER>
-STG_HD void substep(const StepConsts<R>& c, double& mdx, double& mdy, double& mdz, R a1, R a2, R a3, R a4, const R* xi,
-                    int& guard) {
-    R mx = (R)mdx, my = (R)mdy, mz = (R)mdz;
-    R k1x, k1y, k1z;
-    stage<R, AXIS_Z, THERMAL>(c, mx, my, mz, a1, THERMAL ? xi[0] : R(0), THERMAL ? xi[1] : R(0), THERMAL ? xi[2] : R(0),
-                              k1x, k1y, k1z);
-    R ix, iy, iz;
-    if (EULER) {
-        ix = k1x; iy = k1y; iz = k1z;
-    } else {
-        const R h = R(0.5);
-        R k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
-        stage<R, AXIS_Z, THERMAL>(c, mx + h * k1x, my + h * k1y, mz + h * k1z, a2, THERMAL ? xi[3] : R(0),
-                                  THERMAL ? xi[4] : R(0), THERMAL ? xi[5] : R(0), k2x, k2y, k2z);
-        stage<R, AXIS_Z, THERMAL>(c, mx + h * k2x, my + h * k2y, mz + h * k2z, a3, THERMAL ? xi[6] : R(0),
-                                  THERMAL ? xi[7] : R(0), THERMAL ? xi[8] : R(0), k3x, k3y, k3z);
-        stage<R, AXIS_Z, THERMAL>(c, mx + k3x, my + k3y, mz + k3z, a4, THERMAL ? xi[9] : R(0), THERMAL ? xi[10] : R(0),
-                                  THERMAL ? xi[11] : R(0), k4x, k4y, k4z);
-        const R sixth = R(1.0 / 6.0);
-        ix = (k1x + R(2) * (k2x + k3x) + k4x) * sixth;
-        iy = (k1y + R(2) * (k2y + k3y) + k4y) * sixth;
-        iz = (k1z + R(2) * (k2z + k3z) + k4z) * sixth;
-    }
-    mdx += (double)ix;
-    mdy += (double)iy;
-    mdz += (double)iz;
-    guard_normalise<R>(mdx, mdy, mdz, guard);
-}
-
-// ---- FP32 stages with a block-scaled transverse state (easy axis == z^, no thermal field) ------------------------------
+// ---- block-scaled state ----------------------------------------------------------------------------------------------------
 // Without noise the magnetisation converges onto a pole exponentially (transverse components reach 1e-100 and below within
 // a few env steps) and the reference, being FP64, regrows them from there when the current reverses. A float cannot hold
-// anything below ~1e-38, so the FP32 variant carries the transverse pair multiplied by a power of two S = 1/inv_s:
-// every term of k_x, k_y is linear in (m_x, m_y) (so it comes out scaled by S for free) and every term of k_z is quadratic
-// (so it is multiplied back by inv_s^2, which simply underflows to 0 when the pair is negligible against m_z = +-1).
-// With inv_s == 1 the arithmetic is identical to substep<float, true, false, EULER>.
+// anything below ~1e-38, so the FP32 axis-z variants carry the transverse pair multiplied by a power of two S = 1/inv_s:
+// every term of k_x, k_y is linear in (m_x, m_y) (it comes out scaled by S for free) and k_z is quadratic (it is multiplied
+// back by inv_s^2, which simply underflows to 0 when the pair is negligible against m_z = +-1). With inv_s == 1 nothing
+// changes. Every other variant keeps inv_s == 1.
 struct ScaledState {
     double sx, sy, z;      // S*m_x, S*m_y, m_z
     double inv_s;          // 1/S, a power of two <= 1
@@ -298,40 +334,129 @@ STG_HD void rescale(ScaledState& st) {
     st.inv_s2f = (float)st.inv_s2d;
 }
 
-template <bool EULER>
-STG_HD void substep_scaled(const StepConsts<float>& c, ScaledState& st, float a1, float a2, float a3, float a4, int& guard) {
-    const float mx = (float)st.sx, my = (float)st.sy, mz = (float)st.z;
-    const float q = st.inv_s2f;
-    float k1x, k1y, k1z;
-    stage<float, true, false>(c, mx, my, mz, a1, 0.f, 0.f, 0.f, k1x, k1y, k1z);
-    k1z *= q;
-    float ix, iy, iz;
-    if (EULER) {
-        ix = k1x; iy = k1y; iz = k1z;
-    } else {
-        float k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
-        stage<float, true, false>(c, mx + 0.5f * k1x, my + 0.5f * k1y, mz + 0.5f * k1z, a2, 0.f, 0.f, 0.f, k2x, k2y, k2z);
-        k2z *= q;
-        stage<float, true, false>(c, mx + 0.5f * k2x, my + 0.5f * k2y, mz + 0.5f * k2z, a3, 0.f, 0.f, 0.f, k3x, k3y, k3z);
-        k3z *= q;
-        stage<float, true, false>(c, mx + k3x, my + k3y, mz + k3z, a4, 0.f, 0.f, 0.f, k4x, k4y, k4z);
-        k4z *= q;
-        const float sixth = 1.0f / 6.0f;
-        ix = (k1x + 2.0f * (k2x + k3x) + k4x) * sixth;
-        iy = (k1y + 2.0f * (k2y + k3y) + k4y) * sixth;
-        iz = (k1z + 2.0f * (k2z + k3z) + k4z) * sixth;
-    }
-    st.sx += (double)ix;
-    st.sy += (double)iy;
-    st.z += (double)iz;
+// Guard + normalise of the FP64 master (physics/simple_solver.py:208-229): non-finite or |m| < 1e-12 -> (0,0,1) + guard flag.
+template <typename R>
+STG_HD void guard_normalise(ScaledState& st, int& guard) {
     const double n2 = st.z * st.z + (st.sx * st.sx + st.sy * st.sy) * st.inv_s2d;
     if (n2 >= 1e-24 && n2 <= 1.0e300) {
-        const double inv = inv_norm<float>(n2);
+        const double inv = inv_norm<R>(n2);
         st.sx *= inv; st.sy *= inv; st.z *= inv;
     } else {
         st.sx = 0.0; st.sy = 0.0; st.z = 1.0;
         st.inv_s = 1.0; st.inv_s2d = 1.0; st.inv_s2f = 1.0f;
         guard = 1;
+    }
+}
+template <typename R>
+STG_HD void guard_normalise(double& mx, double& my, double& mz, int& guard) {
+    ScaledState st{mx, my, mz, 1.0, 1.0, 1.0f};
+    guard_normalise<R>(st, guard);
+    mx = st.sx; my = st.sy; mz = st.z;
+}
+
+// ---- reference-structure substep: FP64 master renormalised exactly after every substep ----------------------------------
+// Used by the FP64 variants, the general-axis variants and Euler. aH/aL: aJ*dt (hi, lo) seen by the stages (pulse gating:
+// [0] stage 1, [1] stages 2 and 3, [2] stage 4). nz: 12 (rk4) / 3 (euler) noise rotation components, already scaled by cth.
+template <typename R, bool AXIS_Z, bool THERMAL, bool EULER>
+STG_HD void substep_ref(const StepConsts<R>& c, ScaledState& st, const R* aH, const R* aL, const R* nz, int& guard) {
+    constexpr bool SCALED = AXIS_Z && !THERMAL && sizeof(R) == 4;
+    const R mx = (R)st.sx, my = (R)st.sy, mz = (R)st.z;
+    const R q = SCALED ? (R)st.inv_s2f : R(1);
+    auto f = [&](R x, R y, R z, int g, int s, R& kx, R& ky, R& kz) {
+        if (AXIS_Z) {
+            stage_z<R, SCALED>(c, x, y, z, aH[g], aL[g], q, kx, ky, kz);
+            if (THERMAL) stage_noise<R>(c, x, y, z, nz[3 * s], nz[3 * s + 1], nz[3 * s + 2], kx, ky, kz);
+        } else {
+            stage_general<R, THERMAL>(c, x, y, z, aH[g], aL[g], THERMAL ? nz[3 * s] : R(0), THERMAL ? nz[3 * s + 1] : R(0),
+                                      THERMAL ? nz[3 * s + 2] : R(0), kx, ky, kz);
+        }
+    };
+    R k1x, k1y, k1z;
+    f(mx, my, mz, 0, 0, k1x, k1y, k1z);
+    R ix, iy, iz;
+    if (EULER) {
+        ix = k1x; iy = k1y; iz = k1z;
+    } else {
+        const R h = R(0.5);
+        R k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
+        f(mx + h * k1x, my + h * k1y, mz + h * k1z, 1, 1, k2x, k2y, k2z);
+        f(mx + h * k2x, my + h * k2y, mz + h * k2z, 1, 2, k3x, k3y, k3z);
+        f(mx + k3x, my + k3y, mz + k3z, 2, 3, k4x, k4y, k4z);
+        ix = k1x + R(2) * (k2x + k3x) + k4x;
+        iy = k1y + R(2) * (k2y + k3y) + k4y;
+        iz = k1z + R(2) * (k2z + k3z) + k4z;
+    }
+    const double w = EULER ? 1.0 : (1.0 / 6.0);
+    st.sx += w * (double)ix;
+    st.sy += w * (double)iy;
+    st.z += w * (double)iz;
+    guard_normalise<R>(st, guard);
+}
+
+// ---- fast RK4 substep: FP32 stages, e = z^ -------------------------------------------------------------------------------
+// Working copy (fx, fy, fz) in FP32, master in FP64. All constants carry the factor 1/6 (k' = k/6), so
+//     stage inputs are  m + 3 k1', m + 3 k2', m + 6 k3'  and the increment is  k1' + 2 (k2' + k3') + k4'.
+// The per-substep renormalisation m/|m| of the reference is applied as a first-order-exact correction computed in FP32:
+//     d = |m + inc|^2 - 1 = inc . (2 m + inc),   1/sqrt(1+d) - 1 = rho(d),   m_new = m + [inc + rho (m + inc)]
+// and only the bracket (small) is added to the FP64 master, so the master keeps ~1e-15 resolution while no FP64 sqrt/div
+// and only three F2F conversions are needed per substep. Every 8 substeps the master is renormalised exactly in FP64 and
+// the working copy is refreshed from it (integrate_fast below), which bounds the drift of both.
+struct FastState {
+    ScaledState st;
+    float fx, fy, fz, q;
+};
+STG_HD void fast_resync(FastState& s) {
+    s.fx = (float)s.st.sx; s.fy = (float)s.st.sy; s.fz = (float)s.st.z; s.q = s.st.inv_s2f;
+}
+
+template <bool THERMAL, bool SCALED>
+STG_HD void substep_fast(const StepConsts<float>& c, FastState& s, float aH1, float aL1, float aH2, float aL2, float aH4,
+                         float aL4, const float* nz, int& guard) {
+    const float fx = s.fx, fy = s.fy, fz = s.fz, q = s.q;
+    float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
+    stage_z<float, SCALED>(c, fx, fy, fz, aH1, aL1, q, k1x, k1y, k1z);
+    if (THERMAL) stage_noise<float>(c, fx, fy, fz, nz[0], nz[1], nz[2], k1x, k1y, k1z);
+    {
+        const float x = fx + 3.0f * k1x, y = fy + 3.0f * k1y, z = fz + 3.0f * k1z;
+        stage_z<float, SCALED>(c, x, y, z, aH2, aL2, q, k2x, k2y, k2z);
+        if (THERMAL) stage_noise<float>(c, x, y, z, nz[3], nz[4], nz[5], k2x, k2y, k2z);
+    }
+    {
+        const float x = fx + 3.0f * k2x, y = fy + 3.0f * k2y, z = fz + 3.0f * k2z;
+        stage_z<float, SCALED>(c, x, y, z, aH2, aL2, q, k3x, k3y, k3z);
+        if (THERMAL) stage_noise<float>(c, x, y, z, nz[6], nz[7], nz[8], k3x, k3y, k3z);
+    }
+    {
+        const float x = fx + 6.0f * k3x, y = fy + 6.0f * k3y, z = fz + 6.0f * k3z;
+        stage_z<float, SCALED>(c, x, y, z, aH4, aL4, q, k4x, k4y, k4z);
+        if (THERMAL) stage_noise<float>(c, x, y, z, nz[9], nz[10], nz[11], k4x, k4y, k4z);
+    }
+    const float ix = k1x + 2.0f * (k2x + k3x) + k4x;
+    const float iy = k1y + 2.0f * (k2y + k3y) + k4y;
+    const float iz = k1z + 2.0f * (k2z + k3z) + k4z;
+    const float ux = fx + ix, uy = fy + iy, uz = fz + iz;                 // un-normalised new vector
+    const float dxy = ix * (fx + ux) + iy * (fy + uy);
+    const float d = SCALED ? iz * (fz + uz) + q * dxy : iz * (fz + uz) + dxy;
+    if (fabsf(d) < 0.015625f) {
+        // rho = (1+d)^(-1/2) - 1, |d| < 2^-6: truncation error < 0.28 d^4 = 1.6e-8 (relative to rho)
+        const float rho = d * (-0.5f + d * (0.375f + d * -0.3125f));
+        s.st.sx += (double)(ix + rho * ux);
+        s.st.sy += (double)(iy + rho * uy);
+        s.st.z += (double)(iz + rho * uz);
+#if STG_FAST_COPY_FROM_MASTER
+        s.fx = (float)s.st.sx; s.fy = (float)s.st.sy; s.fz = (float)s.st.z;
+#else
+        s.fx = ux + rho * ux;
+        s.fy = uy + rho * uy;
+        s.fz = uz + rho * uz;
+#endif
+    } else {
+        // large or non-finite norm change (diverging parameters): exact FP64 path with the reference's guard
+        s.st.sx += (double)ix;
+        s.st.sy += (double)iy;
+        s.st.z += (double)iz;
+        guard_normalise<float>(s.st, guard);
+        fast_resync(s);
     }
 }
 

@@ -8,6 +8,9 @@
 namespace stg {
 
 constexpr int kObs = 12;
+#ifndef STG_RESYNC_MASK
+#define STG_RESYNC_MASK 15   // exact FP64 renormalisation of the master every 16 substeps (fast path)
+#endif
 
 // ---- action -> (J, T) ------------------------------------------------------------------------------------------------
 // utils/monitoring.py:288-315 (float32 clips, NaN/Inf -> (0, 1e-12)) then envs/spin_torque_env.py:409-433 (FP64 clips)
@@ -25,86 +28,103 @@ STG_HD void parse_action(float a0, float a1, double max_current, double max_dura
     T = fmin(fmax((double)a1, 1e-12), max_duration);
 }
 
-template <typename R>
-STG_HD void make_consts(const double* f, double dt, double J, StepConsts<R>& c) {
-    double G = -f[FI_GEFF] * dt;
-    c.ck = (R)(G * f[FI_HK]);
-    c.cd = (R)(-G * f[FI_MS]);
-    c.cth = (R)(G * f[FI_HTH]);
-    c.alpha = (R)f[FI_ALPHA];
-    c.a_on = (fabs(J) > 1e-12) ? (R)(f[FI_AJ_PER_J] * J * dt) : R(0);   // physics/simple_solver.py:327-331
-    c.ex = (R)f[FI_EX]; c.ey = (R)f[FI_EY]; c.ez = (R)f[FI_EZ];
-    c.bax = (R)(G * f[FI_HAX]); c.bay = (R)(G * f[FI_HAY]); c.baz = (R)(G * f[FI_HAZ]);
-}
-
-// Integrate n substeps of size dt from (mx,my,mz); pulse of density J on while t <= t_pulse.
-// NOISE: 0 none, 1 Philox, 2 injected tensor. Traj: optional [n+1][3] FP64 rows.
+// Integrate n substeps of size dt from (mx,my,mz); pulse of density J on while t <= t_pulse (envs/spin_torque_env.py:442-443).
+// NOISE: 0 none, 1 Philox, 2 injected tensor [n][S][3]. traj: optional [n+1][3] FP64 rows.
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>
-STG_HD void integrate(const StepConsts<R>& c, double& mx, double& my, double& mz, int n, double dt,
-                                          double t_pulse, double t_end, const Philox& ph, uint64_t gid, uint32_t step_id,
-                                          const double* noise_row, double* traj, int& guard) {
+STG_HD void integrate(const double* f, double J, double& mx, double& my, double& mz, int n, double dt, double t_pulse,
+                      double t_end, const Philox& ph, uint64_t gid, uint32_t step_id, const double* noise_row, double* traj,
+                      int& guard) {
     constexpr bool TH = NOISE != 0;
-    // substeps whose four stage times are certainly inside the pulse run with constant a_on; the few around the pulse edge
+    constexpr bool FAST = sizeof(R) == 4 && AXIS_Z && !EULER;          // substep_fast (llgs_core.cuh)
+    constexpr bool SCALED = sizeof(R) == 4 && AXIS_Z && !TH;            // block-scaled transverse pair
+    constexpr int NS = EULER ? 3 : 12;
+    // substeps whose stage times are certainly inside the pulse run with the constant a; the few around the pulse edge
     // evaluate current_func(t) exactly in FP64 (the k4 stage of the LAST substep sees t_i+dt > T for ~16 % of f32 durations)
     int i_safe;
     if (t_pulse >= t_end) {
         i_safe = n - 1;
     } else {
-        double q = t_pulse / dt - 2.0;
-        i_safe = q < 0.0 ? 0 : (q > (double)n ? n : (int)q);
+        const double qd = t_pulse / dt - 2.0;
+        i_safe = qd < 0.0 ? 0 : (qd > (double)n ? n : (int)qd);
     }
     if (traj) { traj[0] = mx; traj[1] = my; traj[2] = mz; }
-    if constexpr (sizeof(R) == 4 && AXIS_Z && NOISE == 0) {
-        // FP32 stages, no noise: block-scaled transverse pair (llgs_core.cuh: ScaledState)
-        ScaledState st{mx, my, mz, 1.0, 1.0, 1.0f};
-        rescale(st);
-        for (int i = 0; i < n; ++i) {
-            float a1 = c.a_on, a2 = c.a_on, a3 = c.a_on, a4 = c.a_on;
-            if (i >= i_safe) {
-                a1 = pulse_on(i, 0, dt, t_pulse) ? c.a_on : 0.0f;
-                a2 = pulse_on(i, 1, dt, t_pulse) ? c.a_on : 0.0f;
-                a3 = a2;
-                a4 = pulse_on(i, 2, dt, t_pulse) ? c.a_on : 0.0f;
+
+    if constexpr (FAST) {
+        StepConsts<float> c;
+        make_consts<float>(f, dt, J, 1.0 / 6.0, c);
+        const float nscale = -1.3862943611198906f * c.cth * c.cth;      // -2 ln2 * (G h_th / 6)^2
+        FastState s;
+        s.st = ScaledState{mx, my, mz, 1.0, 1.0, 1.0f};
+        if (SCALED) rescale(s.st);
+        fast_resync(s);
+        // one substep + the periodic exact renormalisation; `edge` substeps evaluate the pulse gate per stage
+        auto one = [&](int i, bool edge) {
+            float aH1 = c.a_hi, aL1 = c.a_lo, aH2 = c.a_hi, aL2 = c.a_lo, aH4 = c.a_hi, aL4 = c.a_lo;
+            if (edge) {
+                if (!pulse_on(i, 0, dt, t_pulse)) { aH1 = 0.0f; aL1 = 0.0f; }
+                if (!pulse_on(i, 1, dt, t_pulse)) { aH2 = 0.0f; aL2 = 0.0f; }
+                if (!pulse_on(i, 2, dt, t_pulse)) { aH4 = 0.0f; aL4 = 0.0f; }
             }
-            substep_scaled<EULER>(c, st, a1, a2, a3, a4, guard);
-            if ((i & 15) == 15) rescale(st);
+            float nz[12];
+            if (NOISE == 1) {
+                philox_normals12(ph, gid, step_id, (uint32_t)i, nscale, nz);
+            } else if (NOISE == 2) {
+#pragma unroll
+                for (int q = 0; q < 12; ++q) nz[q] = c.cth * (float)noise_row[(int64_t)i * 12 + q];
+            }
+            substep_fast<TH, SCALED>(c, s, aH1, aL1, aH2, aL2, aH4, aL4, TH ? nz : nullptr, guard);
+            if ((i & STG_RESYNC_MASK) == STG_RESYNC_MASK || traj) {
+                guard_normalise<float>(s.st, guard);      // exact FP64 renormalisation of the master
+                if (SCALED) rescale(s.st);
+                fast_resync(s);
+            }
+            if (traj) {
+                traj[3 * (i + 1) + 0] = s.st.sx * s.st.inv_s; traj[3 * (i + 1) + 1] = s.st.sy * s.st.inv_s;
+                traj[3 * (i + 1) + 2] = s.st.z;
+            }
+        };
+        int i = 0;
+        for (; i < i_safe; ++i) one(i, false);
+        for (; i < n; ++i) one(i, true);
+        guard_normalise<float>(s.st, guard);
+        mx = s.st.sx * s.st.inv_s; my = s.st.sy * s.st.inv_s; mz = s.st.z;
+    } else {
+        StepConsts<R> c;
+        make_consts<R>(f, dt, J, 1.0, c);
+        const float nscale = -1.3862943611198906f * (float)c.cth * (float)c.cth;
+        ScaledState st{mx, my, mz, 1.0, 1.0, 1.0f};
+        if (SCALED) rescale(st);
+        for (int i = 0; i < n; ++i) {
+            R aH[3] = {c.a_hi, c.a_hi, c.a_hi}, aL[3] = {c.a_lo, c.a_lo, c.a_lo};
+            if (i >= i_safe) {
+#pragma unroll
+                for (int g = 0; g < 3; ++g)
+                    if (!pulse_on(i, g, dt, t_pulse)) { aH[g] = R(0); aL[g] = R(0); }
+            }
+            R nz[NS];
+            if (NOISE == 1) {
+                if (EULER) {
+                    float z[4];
+                    philox_normals4(ph, gid, step_id, (uint32_t)i, 0u, nscale, z);
+                    nz[0] = (R)z[0]; nz[1] = (R)z[1]; nz[2] = (R)z[2];
+                } else {
+                    float z[12];
+                    philox_normals12(ph, gid, step_id, (uint32_t)i, nscale, z);
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) nz[q] = (R)z[q];
+                }
+            } else if (NOISE == 2) {
+#pragma unroll
+                for (int q = 0; q < NS; ++q) nz[q] = c.cth * (R)noise_row[(int64_t)i * NS + q];
+            }
+            substep_ref<R, AXIS_Z, TH, EULER>(c, st, aH, aL, TH ? nz : nullptr, guard);
+            if (SCALED && (i & 15) == 15) rescale(st);
             if (traj) {
                 traj[3 * (i + 1) + 0] = st.sx * st.inv_s; traj[3 * (i + 1) + 1] = st.sy * st.inv_s;
                 traj[3 * (i + 1) + 2] = st.z;
             }
         }
         mx = st.sx * st.inv_s; my = st.sy * st.inv_s; mz = st.z;
-        return;
-    }
-    for (int i = 0; i < n; ++i) {
-        R a1 = c.a_on, a2 = c.a_on, a3 = c.a_on, a4 = c.a_on;
-        if (i >= i_safe) {
-            a1 = pulse_on(i, 0, dt, t_pulse) ? c.a_on : R(0);
-            a2 = pulse_on(i, 1, dt, t_pulse) ? c.a_on : R(0);
-            a3 = a2;
-            a4 = pulse_on(i, 2, dt, t_pulse) ? c.a_on : R(0);
-        }
-        R xi[EULER ? 3 : 12];
-        if (NOISE == 1) {
-            if (EULER) {
-                float z[4];
-                philox_normals4(ph, gid, step_id, (uint32_t)i, 0u, z);
-                xi[0] = (R)z[0]; xi[1] = (R)z[1]; xi[2] = (R)z[2];
-            } else {
-                float z[12];
-                philox_normals12(ph, gid, step_id, (uint32_t)i, z);
-#pragma unroll
-                for (int q = 0; q < 12; ++q) xi[q] = (R)z[q];
-            }
-        } else if (NOISE == 2) {
-            constexpr int S = EULER ? 3 : 12;
-#pragma unroll
-            for (int q = 0; q < S; ++q) xi[q] = (R)noise_row[(int64_t)i * S + q];
-        }
-        substep<R, AXIS_Z, TH, EULER>(c, mx, my, mz, a1, a2, a3, a4, TH ? xi : nullptr, guard);
-        if (traj) {
-            traj[3 * (i + 1) + 0] = mx; traj[3 * (i + 1) + 1] = my; traj[3 * (i + 1) + 2] = mz;
-        }
     }
 }
 
@@ -188,17 +208,15 @@ STG_HD void env_step_body(const StgSttStepArgs& a, int64_t e, EnvStepResult& r) 
     const bool valid = f[FI_VALID] != 0.0 && (!AXIS_Z || f[FI_AXISZ] != 0.0);
     if (valid) {
         guard_normalise<R>(nx, ny, nz, guard);                                 // SimpleLLGSSolver.solve :119
-        StepConsts<R> c;
-        make_consts<R>(f, plan.dt, J, c);
         Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
         const uint64_t gid = a.env_offset + (uint64_t)e;
         const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
         // Philox stream position: (episode, step) packed so that every env-step of every episode is distinct
         const uint32_t step_id = ((uint32_t)a.state.episode[e] << 12) ^ (uint32_t)step;
         if (f[FI_HTH] > 0.0 || NOISE == 0) {
-            integrate<R, AXIS_Z, NOISE, EULER>(c, nx, ny, nz, plan.n, plan.dt, T, T, ph, gid, step_id, nrow, nullptr, guard);
+            integrate<R, AXIS_Z, NOISE, EULER>(f, J, nx, ny, nz, plan.n, plan.dt, T, T, ph, gid, step_id, nrow, nullptr, guard);
         } else {
-            integrate<R, AXIS_Z, 0, EULER>(c, nx, ny, nz, plan.n, plan.dt, T, T, ph, gid, step_id, nullptr, nullptr, guard);
+            integrate<R, AXIS_Z, 0, EULER>(f, J, nx, ny, nz, plan.n, plan.dt, T, T, ph, gid, step_id, nullptr, nullptr, guard);
         }
         // env-level renormalisation of the last trajectory row (envs/spin_torque_env.py:464)
         const double inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
@@ -309,17 +327,15 @@ STG_HD void solve_body(const StgSttSolveArgs& a, int64_t e) {
     if (t_end > 0.0 && (!AXIS_Z || f[FI_AXISZ] != 0.0)) {        // t_end <= t_start: trivial solution (:122-123)
         const StepPlan plan = substep_plan(t_end, f[FI_MAXSTEP_DT]);
         nsub = plan.n;
-        StepConsts<R> c;
-        make_consts<R>(f, plan.dt, J, c);
         Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
         const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
         double* traj = a.d_traj ? a.d_traj + (int64_t)e * a.traj_stride * 3 : nullptr;
         if (f[FI_HTH] > 0.0 || NOISE == 0)
-            integrate<R, AXIS_Z, NOISE, EULER>(c, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph, a.env_offset + (uint64_t)e,
-                                               0u, nrow, traj, guard);
+            integrate<R, AXIS_Z, NOISE, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph,
+                                               a.env_offset + (uint64_t)e, 0u, nrow, traj, guard);
         else
-            integrate<R, AXIS_Z, 0, EULER>(c, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph, a.env_offset + (uint64_t)e, 0u,
-                                           nullptr, traj, guard);
+            integrate<R, AXIS_Z, 0, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph, a.env_offset + (uint64_t)e,
+                                           0u, nullptr, traj, guard);
     }
     a.d_m_out[3 * e] = mx; a.d_m_out[3 * e + 1] = my; a.d_m_out[3 * e + 2] = mz;
     if (a.d_n_sub) a.d_n_sub[e] = nsub;

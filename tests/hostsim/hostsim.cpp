@@ -87,6 +87,7 @@ extern "C" void hostsim_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c
     ph(c0, c1, c2, c3, out);
 }
 extern "C" void hostsim_normals12(uint64_t seed, uint64_t gid, uint32_t step, uint32_t sub, float* out) {
+    const float unit = -1.3862943611198906f;
     Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
-    philox_normals12(ph, gid, step, sub, out);
+    philox_normals12(ph, gid, step, sub, unit, out);
 }
