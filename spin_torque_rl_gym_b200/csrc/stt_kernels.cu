@@ -171,6 +171,9 @@ static cudaError_t launch_step2(const StepArgs& a, cudaStream_t s) {
         stt_env_step_kernel<R, AXIS_Z, NOISE, false><<<grid, kBlock, 0, s>>>(a);
     return cudaGetLastError();
 }
+// FP32 stage arithmetic exists for the axis-aligned geometry only (compensated constants + block scaling, llgs_core.cuh).
+// A tilted easy axis / applied field always runs FP64 stages, also through the _f32 entry points: rounding the axis
+// components to 24 bits is a systematic rate error the 1e-4 contract does not survive over thousands of substeps.
 template <typename R>
 static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
     const int noise = (a.flags & STG_F_THERMAL_INJECT) ? 2 : ((a.flags & STG_F_THERMAL_PHILOX) ? 1 : 0);
@@ -179,9 +182,9 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
         if (noise == 1) return launch_step2<R, true, 1>(a, s);
         return launch_step2<R, true, 2>(a, s);
     }
-    if (noise == 0) return launch_step2<R, false, 0>(a, s);
-    if (noise == 1) return launch_step2<R, false, 1>(a, s);
-    return launch_step2<R, false, 2>(a, s);
+    if (noise == 0) return launch_step2<double, false, 0>(a, s);
+    if (noise == 1) return launch_step2<double, false, 1>(a, s);
+    return launch_step2<double, false, 2>(a, s);
 }
 
 template <typename R, bool AXIS_Z, int NOISE>
@@ -201,9 +204,9 @@ static cudaError_t launch_solve(const SolveArgs& a, uint32_t flags, bool axis_z,
         if (noise == 1) return launch_solve2<R, true, 1>(a, flags, s);
         return launch_solve2<R, true, 2>(a, flags, s);
     }
-    if (noise == 0) return launch_solve2<R, false, 0>(a, flags, s);
-    if (noise == 1) return launch_solve2<R, false, 1>(a, flags, s);
-    return launch_solve2<R, false, 2>(a, flags, s);
+    if (noise == 0) return launch_solve2<double, false, 0>(a, flags, s);
+    if (noise == 1) return launch_solve2<double, false, 1>(a, flags, s);
+    return launch_solve2<double, false, 2>(a, flags, s);
 }
 
 }  // namespace stg

@@ -45,7 +45,7 @@ extern "C" int hostsim_stt_step(const StgSttStepArgs* a, int f64) {
     FtzScope ftz(!f64);
     const bool z = (a->flags & STG_F_AXIS_Z) != 0;
     if (f64) { if (z) step_noise<double, true>(*a); else step_noise<double, false>(*a); }
-    else     { if (z) step_noise<float, true>(*a);  else step_noise<float, false>(*a); }
+    else     { if (z) step_noise<float, true>(*a);  else step_noise<double, false>(*a); }   // as launch_step<> dispatches
     return 0;
 }
 
@@ -72,7 +72,7 @@ extern "C" int hostsim_stt_solve(const StgSttSolveArgs* a, int f64) {
     FtzScope ftz(!f64);
     const bool z = (a->flags & STG_F_AXIS_Z) != 0;
     if (f64) { if (z) solve_noise<double, true>(*a); else solve_noise<double, false>(*a); }
-    else     { if (z) solve_noise<float, true>(*a);  else solve_noise<float, false>(*a); }
+    else     { if (z) solve_noise<float, true>(*a);  else solve_noise<double, false>(*a); }
     return 0;
 }
 

@@ -252,10 +252,11 @@ def test_full_size_properties(cuda_device):
     assert torch.equal(torch.cat(parts), o)
     # different seed -> different thermal stream
     env3 = _make(n, "f32", cuda_device, **dict(kw, rng_seed=8))
-    env3.reset(seed=7)
-    env3._m.copy_(torch.as_tensor(m_before.t().contiguous()))
+    env3.reset(seed=8)                                  # reset(seed) re-keys the Philox stream
+    env3._m.copy_(m_before.t().contiguous())
+    env3._target.copy_(env2._target)
     o3, *_ = env3.step(act)
-    assert not torch.equal(o3, o)
+    assert not torch.equal(o3[:, :3], o[:, :3])
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
