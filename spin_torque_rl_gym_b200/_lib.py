@@ -100,7 +100,8 @@ class StgError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # STG_LIB_PATH: load an alternative build of libstg.so (kernel tuning experiments); default is the in-tree library
+    return os.environ.get("STG_LIB_PATH") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:
@@ -109,7 +110,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if _LIB is not None:
         return _LIB
     path = lib_path()
-    if build_if_missing and _build.needs_build():
+    if build_if_missing and path == _build.LIB_PATH and _build.needs_build():
         try:
             _build.build()
         except Exception as exc:  # a stale but present library is still usable on a box without nvcc

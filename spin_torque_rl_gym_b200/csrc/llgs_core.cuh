@@ -76,7 +76,9 @@ struct Philox {
 // ---- fast device intrinsics (MUFU) with libm fallbacks for the host build ---------------------------------------------
 STG_HD float fast_lg2(float x) {
 #if defined(__CUDA_ARCH__)
-    return __log2f(x);
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // x >= 2^-33 here: no denormal fix-up needed
+    return r;
 #else
     return log2f(x);
 #endif
@@ -90,8 +92,7 @@ STG_HD float fast_sqrt(float x) {
     return sqrtf(x);
 #endif
 }
-STG_HD void fast_sincos_rev(float rev, float& s, float& c) {   // angle given in revolutions [0,1)
-    const float ang = rev * 6.283185307179586f;
+STG_HD void fast_sincos(float ang, float& s, float& c) {   // angle in radians, [0, 2 pi)
 #if defined(__CUDA_ARCH__)
     s = __sinf(ang);
     c = __cosf(ang);
@@ -100,13 +101,14 @@ STG_HD void fast_sincos_rev(float rev, float& s, float& c) {   // angle given in
     c = cosf(ang);
 #endif
 }
-STG_HD float bits_to_unit(uint32_t x) {   // top 23 bits -> [0,1) without an int->float conversion
+STG_HD float bits_to_angle(uint32_t x) {   // top 23 bits -> [0, 2 pi) without an int->float conversion (one FFMA)
+    const float twopi = 6.283185307179586f;
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(0x3f800000u | (x >> 9)) - 1.0f;
+    return fmaf(__uint_as_float(0x3f800000u | (x >> 9)), twopi, -twopi);
 #else
     union { uint32_t u; float f; } v;
     v.u = 0x3f800000u | (x >> 9);
-    return v.f - 1.0f;
+    return fmaf(v.f, twopi, -twopi);
 #endif
 }
 
@@ -118,7 +120,7 @@ STG_HD void box_muller_scaled(uint32_t u0, uint32_t u1, float neg2ln2_scale2, fl
     const float a = fmaf((float)u0, two_m32, 0.5f * two_m32);   // (0, 1]
     const float r = fast_sqrt(neg2ln2_scale2 * fast_lg2(a));
     float s, c;
-    fast_sincos_rev(bits_to_unit(u1), s, c);
+    fast_sincos(bits_to_angle(u1), s, c);
     n0 = r * c;
     n1 = r * s;
 }

@@ -19,7 +19,13 @@
 
 namespace stg {
 
-constexpr int kBlock = 64;      // 65,536 envs -> 1024 CTAs = 6.9 per SM: balanced to 1.2 % on 148 SMs
+#ifndef STG_BLOCK
+#define STG_BLOCK 64
+#endif
+#ifndef STG_MINBLOCKS
+#define STG_MINBLOCKS 1
+#endif
+constexpr int kBlock = STG_BLOCK;   // 64: 65,536 envs -> 1024 CTAs = 6.9 per SM, balanced to 1.2 % on 148 SMs
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -39,7 +45,7 @@ __device__ __forceinline__ void store_row(float* dst, const float* o) {
 }
 
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>
-__global__ void __launch_bounds__(kBlock) stt_env_step_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kBlock, STG_MINBLOCKS) stt_env_step_kernel(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) float s_obs[kBlock * kObs];
     const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool active = slot < a.n_envs;
