@@ -222,6 +222,116 @@ int stg_stt_sort_by_substeps(const StgSttFolded* d_table, int32_t n_sets, const 
 int stg_stt_solve_f32(const StgSttSolveArgs* args, void* stream);
 int stg_stt_solve_f64(const StgSttSolveArgs* args, void* stream);
 
+/* ---- K2: adaptive RK45 (SciPy-compatible Dormand-Prince 5(4)) on the generalised LLGS right-hand side --------------------
+ * One parameter set of the generalised RHS (FP64). LLGSSolver form (physics/llgs_solver.py:92-126, 182-237):
+ *   H   = H_app + (2K/(mu0 Ms)) (m.e) e - Ms N (.) m + exchange_coeff m + h_th xi
+ *   tau = J [ c_dl_p m x (m x p) + c_fl_p (m x p) + c_dl_s (sigma x m) + c_fl_s sigma ]      (0 when |J| < 1e-12)
+ *   dm  = -gamma m x H;  dm += alpha m x dm;  dm += tau                     with m = y/|y| inside the RHS
+ * STT (LLGSSolver._compute_spin_torques): c_dl_p = P gamma/(2 Ms V), c_fl_p = 0.1 c_dl_p, p = z^.
+ * SOT (devices/sot_mram.py:163-194): c_dl_s / c_fl_s = tau_dl_factor / tau_fl_factor, sigma = z^ x J^.
+ * VCMA (devices/vcma_mram.py:122-147): use_vcma = 1, K = K_eff(V) from the per-env voltage. */
+typedef struct StgLlgParams {
+    double gamma;
+    double mu0;
+    double alpha;
+    double saturation_magnetization;
+    double uniaxial_anisotropy;
+    double volume;
+    double easy_axis[3];             /* used as given (LLGSSolver does not normalise it)                          */
+    double demag_n[3];               /* params['demag_factors'] (default 0,0,1) or N(aspect_ratio)                */
+    double exchange_coeff;           /* (2 A_ex/(mu0 Ms))*0.1 if A_ex > 0 else 0 (physics/llgs_solver.py:204-209) */
+    double h_th;                     /* sqrt(2 alpha k_B T/(gamma mu0 Ms V)), k_B = 1.380649e-23; 0 = no noise    */
+    double c_dl_p, c_fl_p;
+    double p_hat[3];
+    double c_dl_s, c_fl_s;
+    double sigma[3];
+    double vcma_coefficient, dielectric_thickness, breakdown_voltage;
+    int32_t use_vcma;
+    int32_t reserved;
+} StgLlgParams;
+
+/* Argument block of a batched LLGSSolver.solve(m_initial, (0, t_end), params, current_func, field_func, thermal_noise,
+ * temperature) with current_func(t) = J if t <= t_pulse else 0 and a constant H_app per trajectory.
+ *   d_table [n_sets] (DEVICE copy of StgLlgParams), d_param_index [n] or NULL
+ *   d_m0 [n][3]; d_t_end [n]; d_current [n] or NULL; d_t_pulse [n] or NULL (= always on); d_happ [n][3] or NULL;
+ *   d_voltage [n] or NULL
+ *   outputs: d_y_out [n][3] raw end state (sol.y[:, -1]); d_n_accepted / d_n_rejected / d_n_rhs / d_status [n] int32
+ *            (status bit0 step size too small (SciPy failure), bit1 trajectory buffer overflow, bit2 max_attempts reached,
+ *            bit3 non-finite error norm); d_t_reached [n];
+ *            d_traj NULL or [n][traj_stride][6] rows (t, m_x, m_y, m_z normalised, energy, |tau_DL|+|tau_FL|) for row 0 (t=0)
+ *            and every accepted step, as LLGSSolver returns them (physics/llgs_solver.py:146-180)
+ *   thermal: STG_F_THERMAL_PHILOX (counter = RHS evaluation index) or STG_F_THERMAL_INJECT with d_noise [n][noise_stride][3]
+ *            consumed one row per RHS evaluation in call order (select_initial_step's two evaluations included). */
+typedef struct StgRk45Args {
+    const StgLlgParams* d_table;
+    const int32_t* d_param_index;
+    const double* d_m0;
+    const double* d_t_end;
+    const double* d_current;
+    const double* d_t_pulse;
+    const double* d_happ;
+    const double* d_voltage;
+    double* d_y_out;
+    int32_t* d_n_accepted;
+    int32_t* d_n_rejected;
+    int32_t* d_n_rhs;
+    int32_t* d_status;
+    double* d_t_reached;
+    double* d_traj;
+    int64_t traj_stride;
+    const double* d_noise;
+    int64_t noise_stride;
+    double rtol, atol, max_step;
+    int64_t max_attempts;            /* safety bound on attempted steps per trajectory (0 = 1e6)                  */
+    uint64_t seed;
+    uint64_t env_offset;
+    int64_t n_envs;
+    int32_t n_sets;
+    uint32_t flags;
+} StgRk45Args;
+
+int stg_llgs_rk45_f64(const StgRk45Args* args, void* stream);
+
+/* ---- K4: batched device-class operations (FP64, one row per device state) -------------------------------------------------
+ * Host struct passed by pointer; mirrors what the reference's device constructors cache (devices/sot_mram.py:61-76,
+ * devices/vcma_mram.py:60-84). easy_axis is used AS GIVEN (the device methods do not normalise it);
+ * reference_magnetization must already be normalised by the caller. */
+typedef struct StgDeviceParams {
+    int32_t kind;                    /* STG_DEV_*                                                                 */
+    int32_t reserved;
+    double saturation_magnetization;
+    double uniaxial_anisotropy;
+    double mu0;                      /* 4*pi*1e-7 (devices/base_device.py:30)                                     */
+    double easy_axis[3];
+    double demag_n[3];               /* (N_x, N_y, N_z) of devices/sot_mram.py:114-132; zeros for STT             */
+    double vcma_coefficient;         /* VCMA: xi [J/(V m)]                                                        */
+    double dielectric_thickness;     /* VCMA: t_d [m]                                                             */
+    double breakdown_voltage;        /* VCMA: V_bd [V]                                                            */
+    double tau_dl_factor;            /* SOT: damping_like_efficiency * j_s_efficiency                             */
+    double tau_fl_factor;            /* SOT: field_like_efficiency * j_s_efficiency                               */
+    double resistance_parallel;
+    double resistance_antiparallel;
+    double reference_magnetization[3];
+    double series_resistance;        /* SOT: 0.1 * sheet_resistance_hm / (area*1e-12)                             */
+} StgDeviceParams;
+
+/* device.compute_effective_field(m, H_app[, V]) for n rows (devices/stt_mram.py:56-76, sot_mram.py:78-112,
+ * vcma_mram.py:86-120). d_happ: NULL (zero), 1 row (broadcast) or n rows; d_voltage: VCMA only, NULL = 0 V. */
+int stg_device_field_f64(const StgDeviceParams* p, const double* d_m, const double* d_happ, int32_t happ_rows,
+                         const double* d_voltage, double* d_out, int64_t n, void* stream);
+/* device.compute_resistance(m) (devices/stt_mram.py:78-94, sot_mram.py:196-228, vcma_mram.py:236-257). */
+int stg_device_resistance_f64(const StgDeviceParams* p, const double* d_m, double* d_out, int64_t n, void* stream);
+/* SOTMRAMDevice.compute_spin_torque(J, m, direction) (devices/sot_mram.py:163-194); current_direction: 3 host doubles. */
+int stg_device_sot_torque_f64(const StgDeviceParams* p, const double* d_current, int32_t current_rows, const double* d_m,
+                              const double* current_direction, double* d_tau_dl, double* d_tau_fl, int64_t n, void* stream);
+/* VCMAMRAMDevice._compute_effective_anisotropy(V) (devices/vcma_mram.py:122-147). */
+int stg_vcma_anisotropy_f64(const StgDeviceParams* p, const double* d_voltage, double* d_out, int64_t n, void* stream);
+/* ThermalFluctuations.generate_thermal_field (physics/thermal_model.py:75-137) for n devices: white noise (d_state NULL)
+ * or Ornstein-Uhlenbeck x <- decay*x + sqrt(1-decay^2)*xi on d_state [n][3]; out = strength * x. Philox counter =
+ * (offset + row, call_index). */
+int stg_thermal_field_f64(double strength, double decay, double* d_state, double* d_out, uint64_t seed, uint64_t offset,
+                          uint64_t call_index, int64_t n, void* stream);
+
 /* FMA-pipe throughput probe (bench.py's measured FP32/FP64 roofline denominator): blocks*256 threads x iters*64 FMAs.
  * d_out: >= blocks*256 elements of the probed type (never written in practice). */
 int stg_probe_fma(void* d_out, int32_t blocks, int32_t iters, int32_t f64, void* stream);

@@ -184,6 +184,103 @@ def gen_multi():
     print("wrote stt_multi.npz")
 
 
+def gen_devices():
+    """Device-class methods of the reference on random inputs (devices/stt_mram.py, sot_mram.py, vcma_mram.py)."""
+    _import_reference()
+    from spin_torque_gym.devices import DeviceFactory
+    from spin_torque_gym.physics import ThermalFluctuations
+    fac = DeviceFactory()
+    rng = np.random.default_rng(11)
+    n = 48
+    m = rng.normal(size=(n, 3))
+    m[: n // 2] /= np.linalg.norm(m[: n // 2], axis=1, keepdims=True)      # half normalised, half not
+    happ = rng.normal(size=(n, 3)) * 1e4
+    volt = rng.uniform(-3.0, 3.0, n)
+    cur = rng.uniform(-2e6, 2e6, n)
+    out = dict(m=m, happ=happ, volt=volt, cur=cur)
+    variants = {
+        'stt': ('stt_mram', dict(easy_axis=np.array([0.0, 0.6, 0.8]), reference_magnetization=np.array([0.0, 1.0, 1.0]))),
+        'sot': ('sot_mram', dict(aspect_ratio=2.5, spin_hall_angle=0.3, reference_magnetization=np.array([1.0, 0.0, 1.0]))),
+        'sot_ar': ('sot_mram', dict(aspect_ratio=0.4)),
+        'vcma': ('vcma_mram', dict(aspect_ratio=1.7, vcma_coefficient=80e-6, breakdown_voltage=1.5)),
+    }
+    for key, (dtype, over) in variants.items():
+        p = fac.get_default_parameters(dtype)
+        p.update(over)
+        dev = fac.create_device(dtype, p)
+        if dtype == 'vcma_mram':
+            out[f'{key}/field'] = np.array([dev.compute_effective_field(m[i], happ[i], volt[i]) for i in range(n)])
+            out[f'{key}/keff'] = np.array([dev._compute_effective_anisotropy(v) for v in volt])
+            out[f'{key}/power'] = np.array([dev.compute_power_consumption(v, 1e-9) for v in volt])
+            out[f'{key}/pswitch'] = np.array([dev.compute_switching_probability(v, 1e-9) for v in volt])
+        else:
+            out[f'{key}/field'] = np.array([dev.compute_effective_field(m[i], happ[i]) for i in range(n)])
+        out[f'{key}/resistance'] = np.array([dev.compute_resistance(m[i]) for i in range(n)])
+        if dtype == 'sot_mram':
+            d = np.array([1.0, 2.0, 0.0])
+            t = [dev.compute_spin_torque(cur[i], m[i], d) for i in range(n)]
+            out[f'{key}/tau_dl'] = np.array([x[0] for x in t])
+            out[f'{key}/tau_fl'] = np.array([x[1] for x in t])
+            t = [dev.compute_spin_torque(cur[i], m[i]) for i in range(n)]
+            out[f'{key}/tau_dl_default'] = np.array([x[0] for x in t])
+            out[f'{key}/power'] = np.array([dev.compute_power_consumption(cur[i], 1e-9, m[i]) for i in range(n)])
+        for k, v in over.items():
+            out[f'{key}/param/{k}'] = np.asarray(v)
+    th = ThermalFluctuations(temperature=350.0, correlation_time=2e-12, seed=1)
+    out['thermal/strength'] = th.compute_noise_strength(0.01, 800e3, 1e-23)
+    out['thermal/barrier'] = th.compute_thermal_barrier(1.2e6, 1e-23)
+    out['thermal/pswitch'] = th.compute_switching_probability(1.2e6 * 1e-23 * 0.05)
+    out['thermal/retention'] = th.compute_retention_time(1.2e6 * 1e-23 * 0.05)
+    np.savez_compressed(os.path.join(GOLD, "devices.npz"), **out)
+    print("wrote devices.npz")
+
+
+def gen_rk45():
+    """LLGSSolver.solve of the live reference (SciPy RK45, rtol 1e-6, atol 1e-9, max_step 1e-12)."""
+    _import_reference()
+    from spin_torque_gym.physics.llgs_solver import LLGSSolver
+    solver = LLGSSolver(method='RK45', rtol=1e-6, atol=1e-9, max_step=1e-12)
+    rng = np.random.default_rng(5)
+    out = {}
+    # LLGSSolver's torque prefactor is P*gamma/(2 Ms V) * J: with V = 1e-11 m^3 a current of ~10 A/m^2 gives a torque rate of
+    # ~1e11 1/s, comparable to the precession rate; at action-scale currents SciPy's step size collapses (SURVEY 3.4)
+    base = _stt_params(volume=1e-23 * 1e12)
+    cases = {
+        'stt_on': dict(params=base, J=12.0, t_pulse=1e9, t_end=1.5e-10, happ=np.zeros(3)),
+        'stt_pulse': dict(params=base, J=-15.0, t_pulse=6e-11, t_end=1.6e-10, happ=np.array([2e4, -1e4, 5e3])),
+        'stt_nocurrent': dict(params=dict(base, demag_factors=np.array([0.1, 0.2, 0.7])), J=0.0, t_pulse=1e9, t_end=1e-10,
+                              happ=np.array([0.0, 3e4, 0.0])),
+        'stt_tilted': dict(params=dict(base, easy_axis=np.array([0.3, 0.0, 0.9]), exchange_constant=0.0, damping=0.05),
+                           J=8.0, t_pulse=1e9, t_end=1.2e-10, happ=np.zeros(3)),
+        'stt_short': dict(params=base, J=20.0, t_pulse=1e9, t_end=2.5e-12, happ=np.zeros(3)),
+    }
+    for name, c in cases.items():
+        m0 = rng.normal(0, 1, 3)
+        J, tp, happ = c['J'], c['t_pulse'], c['happ']
+        res = solver.solve(m0, (0, c['t_end']), c['params'], lambda t: J if t <= tp else 0.0, lambda t: happ,
+                           thermal_noise=False)
+        for k in ('t', 'm', 'energy', 'torques'):
+            out[f'{name}/{k}'] = np.asarray(res[k])
+        out[f'{name}/success'] = res['success']
+        out[f'{name}/m0'] = m0
+        out[f'{name}/J'] = J; out[f'{name}/t_pulse'] = tp; out[f'{name}/t_end'] = c['t_end']; out[f'{name}/happ'] = happ
+        for k, v in c['params'].items():
+            if k in ('volume', 'easy_axis', 'demag_factors', 'exchange_constant', 'damping'):
+                out[f'{name}/param/{k}'] = np.asarray(v)
+        print(name, len(res['t']), res['success'], flush=True)
+    # thermal: the global NumPy stream is consumed one normal(0,1,3) per RHS call
+    m0 = rng.normal(0, 1, 3)
+    np.random.seed(77)
+    res = solver.solve(m0, (0, 4e-11), base, lambda t: 10.0, lambda t: np.zeros(3), thermal_noise=True, temperature=300.0)
+    for k in ('t', 'm', 'energy', 'torques'):
+        out[f'stt_thermal/{k}'] = np.asarray(res[k])
+    out['stt_thermal/m0'] = m0; out['stt_thermal/seed'] = 77; out['stt_thermal/J'] = 10.0
+    out['stt_thermal/t_end'] = 4e-11; out['stt_thermal/param/volume'] = np.asarray(base['volume'])
+    print('stt_thermal', len(res['t']), flush=True)
+    np.savez_compressed(os.path.join(GOLD, "rk45.npz"), **out)
+    print("wrote rk45.npz")
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["stt", "multi", "array", "rk45", "devices"]
     os.makedirs(GOLD, exist_ok=True)

@@ -76,6 +76,35 @@ class StgSttSolveArgs(C.Structure):
                 ("n_sets", C.c_int32), ("flags", C.c_uint32)]
 
 
+class StgDeviceParams(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("saturation_magnetization", C.c_double),
+                ("uniaxial_anisotropy", C.c_double), ("mu0", C.c_double), ("easy_axis", c_double3),
+                ("demag_n", c_double3), ("vcma_coefficient", C.c_double), ("dielectric_thickness", C.c_double),
+                ("breakdown_voltage", C.c_double), ("tau_dl_factor", C.c_double), ("tau_fl_factor", C.c_double),
+                ("resistance_parallel", C.c_double), ("resistance_antiparallel", C.c_double),
+                ("reference_magnetization", c_double3), ("series_resistance", C.c_double)]
+
+
+class StgLlgParams(C.Structure):
+    _fields_ = [("gamma", C.c_double), ("mu0", C.c_double), ("alpha", C.c_double),
+                ("saturation_magnetization", C.c_double), ("uniaxial_anisotropy", C.c_double), ("volume", C.c_double),
+                ("easy_axis", c_double3), ("demag_n", c_double3), ("exchange_coeff", C.c_double), ("h_th", C.c_double),
+                ("c_dl_p", C.c_double), ("c_fl_p", C.c_double), ("p_hat", c_double3), ("c_dl_s", C.c_double),
+                ("c_fl_s", C.c_double), ("sigma", c_double3), ("vcma_coefficient", C.c_double),
+                ("dielectric_thickness", C.c_double), ("breakdown_voltage", C.c_double), ("use_vcma", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class StgRk45Args(C.Structure):
+    _fields_ = [("d_table", C.c_void_p), ("d_param_index", C.c_void_p), ("d_m0", C.c_void_p), ("d_t_end", C.c_void_p),
+                ("d_current", C.c_void_p), ("d_t_pulse", C.c_void_p), ("d_happ", C.c_void_p), ("d_voltage", C.c_void_p),
+                ("d_y_out", C.c_void_p), ("d_n_accepted", C.c_void_p), ("d_n_rejected", C.c_void_p),
+                ("d_n_rhs", C.c_void_p), ("d_status", C.c_void_p), ("d_t_reached", C.c_void_p), ("d_traj", C.c_void_p),
+                ("traj_stride", C.c_int64), ("d_noise", C.c_void_p), ("noise_stride", C.c_int64), ("rtol", C.c_double),
+                ("atol", C.c_double), ("max_step", C.c_double), ("max_attempts", C.c_int64), ("seed", C.c_uint64),
+                ("env_offset", C.c_uint64), ("n_envs", C.c_int64), ("n_sets", C.c_int32), ("flags", C.c_uint32)]
+
+
 # every symbol include/stg.h declares: (name, restype, argtypes)
 SYMBOLS = {
     "stg_abi_version": (C.c_int, []),
@@ -89,6 +118,15 @@ SYMBOLS = {
                                            C.c_int64, C.c_void_p]),
     "stg_stt_solve_f32": (C.c_int, [C.POINTER(StgSttSolveArgs), C.c_void_p]),
     "stg_stt_solve_f64": (C.c_int, [C.POINTER(StgSttSolveArgs), C.c_void_p]),
+    "stg_llgs_rk45_f64": (C.c_int, [C.POINTER(StgRk45Args), C.c_void_p]),
+    "stg_device_field_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_int64, C.c_void_p]),
+    "stg_device_resistance_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "stg_device_sot_torque_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_int32, C.c_void_p,
+                                            C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "stg_vcma_anisotropy_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "stg_thermal_field_f64": (C.c_int, [C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                        C.c_uint64, C.c_int64, C.c_void_p]),
     "stg_probe_fma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 

@@ -1,0 +1,259 @@
+// rk45_core.cuh — K2: adaptive Dormand-Prince 5(4) integration of the generalised LLGS right-hand side, one trajectory
+// per thread, with SciPy's RK45 step-size controller reproduced decision for decision.
+//
+// Replaces LLGSSolver.solve (physics/llgs_solver.py:51-180 of the reference), whose arithmetic lives in the third-party
+// dependency scipy.integrate.solve_ivp (pyproject pins scipy>=1.7.0; 1.18.1 installed): scipy/integrate/_ivp/rk.py
+// (rk_step :14-72, RungeKutta._step_impl :111-167, RK45 tableau :281-378), common.py (select_initial_step :68-133, norm :63).
+// Controller constants: SAFETY 0.9, MIN_FACTOR 0.2, MAX_FACTOR 10, error exponent -1/5, RMS error norm against
+// atol + rtol*max(|y|,|y_new|), first step from select_initial_step, min_step = 10*ulp(t), last step clipped to t_bound,
+// no growth right after a rejected step. FP64 throughout (atol = 1e-9 is below FP32 resolution).
+#pragma once
+
+#include "../../include/stg.h"
+#include "llgs_core.cuh"
+
+namespace stg {
+
+struct Rk45Tableau {
+    // scipy/integrate/_ivp/rk.py:281-302 (Dormand & Prince 1980)
+    static constexpr double c2 = 1.0 / 5, c3 = 3.0 / 10, c4 = 4.0 / 5, c5 = 8.0 / 9;
+    static constexpr double a21 = 1.0 / 5;
+    static constexpr double a31 = 3.0 / 40, a32 = 9.0 / 40;
+    static constexpr double a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9;
+    static constexpr double a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729;
+    static constexpr double a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176,
+                            a65 = -5103.0 / 18656;
+    static constexpr double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
+    static constexpr double e1 = -71.0 / 57600, e3 = 71.0 / 16695, e4 = -71.0 / 1920, e5 = 17253.0 / 339200,
+                            e6 = -22.0 / 525, e7 = 1.0 / 40;
+};
+
+struct V3 {
+    double x, y, z;
+};
+STG_HD V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+STG_HD V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+STG_HD V3 cross3(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+STG_HD double dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+STG_HD double rms3(V3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z) / 1.7320508075688772; }   // common.py:63-65
+
+// per-trajectory inputs resolved from the parameter set + the per-env controls
+struct LlgRhs {
+    const StgLlgParams* p;
+    double hk;          // 2 K_eff /(mu0 Ms)
+    double J, t_pulse;
+    V3 happ;
+    // thermal
+    int noise_mode;     // 0 none, 1 Philox, 2 injected
+    Philox ph;
+    uint64_t gid;
+    const double* noise_row;
+    int64_t noise_cap;
+    int n_eval;
+
+    // llgs_rhs (physics/llgs_solver.py:92-126) generalised with the SOT terms (devices/sot_mram.py:163-194)
+    STG_HD V3 operator()(double t, V3 y) {
+        const StgLlgParams& q = *p;
+        V3 m = {0.0, 0.0, 1.0};                               // :96-101
+        const double nrm = sqrt(dot3(y, y));
+        if (nrm > 1e-12) { m.x = y.x / nrm; m.y = y.y / nrm; m.z = y.z / nrm; }
+        const double cur = (t <= t_pulse) ? J : 0.0;
+        const V3 e = {q.easy_axis[0], q.easy_axis[1], q.easy_axis[2]};
+        const double s = hk * dot3(m, e);
+        V3 h = {happ.x + s * e.x, happ.y + s * e.y, happ.z + s * e.z};
+        h.x += -q.saturation_magnetization * q.demag_n[0] * m.x;
+        h.y += -q.saturation_magnetization * q.demag_n[1] * m.y;
+        h.z += -q.saturation_magnetization * q.demag_n[2] * m.z;
+        if (q.exchange_coeff != 0.0) { h.x += q.exchange_coeff * m.x; h.y += q.exchange_coeff * m.y; h.z += q.exchange_coeff * m.z; }
+        if (noise_mode != 0 && q.h_th > 0.0) {
+            double nx, ny, nz;
+            if (noise_mode == 2) {
+                const int64_t k = n_eval < noise_cap ? n_eval : noise_cap - 1;
+                nx = noise_row[3 * k]; ny = noise_row[3 * k + 1]; nz = noise_row[3 * k + 2];
+            } else {
+                uint32_t o[4];
+                ph((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)n_eval, 0x524b3435u, o);
+                float z0, z1, z2, z3;
+                box_muller(o[0], o[1], z0, z1);
+                box_muller(o[2], o[3], z2, z3);
+                nx = z0; ny = z1; nz = z2;
+            }
+            h.x += q.h_th * nx; h.y += q.h_th * ny; h.z += q.h_th * nz;
+        }
+        ++n_eval;
+        V3 tau = {0.0, 0.0, 0.0};
+        if (!(fabs(cur) < 1e-12)) {                            // :221-222
+            const V3 ph3 = {q.p_hat[0], q.p_hat[1], q.p_hat[2]};
+            const V3 mxp = cross3(m, ph3);
+            const V3 dl = (q.c_dl_p * cur) * cross3(m, mxp);
+            const V3 fl = (q.c_fl_p * cur) * mxp;
+            const V3 sg = {q.sigma[0], q.sigma[1], q.sigma[2]};
+            const V3 sdl = (q.c_dl_s * cur) * cross3(sg, m);
+            const V3 sfl = (q.c_fl_s * cur) * sg;
+            tau = dl + fl + sdl + sfl;
+        }
+        V3 dm = (-q.gamma) * cross3(m, h);                     // :121-124
+        dm = dm + q.alpha * cross3(m, dm);
+        return dm + tau;
+    }
+
+    // _compute_energy (physics/llgs_solver.py:239-262) and the torque norm of :168-172 for a NORMALISED m
+    STG_HD void diagnostics(double t, V3 m, double& energy, double& torque) const {
+        const StgLlgParams& q = *p;
+        const V3 e = {q.easy_axis[0], q.easy_axis[1], q.easy_axis[2]};
+        const double msv = q.saturation_magnetization * q.volume;
+        const double ez = -q.mu0 * msv * dot3(m, happ);
+        const double c = dot3(m, e);
+        const double ku = hk * q.mu0 * q.saturation_magnetization * 0.5;
+        const double ea = -ku * q.volume * c * c;
+        const double ed = 0.5 * q.mu0 * q.saturation_magnetization * msv *
+                          (q.demag_n[0] * m.x * m.x + q.demag_n[1] * m.y * m.y + q.demag_n[2] * m.z * m.z);
+        energy = ez + ea + ed;
+        const double cur = (t <= t_pulse) ? J : 0.0;
+        torque = 0.0;
+        if (!(fabs(cur) < 1e-12)) {
+            const V3 ph3 = {q.p_hat[0], q.p_hat[1], q.p_hat[2]};
+            const V3 mxp = cross3(m, ph3);
+            const V3 dl = (q.c_dl_p * cur) * cross3(m, mxp);
+            const V3 fl = (q.c_fl_p * cur) * mxp;
+            const V3 sg = {q.sigma[0], q.sigma[1], q.sigma[2]};
+            const V3 sdl = (q.c_dl_s * cur) * cross3(sg, m) + dl;
+            const V3 sfl = (q.c_fl_s * cur) * sg + fl;
+            torque = sqrt(dot3(sdl, sdl)) + sqrt(dot3(sfl, sfl));
+        }
+    }
+};
+
+STG_HD double ulp_above(double t) {   // |nextafter(t, +inf) - t|
+#if defined(__CUDA_ARCH__)
+    return fabs(nextafter(t, INFINITY) - t);
+#else
+    return fabs(nextafter(t, INFINITY) - t);
+#endif
+}
+STG_HD V3 vabs_max(V3 a, V3 b) { return {fmax(fabs(a.x), fabs(b.x)), fmax(fabs(a.y), fabs(b.y)), fmax(fabs(a.z), fabs(b.z))}; }
+
+// One trajectory of LLGSSolver.solve. Returns through the StgRk45Args output arrays of env e.
+STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
+    using T = Rk45Tableau;
+    const StgLlgParams& q = a.d_table[a.d_param_index ? a.d_param_index[e] : 0];
+    LlgRhs f;
+    f.p = &q;
+    f.J = a.d_current ? a.d_current[e] : 0.0;
+    f.t_pulse = a.d_t_pulse ? a.d_t_pulse[e] : 1.0e300;
+    f.happ = a.d_happ ? V3{a.d_happ[3 * e], a.d_happ[3 * e + 1], a.d_happ[3 * e + 2]} : V3{0.0, 0.0, 0.0};
+    double ku = q.uniaxial_anisotropy;
+    if (q.use_vcma) {   // devices/vcma_mram.py:122-147
+        double v = a.d_voltage ? a.d_voltage[e] : 0.0;
+        v = fmin(fmax(v, -q.breakdown_voltage), q.breakdown_voltage);
+        const double k = ku + (-q.vcma_coefficient * fabs(v) / (q.dielectric_thickness * q.dielectric_thickness));
+        ku = fmax(k, -0.5 * ku);
+    }
+    f.hk = 2.0 * ku / (q.mu0 * q.saturation_magnetization);
+    f.noise_mode = (a.flags & STG_F_THERMAL_INJECT) ? 2 : ((a.flags & STG_F_THERMAL_PHILOX) ? 1 : 0);
+    f.ph = Philox{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+    f.gid = a.env_offset + (uint64_t)e;
+    f.noise_row = a.d_noise ? a.d_noise + (int64_t)e * a.noise_stride * 3 : nullptr;
+    f.noise_cap = a.noise_stride;
+    f.n_eval = 0;
+
+    const double t0 = 0.0, tb = a.d_t_end[e];
+    const double rtol = a.rtol, atol = a.atol, max_step = a.max_step;
+    V3 y = {a.d_m0[3 * e], a.d_m0[3 * e + 1], a.d_m0[3 * e + 2]};
+    {   // m_initial / ||m_initial|| (physics/llgs_solver.py:75)
+        const double n0 = sqrt(dot3(y, y));
+        y = {y.x / n0, y.y / n0, y.z / n0};
+    }
+    double t = t0;
+    int n_acc = 0, n_rej = 0, status = 0, overflow = 0;
+    double* traj = a.d_traj ? a.d_traj + (int64_t)e * a.traj_stride * 6 : nullptr;
+    auto record = [&](int row, double tt, V3 yy) {
+        if (!traj) return;
+        if (row >= a.traj_stride) { overflow = 2; return; }   // keeps integrating; only the recording stops
+        const double n = sqrt(dot3(yy, yy));
+        const V3 m = {yy.x / n, yy.y / n, yy.z / n};            // :152-153
+        double en, tq;
+        f.diagnostics(tt, m, en, tq);
+        double* r = traj + 6 * (int64_t)row;
+        r[0] = tt; r[1] = m.x; r[2] = m.y; r[3] = m.z; r[4] = en; r[5] = tq;
+    };
+    record(0, t, y);
+
+    if (tb > t0) {
+        V3 fk = f(t, y);                                        // rk.py:94
+        // select_initial_step (common.py:68-133), order = 4
+        double h_abs;
+        {
+            const double interval = fabs(tb - t0);
+            const V3 sc = {atol + fabs(y.x) * rtol, atol + fabs(y.y) * rtol, atol + fabs(y.z) * rtol};
+            const double d0 = rms3({y.x / sc.x, y.y / sc.y, y.z / sc.z});
+            const double d1 = rms3({fk.x / sc.x, fk.y / sc.y, fk.z / sc.z});
+            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            h0 = fmin(h0, interval);
+            const V3 y1 = y + h0 * fk;
+            const V3 f1 = f(t0 + h0, y1);
+            const double d2 = rms3({(f1.x - fk.x) / sc.x, (f1.y - fk.y) / sc.y, (f1.z - fk.z) / sc.z}) / h0;
+            double h1;
+            if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+            else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+            h_abs = fmin(fmin(100.0 * h0, h1), fmin(interval, max_step));
+        }
+        // solve_ivp main loop: step until t == t_bound (ivp.py), RungeKutta._step_impl (rk.py:111-167)
+        const int64_t max_attempts = a.max_attempts > 0 ? a.max_attempts : 1000000;
+        int64_t attempts = 0;
+        while (t != tb && status == 0) {
+            const double min_step = 10.0 * ulp_above(t);
+            if (h_abs > max_step) h_abs = max_step;
+            else if (h_abs < min_step) h_abs = min_step;
+            bool accepted = false, rejected = false;
+            V3 y_new = y, f_new = fk;
+            double t_new = t;
+            while (!accepted) {
+                if (h_abs < min_step) { status |= 1; break; }   // TOO_SMALL_STEP
+                if (++attempts > max_attempts) { status |= 4; break; }
+                double h = h_abs;
+                t_new = t + h;
+                if (t_new - tb > 0.0) t_new = tb;
+                h = t_new - t;
+                h_abs = fabs(h);
+                // rk_step (rk.py:14-72)
+                const V3 k1 = fk;
+                const V3 k2 = f(t + T::c2 * h, y + h * (T::a21 * k1));
+                const V3 k3 = f(t + T::c3 * h, y + h * (T::a31 * k1 + T::a32 * k2));
+                const V3 k4 = f(t + T::c4 * h, y + h * (T::a41 * k1 + T::a42 * k2 + T::a43 * k3));
+                const V3 k5 = f(t + T::c5 * h, y + h * (T::a51 * k1 + T::a52 * k2 + T::a53 * k3 + T::a54 * k4));
+                const V3 k6 = f(t + h, y + h * (T::a61 * k1 + T::a62 * k2 + T::a63 * k3 + T::a64 * k4 + T::a65 * k5));
+                y_new = y + h * (T::b1 * k1 + T::b3 * k3 + T::b4 * k4 + T::b5 * k5 + T::b6 * k6);
+                f_new = f(t + h, y_new);
+                const V3 err = h * (T::e1 * k1 + T::e3 * k3 + T::e4 * k4 + T::e5 * k5 + T::e6 * k6 + T::e7 * f_new);
+                const V3 mx = vabs_max(y, y_new);
+                const double en = rms3({err.x / (atol + mx.x * rtol), err.y / (atol + mx.y * rtol), err.z / (atol + mx.z * rtol)});
+                if (en < 1.0) {
+                    double factor = (en == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(en, -0.2));
+                    if (rejected) factor = fmin(1.0, factor);
+                    h_abs *= factor;
+                    accepted = true;
+                } else if (en >= 1.0) {
+                    h_abs *= fmax(0.2, 0.9 * pow(en, -0.2));
+                    rejected = true;
+                    ++n_rej;
+                } else {               // NaN error norm: SciPy would loop forever shrinking nothing; flag and stop
+                    status |= 8;
+                    break;
+                }
+            }
+            if (!accepted) break;
+            t = t_new; y = y_new; fk = f_new;
+            ++n_acc;
+            record(n_acc, t, y);
+        }
+    }
+    a.d_y_out[3 * e] = y.x; a.d_y_out[3 * e + 1] = y.y; a.d_y_out[3 * e + 2] = y.z;
+    if (a.d_n_accepted) a.d_n_accepted[e] = n_acc;
+    if (a.d_n_rejected) a.d_n_rejected[e] = n_rej;
+    if (a.d_n_rhs) a.d_n_rhs[e] = f.n_eval;
+    if (a.d_status) a.d_status[e] = status | overflow;
+    if (a.d_t_reached) a.d_t_reached[e] = t;
+}
+
+}  // namespace stg

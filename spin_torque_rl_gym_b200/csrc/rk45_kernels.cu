@@ -1,0 +1,31 @@
+// rk45_kernels.cu — K2 launch + C-ABI entry (see rk45_core.cuh). One trajectory per thread; lanes whose trajectory has
+// finished idle until the warp's slowest lane is done (step counts differ by a few percent within a device class).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/stg.h"
+#include "rk45_core.cuh"
+
+namespace stg {
+
+__global__ void __launch_bounds__(64) llgs_rk45_kernel(const __grid_constant__ StgRk45Args a) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < a.n_envs) rk45_body(a, e);
+}
+
+}  // namespace stg
+
+extern "C" int stg_llgs_rk45_f64(const StgRk45Args* args, void* stream) {
+    if (!args) return STG_E_NULL;
+    const StgRk45Args& a = *args;
+    if (a.n_envs < 0 || a.n_sets <= 0) return STG_E_SIZE;
+    if (!a.d_table || !a.d_m0 || !a.d_t_end || !a.d_y_out) return STG_E_NULL;
+    if (!(a.rtol > 0.0) || !(a.atol > 0.0) || !(a.max_step > 0.0)) return STG_E_SIZE;
+    if ((a.flags & STG_F_THERMAL_PHILOX) && (a.flags & STG_F_THERMAL_INJECT)) return STG_E_ENUM;
+    if ((a.flags & STG_F_THERMAL_INJECT) && (!a.d_noise || a.noise_stride <= 0)) return STG_E_NULL;
+    if (a.d_traj && a.traj_stride <= 0) return STG_E_SIZE;
+    if (a.n_envs == 0) return STG_OK;
+    const unsigned grid = (unsigned)((a.n_envs + 63) / 64);
+    stg::llgs_rk45_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}

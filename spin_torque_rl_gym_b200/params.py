@@ -181,3 +181,58 @@ def all_axis_z(folded: np.ndarray) -> bool:
     lib = _lib.load()
     buf = np.ascontiguousarray(folded, dtype=np.float64)
     return bool(lib.stg_stt_all_axis_z(buf.ctypes.data_as(C.POINTER(_lib.StgSttFolded)), buf.shape[0]))
+
+
+# ---- generalised LLGS right-hand side of the RK45 solver (K2) ---------------------------------------------------------------
+GAMMA_LLGS = 2.21e5
+MU0 = 4 * np.pi * 1e-7
+KB_LLGS = 1.380649e-23     # physics/llgs_solver.py:49
+
+
+def make_llg_struct(kind: str, params: Dict[str, Any], *, thermal: bool = False, temperature: float = 300.0,
+                    current_direction: Optional[Sequence[float]] = None, gamma: float = GAMMA_LLGS) -> _lib.StgLlgParams:
+    """StgLlgParams for one device parameter dict. kind 'stt_mram' is exactly LLGSSolver's RHS (physics/llgs_solver.py:
+    92-126, 182-237); 'sot_mram' / 'vcma_mram' compose the device methods' terms into the same RHS."""
+    kind = kind.lower()
+    p = _lib.StgLlgParams()
+    alpha = float(params.get("damping", 0.01))
+    ms = float(params.get("saturation_magnetization", 800e3))
+    vol = float(params.get("volume", 1e-24))
+    p.gamma, p.mu0, p.alpha, p.saturation_magnetization, p.volume = gamma, MU0, alpha, ms, vol
+    p.uniaxial_anisotropy = float(params.get("uniaxial_anisotropy", 1e6))
+    p.easy_axis = _lib.c_double3(*np.asarray(params.get("easy_axis", [0, 0, 1]), dtype=float))
+    p.h_th = math.sqrt(2 * alpha * KB_LLGS * temperature / (gamma * MU0 * ms * vol)) if thermal else 0.0
+    p.p_hat = _lib.c_double3(0.0, 0.0, 1.0)
+    if kind == "stt_mram":
+        p.demag_n = _lib.c_double3(*np.asarray(params.get("demag_factors", [0, 0, 1]), dtype=float))
+        a_ex = float(params.get("exchange_constant", 20e-12))
+        p.exchange_coeff = (2 * a_ex / (MU0 * ms)) * 0.1 if a_ex > 0 else 0.0
+        beta = float(params.get("polarization", 0.7)) * gamma / (2 * ms * vol)
+        p.c_dl_p, p.c_fl_p = beta, 0.1 * beta
+    elif kind in ("sot_mram", "vcma_mram"):
+        ar = float(params.get("aspect_ratio", 1.0))
+        nx, ny = (1.0 / (1.0 + ar), ar / (1.0 + ar)) if ar >= 1.0 else (ar / (1.0 + ar), 1.0 / (1.0 + ar))
+        p.demag_n = _lib.c_double3(nx, ny, 1.0 - nx - ny)
+        if kind == "sot_mram":
+            t_hm = float(params.get("heavy_metal_thickness", 5e-9))
+            js = float(params.get("spin_hall_angle", 0.1)) * float(params.get("interface_transparency", 0.5)) * \
+                (t_hm / (t_hm + float(params.get("thickness", 1e-9))))
+            p.c_dl_s = float(params.get("damping_like_efficiency", 0.2)) * js
+            p.c_fl_s = float(params.get("field_like_efficiency", 0.1)) * js
+            d = np.array([1.0, 0.0, 0.0]) if current_direction is None else np.asarray(current_direction, dtype=float)
+            d = d / np.linalg.norm(d)
+            p.sigma = _lib.c_double3(*np.cross(np.array([0.0, 0.0, 1.0]), d))
+        else:
+            p.use_vcma = 1
+            p.vcma_coefficient = float(params.get("vcma_coefficient", 100e-6))
+            p.dielectric_thickness = float(params.get("dielectric_thickness", 1e-9))
+            p.breakdown_voltage = float(params.get("breakdown_voltage", 2.0))
+    else:
+        raise ValueError(f"Unknown device type '{kind}'")
+    return p
+
+
+def llg_table(structs: List[_lib.StgLlgParams]) -> np.ndarray:
+    """Raw bytes of a StgLlgParams array as a uint8 NumPy array (uploaded as the device table)."""
+    arr = (_lib.StgLlgParams * len(structs))(*structs)
+    return np.frombuffer(arr, dtype=np.uint8).copy()

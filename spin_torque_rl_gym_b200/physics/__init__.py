@@ -1,0 +1,2 @@
+from .thermal_model import ThermalFluctuations  # noqa: F401
+from .llgs_solver import LLGSSolver  # noqa: F401

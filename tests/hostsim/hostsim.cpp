@@ -9,6 +9,7 @@
 #include "../../include/stg.h"
 #include "../../spin_torque_rl_gym_b200/csrc/llgs_core.cuh"
 #include "../../spin_torque_rl_gym_b200/csrc/stt_env_core.cuh"
+#include "../../spin_torque_rl_gym_b200/csrc/rk45_core.cuh"
 
 using namespace stg;
 
@@ -90,4 +91,9 @@ extern "C" void hostsim_normals12(uint64_t seed, uint64_t gid, uint32_t step, ui
     const float unit = -1.3862943611198906f;
     Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
     philox_normals12(ph, gid, step, sub, unit, out);
+}
+
+extern "C" int hostsim_llgs_rk45(const StgRk45Args* a) {
+    for (int64_t e = 0; e < a->n_envs; ++e) rk45_body(*a, e);
+    return 0;
 }
