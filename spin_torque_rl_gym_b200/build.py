@@ -18,6 +18,7 @@ HEADERS = ["llgs_core.cuh", os.path.join("..", "..", "include", "stg.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
+    "-Werror", "cross-execution-space-call",     # a host-only call inside device code silently drops the function body
     "-Xcompiler", "-fPIC", "-shared",
 ]
 

@@ -11,6 +11,9 @@
 
 #include "../../include/stg.h"
 #include "llgs_core.cuh"
+#ifdef STG_DEBUG_RK45
+#include <cstdio>
+#endif
 
 namespace stg {
 
@@ -124,11 +127,11 @@ struct LlgRhs {
     }
 };
 
-STG_HD double ulp_above(double t) {   // |nextafter(t, +inf) - t|
+STG_HD double ulp_above(double t) {   // |nextafter(t, +inf) - t| for t >= 0 (the integration always runs forward from 0)
 #if defined(__CUDA_ARCH__)
-    return fabs(nextafter(t, INFINITY) - t);
+    return __longlong_as_double(__double_as_longlong(t) + 1LL) - t;
 #else
-    return fabs(nextafter(t, INFINITY) - t);
+    return nextafter(t, (double)INFINITY) - t;
 #endif
 }
 STG_HD V3 vabs_max(V3 a, V3 b) { return {fmax(fabs(a.x), fabs(b.x)), fmax(fabs(a.y), fabs(b.y)), fmax(fabs(a.z), fabs(b.z))}; }
@@ -178,6 +181,9 @@ STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
         r[0] = tt; r[1] = m.x; r[2] = m.y; r[3] = m.z; r[4] = en; r[5] = tq;
     };
     record(0, t, y);
+#ifdef STG_DEBUG_RK45
+    printf("rk45 e=%lld tb=%g rtol=%g atol=%g max_step=%g J=%g tp=%g hk=%g flags=%u\n", (long long)e, tb, rtol, atol, max_step, f.J, f.t_pulse, f.hk, a.flags);
+#endif
 
     if (tb > t0) {
         V3 fk = f(t, y);                                        // rk.py:94
@@ -199,6 +205,9 @@ STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
             h_abs = fmin(fmin(100.0 * h0, h1), fmin(interval, max_step));
         }
         // solve_ivp main loop: step until t == t_bound (ivp.py), RungeKutta._step_impl (rk.py:111-167)
+#ifdef STG_DEBUG_RK45
+        printf("rk45 h_abs=%g fk=(%g %g %g) n_eval=%d\n", h_abs, fk.x, fk.y, fk.z, f.n_eval);
+#endif
         const int64_t max_attempts = a.max_attempts > 0 ? a.max_attempts : 1000000;
         int64_t attempts = 0;
         while (t != tb && status == 0) {
@@ -228,6 +237,9 @@ STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
                 const V3 err = h * (T::e1 * k1 + T::e3 * k3 + T::e4 * k4 + T::e5 * k5 + T::e6 * k6 + T::e7 * f_new);
                 const V3 mx = vabs_max(y, y_new);
                 const double en = rms3({err.x / (atol + mx.x * rtol), err.y / (atol + mx.y * rtol), err.z / (atol + mx.z * rtol)});
+#ifdef STG_DEBUG_RK45
+                if (attempts < 4) printf("rk45 attempt %lld h=%g en=%g t_new=%g\n", (long long)attempts, h, en, t_new);
+#endif
                 if (en < 1.0) {
                     double factor = (en == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(en, -0.2));
                     if (rejected) factor = fmin(1.0, factor);
@@ -248,6 +260,9 @@ STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
             record(n_acc, t, y);
         }
     }
+#ifdef STG_DEBUG_RK45
+    printf("rk45 end t=%g n_acc=%d n_rej=%d status=%d n_eval=%d ptrs %p %p %p\n", t, n_acc, n_rej, status, f.n_eval, (void*)a.d_n_accepted, (void*)a.d_n_rhs, (void*)a.d_t_reached);
+#endif
     a.d_y_out[3 * e] = y.x; a.d_y_out[3 * e + 1] = y.y; a.d_y_out[3 * e + 2] = y.z;
     if (a.d_n_accepted) a.d_n_accepted[e] = n_acc;
     if (a.d_n_rejected) a.d_n_rejected[e] = n_rej;
