@@ -292,6 +292,67 @@ typedef struct StgRk45Args {
 
 int stg_llgs_rk45_f64(const StgRk45Args* args, void* stream);
 
+/* ---- K3: SpinTorqueArray-v0 (envs/array_env.py) ------------------------------------------------------------------------- */
+#define STG_ARRAY_INDIVIDUAL 0
+#define STG_ARRAY_ROW 1
+#define STG_ARRAY_COLUMN 2
+#define STG_ARRAY_GLOBAL 3
+#define STG_ARRAY_MAX_DEVICES 1024
+
+typedef struct StgArrayParams {
+    int32_t n_rows, n_cols;
+    int32_t action_mode;             /* STG_ARRAY_*                                                                 */
+    int32_t device_kind;             /* STG_DEV_*: which compute_effective_field / compute_resistance form          */
+    int32_t max_steps;               /* 200 (envs/array_env.py:36)                                                  */
+    int32_t reserved;
+    double hk;                       /* 2 K_u / (mu0 Ms)                                                            */
+    double saturation_magnetization;
+    double easy_axis[3];             /* as given (devices/stt_mram.py:68-72)                                        */
+    double demag_n[3];               /* SOT/VCMA shape factors; zeros for STT                                       */
+    double resistance_parallel, resistance_antiparallel;
+    double reference_magnetization[3];   /* normalised                                                              */
+    double series_resistance;
+    double area;
+    double max_current, max_duration;
+    double success_threshold, energy_penalty_weight;
+} StgArrayParams;
+
+/* One step of n_arrays independent crossbar arrays (envs/array_env.py:358-411). D = n_rows*n_cols devices per array.
+ *   d_coupling  [D][D] f64 coupling matrix (envs/array_env.py:289-318) or NULL (include_coupling=False)
+ *   d_pattern   [n][D][3] f64 current_pattern (updated in place); d_target [n][D][3] f64
+ *   d_action    [n][3] f32 (idx, J, T); `global` mode: [n][2] f32 (J, T) with action_stride = 2
+ *   outputs     d_obs [n][D][6] f32 (pattern, target), d_reward/d_step_energy/d_similarity [n] f64, flags [n] u8
+ *   STG_F_AUTORESET: arrays that terminate/truncate are reset in the same call (random unit vectors from the Philox stream,
+ *   target kept), d_final_obs receives the pre-reset observation. */
+typedef struct StgArrayStepArgs {
+    StgArrayParams params;
+    const double* d_coupling;
+    double* d_pattern;
+    const double* d_target;
+    double* d_total_energy;
+    int32_t* d_step_count;
+    int32_t* d_episode;
+    const float* d_action;
+    float* d_obs;
+    double* d_reward;
+    uint8_t* d_terminated;
+    uint8_t* d_truncated;
+    double* d_step_energy;
+    double* d_similarity;
+    float* d_final_obs;
+    double* d_stats;                 /* [STG_NSTATS] or NULL                                                        */
+    uint64_t seed;
+    uint64_t array_offset;
+    int64_t n_arrays;
+    int32_t action_stride;
+    uint32_t flags;
+} StgArrayStepArgs;
+
+int stg_array_step_f64(const StgArrayStepArgs* args, void* stream);
+/* Reset of the arrays with d_mask[i] != 0 (all if NULL): per-device normalised N(0,1)^3 from the Philox stream, or the rows
+ * of d_pattern0 [n][D][3] (options['initial_pattern'], stored as given); counters zeroed; observation written. */
+int stg_array_reset(const StgArrayStepArgs* args, const uint8_t* d_mask, const double* d_pattern0, void* stream);
+
 /* ---- K4: batched device-class operations (FP64, one row per device state) -------------------------------------------------
  * Host struct passed by pointer; mirrors what the reference's device constructors cache (devices/sot_mram.py:61-76,
  * devices/vcma_mram.py:60-84). easy_axis is used AS GIVEN (the device methods do not normalise it);

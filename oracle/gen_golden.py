@@ -281,6 +281,48 @@ def gen_rk45():
     print("wrote rk45.npz")
 
 
+def gen_array():
+    """SpinTorqueArrayEnv.step of the live reference: 8x8 dipolar crossbar, all four action modes, a 3x5 stray-field array."""
+    _, SpinTorqueArrayEnv = _import_reference()
+    out = {}
+    rng = np.random.default_rng(21)
+
+    def run(name, size, mode, n_steps, **kw):
+        env = SpinTorqueArrayEnv(array_size=size, action_mode=mode, seed=0, **kw)
+        nd = size[0] * size[1]
+        p0 = rng.normal(size=size + (3,))
+        p0 /= np.linalg.norm(p0, axis=2, keepdims=True)
+        obs0, _ = env.reset(seed=0, options={'initial_pattern': p0})
+        hi = {'individual': nd - 1, 'row': size[0] - 1, 'column': size[1] - 1}.get(mode, 0)
+        if mode == 'global':
+            acts = np.stack([rng.uniform(-2e6, 2e6, n_steps), rng.uniform(0, 5e-9, n_steps)], 1).astype(np.float32)
+        else:
+            acts = np.stack([rng.uniform(-0.5, hi + 0.5, n_steps), rng.uniform(-2.2e6, 2.2e6, n_steps),
+                             rng.uniform(-1e-10, 5.5e-9, n_steps)], 1).astype(np.float32)
+            acts[1, 1] = 0.0
+        rec = dict(obs=[obs0], reward=[], terminated=[], truncated=[], pattern=[env.current_pattern.copy()], energy=[],
+                   similarity=[])
+        for a in acts:
+            o, r, te, tr, info = env.step(a.copy())
+            rec['obs'].append(o); rec['reward'].append(r); rec['terminated'].append(te); rec['truncated'].append(tr)
+            rec['pattern'].append(env.current_pattern.copy()); rec['energy'].append(info['energy_consumed'])
+            rec['similarity'].append(info['pattern_similarity'])
+        for k, v in rec.items():
+            out[f'{name}/{k}'] = np.array(v)
+        out[f'{name}/actions'] = acts
+        out[f'{name}/p0'] = p0
+        out[f'{name}/coupling'] = env.coupling_matrix
+        print(name, 'done', flush=True)
+
+    run('ind8', (8, 8), 'individual', 40)
+    run('row8', (8, 8), 'row', 20)
+    run('col8', (8, 8), 'column', 20)
+    run('glob8', (8, 8), 'global', 6)
+    run('stray35', (3, 5), 'row', 12, coupling_type='stray_field', coupling_strength=0.25, max_steps=10)
+    np.savez_compressed(os.path.join(GOLD, "array_env.npz"), **out)
+    print("wrote array_env.npz")
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["stt", "multi", "array", "rk45", "devices"]
     os.makedirs(GOLD, exist_ok=True)

@@ -7,4 +7,4 @@ include/stg.h (libstg.so). See DESIGN.md.
 __version__ = "0.1.0"
 
 from . import _lib, build, params  # noqa: F401
-from .envs import SpinTorqueVectorEnv  # noqa: F401
+from .envs import SpinTorqueArrayVectorEnv, SpinTorqueVectorEnv  # noqa: F401

@@ -105,6 +105,28 @@ class StgRk45Args(C.Structure):
                 ("env_offset", C.c_uint64), ("n_envs", C.c_int64), ("n_sets", C.c_int32), ("flags", C.c_uint32)]
 
 
+ARRAY_MODES = {"individual": 0, "row": 1, "column": 2, "global": 3}
+
+
+class StgArrayParams(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("n_cols", C.c_int32), ("action_mode", C.c_int32), ("device_kind", C.c_int32),
+                ("max_steps", C.c_int32), ("reserved", C.c_int32), ("hk", C.c_double),
+                ("saturation_magnetization", C.c_double), ("easy_axis", c_double3), ("demag_n", c_double3),
+                ("resistance_parallel", C.c_double), ("resistance_antiparallel", C.c_double),
+                ("reference_magnetization", c_double3), ("series_resistance", C.c_double), ("area", C.c_double),
+                ("max_current", C.c_double), ("max_duration", C.c_double), ("success_threshold", C.c_double),
+                ("energy_penalty_weight", C.c_double)]
+
+
+class StgArrayStepArgs(C.Structure):
+    _fields_ = [("params", StgArrayParams), ("d_coupling", C.c_void_p), ("d_pattern", C.c_void_p),
+                ("d_target", C.c_void_p), ("d_total_energy", C.c_void_p), ("d_step_count", C.c_void_p),
+                ("d_episode", C.c_void_p), ("d_action", C.c_void_p), ("d_obs", C.c_void_p), ("d_reward", C.c_void_p),
+                ("d_terminated", C.c_void_p), ("d_truncated", C.c_void_p), ("d_step_energy", C.c_void_p),
+                ("d_similarity", C.c_void_p), ("d_final_obs", C.c_void_p), ("d_stats", C.c_void_p), ("seed", C.c_uint64),
+                ("array_offset", C.c_uint64), ("n_arrays", C.c_int64), ("action_stride", C.c_int32), ("flags", C.c_uint32)]
+
+
 # every symbol include/stg.h declares: (name, restype, argtypes)
 SYMBOLS = {
     "stg_abi_version": (C.c_int, []),
@@ -119,6 +141,8 @@ SYMBOLS = {
     "stg_stt_solve_f32": (C.c_int, [C.POINTER(StgSttSolveArgs), C.c_void_p]),
     "stg_stt_solve_f64": (C.c_int, [C.POINTER(StgSttSolveArgs), C.c_void_p]),
     "stg_llgs_rk45_f64": (C.c_int, [C.POINTER(StgRk45Args), C.c_void_p]),
+    "stg_array_step_f64": (C.c_int, [C.POINTER(StgArrayStepArgs), C.c_void_p]),
+    "stg_array_reset": (C.c_int, [C.POINTER(StgArrayStepArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
     "stg_device_field_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_void_p]),
     "stg_device_resistance_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

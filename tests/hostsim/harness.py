@@ -17,7 +17,7 @@ _H = None
 def build(force=False):
     src = os.path.join(HERE, "hostsim.cpp")
     deps = [src] + [os.path.join(HERE, "..", "..", "spin_torque_rl_gym_b200", "csrc", f)
-                    for f in ("llgs_core.cuh", "stt_env_core.cuh", "rk45_core.cuh")] + [os.path.join(HERE, "..", "..", "include", "stg.h")]
+                    for f in ("llgs_core.cuh", "stt_env_core.cuh", "rk45_core.cuh", "array_core.cuh")] + [os.path.join(HERE, "..", "..", "include", "stg.h")]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=fast", "-fPIC", "-shared", "-x", "c++", src,
                         "-o", SO], check=True)
@@ -32,6 +32,7 @@ def lib():
         _H.hostsim_stt_reset.argtypes = [C.POINTER(_lib.StgSttResetArgs)]
         _H.hostsim_stt_solve.argtypes = [C.POINTER(_lib.StgSttSolveArgs), C.c_int]
         _H.hostsim_llgs_rk45.argtypes = [C.POINTER(_lib.StgRk45Args)]
+        _H.hostsim_array_step.argtypes = [C.POINTER(_lib.StgArrayStepArgs)]
     return _H
 
 

@@ -10,6 +10,8 @@
 #include "../../spin_torque_rl_gym_b200/csrc/llgs_core.cuh"
 #include "../../spin_torque_rl_gym_b200/csrc/stt_env_core.cuh"
 #include "../../spin_torque_rl_gym_b200/csrc/rk45_core.cuh"
+#include "../../spin_torque_rl_gym_b200/csrc/array_core.cuh"
+#include <vector>
 
 using namespace stg;
 
@@ -95,5 +97,33 @@ extern "C" void hostsim_normals12(uint64_t seed, uint64_t gid, uint32_t step, ui
 
 extern "C" int hostsim_llgs_rk45(const StgRk45Args* a) {
     for (int64_t e = 0; e < a->n_envs; ++e) rk45_body(*a, e);
+    return 0;
+}
+
+// One step of n arrays through the K3 helpers (the CUDA kernel runs the same sequence with thread 0 of each CTA).
+extern "C" int hostsim_array_step(const StgArrayStepArgs* pa) {
+    const StgArrayStepArgs& a = *pa;
+    const StgArrayParams& p = a.params;
+    const int nd = p.n_rows * p.n_cols;
+    std::vector<double> scratch(nd);
+    for (int64_t arr = 0; arr < a.n_arrays; ++arr) {
+        double* pattern = a.d_pattern + arr * nd * 3;
+        const double* target = a.d_target + arr * nd * 3;
+        const double prev = array_similarity(pattern, target, nd, scratch.data());
+        const ArrayAction act = array_parse_action(p, a.d_action + arr * a.action_stride);
+        const double energy = array_apply_action(p, a.d_coupling, pattern, act);
+        const double sim = array_similarity(pattern, target, nd, scratch.data());
+        const bool success = sim >= p.success_threshold;
+        const double sd = array_magnitude_std(pattern, nd, scratch.data());
+        a.d_reward[arr] = array_reward(p, success, sim, energy, dadd(sim, -prev), sd);
+        a.d_step_count[arr] += 1;
+        a.d_total_energy[arr] = dadd(a.d_total_energy[arr], energy);
+        a.d_terminated[arr] = success;
+        a.d_truncated[arr] = a.d_step_count[arr] >= p.max_steps;
+        if (a.d_step_energy) a.d_step_energy[arr] = energy;
+        if (a.d_similarity) a.d_similarity[arr] = sim;
+        for (int q = 0; q < nd * 6; ++q)
+            a.d_obs[arr * nd * 6 + q] = (float)((q % 6) < 3 ? pattern[3 * (q / 6) + q % 6] : target[3 * (q / 6) + q % 6 - 3]);
+    }
     return 0;
 }
