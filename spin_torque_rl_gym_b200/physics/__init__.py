@@ -1,2 +1,3 @@
 from .thermal_model import ThermalFluctuations  # noqa: F401
 from .llgs_solver import LLGSSolver  # noqa: F401
+from .simple_solver import RobustLLGSSolver, SimpleLLGSSolver  # noqa: F401
