@@ -213,6 +213,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner)
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     n_local = args.envs_per_gpu
