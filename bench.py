@@ -267,8 +267,10 @@ def main():
     pinned_rew = torch.empty(n_local, dtype=torch.float64).pin_memory()
     pinned_flags = torch.empty(2, n_local, dtype=torch.uint8).pin_memory()
 
+    act_pinned = torch.from_numpy(act_host).pin_memory()
+
     def e2e_step():
-        o, r, te, tr, _ = env.step(act_host)                # numpy in: staged through pinned memory + H2D inside step()
+        o, r, te, tr, _ = env.step(act_pinned)              # host actions (pinned): async H2D inside step()
         pinned_obs.copy_(o, non_blocking=True)
         pinned_rew.copy_(r, non_blocking=True)
         pinned_flags[0].copy_(env._terminated, non_blocking=True)
@@ -350,7 +352,7 @@ def main():
             "config": workload_config(n_gpus, n_local),
             "e2e": {"value": e2e_value, "unit": "LLGS substeps/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": n_local * 8 * n_gpus, "d2h_bytes_per_step": n_local * (48 + 8 + 2) * n_gpus,
-                    "api": "SpinTorqueVectorEnv.step(numpy actions) + D2H of obs/reward/terminated/truncated"},
+                    "api": "SpinTorqueVectorEnv.step(pinned host actions) + D2H of obs/reward/terminated/truncated to pinned host memory"},
             "gpu_launches": launches,
             "roofline": {
                 "bound": "fp32_fma", "kernel": "stt_env_step_kernel<float, axis_z, philox, rk4>",

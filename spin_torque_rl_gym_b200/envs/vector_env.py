@@ -263,6 +263,10 @@ class SpinTorqueVectorEnv:
             if actions.device == self.device and actions.dtype == torch.float32 and actions.is_contiguous() \
                     and tuple(actions.shape) == (N, 2):
                 return actions
+            if actions.device.type == "cpu" and actions.dtype == torch.float32 and actions.is_pinned() \
+                    and tuple(actions.shape) == (N, 2):
+                self._action_dev.copy_(actions, non_blocking=True)       # pinned host tensor: one async H2D, no staging copy
+                return self._action_dev
             act = actions.to(device=self.device, dtype=torch.float32).reshape(N, 2)
             self._action_dev.copy_(act)
             return self._action_dev
