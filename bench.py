@@ -65,7 +65,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -149,7 +149,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_sample = 256 * threads           # ~1.0 s of CPU work per step at ~2e5 substeps/s/thread... bounded sample
+    n_sample = 2048 * threads          # bounded sample: ~0.5 s of CPU work per step on all host threads
     for _ in range(args.warmup):
         cpu_port_rate(max(threads, n_sample // 8), 1, threads)
     t0 = time.perf_counter()
@@ -183,7 +183,7 @@ def workload_config(n_gpus, n_envs_per_gpu, note=""):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=N_ENVS_PER_GPU)
@@ -333,8 +333,8 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_sample = 256 * threads
-        cpu_port_rate(max(threads, n_sample // 8), 1, threads, thermal)
+        n_sample = 8192 * threads                      # ~10 s of CPU work on all host threads
+        cpu_port_rate(max(threads, n_sample // 64), 1, threads, thermal)
         rate, _, dt = cpu_port_rate(n_sample, 3, threads, thermal)
         cpu_baseline = {"value": rate, "unit": "LLGS substeps/s", "cores": threads, "kind": "port",
                         "sample": f"{n_sample} envs x 3 steps x 999 RK4 substeps (thermal {'on' if thermal else 'off'}), "
@@ -360,7 +360,10 @@ def main():
                 "peak_source": ("stg_probe_fma measured in this run" if fma_probe_tflops else "theoretical"),
                 "peak_theoretical": fp32_peak_theory, "frac_of_theoretical": achieved / fp32_peak_theory,
                 "algorithmic_flop_per_substep": flop_sub, "substeps_per_launch": n_local * 999,
-                "kernel_ms": kernel_ms, "traffic": None,
+                "kernel_ms": kernel_ms,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size from the ncu --set full capture
+                # (profiles/r01_ncu_stt_env_step_f32_thermal1.csv): 76.2 MB + 146.8 MB; algorithmic 150 B x 1M envs = 157 MB
+                "traffic": 223.0e6 if n_local == N_ENVS_PER_GPU else None,
                 "hbm": {"achieved_gbs": n_local * BYTES_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src},
             },

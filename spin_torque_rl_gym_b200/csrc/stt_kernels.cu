@@ -22,8 +22,11 @@ namespace stg {
 #ifndef STG_BLOCK
 #define STG_BLOCK 64
 #endif
-#ifndef STG_MINBLOCKS
-#define STG_MINBLOCKS 1
+#ifndef STG_MINBLOCKS_DET
+#define STG_MINBLOCKS_DET 12    // no-noise variants: 80 registers, 24 warps/SM measured best (profiles/)
+#endif
+#ifndef STG_MINBLOCKS_NOISE
+#define STG_MINBLOCKS_NOISE 1   // thermal variants: let ptxas keep the 12 Gaussians + Philox state in registers
 #endif
 constexpr int kBlock = STG_BLOCK;   // 64: 65,536 envs -> 1024 CTAs = 6.9 per SM, balanced to 1.2 % on 148 SMs
 
@@ -45,7 +48,7 @@ __device__ __forceinline__ void store_row(float* dst, const float* o) {
 }
 
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>
-__global__ void __launch_bounds__(kBlock, STG_MINBLOCKS) stt_env_step_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_MINBLOCKS_DET : STG_MINBLOCKS_NOISE) stt_env_step_kernel(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) float s_obs[kBlock * kObs];
     const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool active = slot < a.n_envs;
