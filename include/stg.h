@@ -49,6 +49,8 @@ extern "C" {
 #define STG_F_EULER 0x08u            /* SimpleLLGSSolver(method='euler') instead of 'rk4'                          */
 #define STG_F_SORTED 0x10u           /* d_perm holds an env permutation (e.g. sorted by substep count)             */
 #define STG_F_AXIS_Z 0x20u           /* caller asserts stg_stt_all_axis_z(): kernels drop structurally-zero terms   */
+#define STG_F_VECTORIZED_PLAN 0x40u  /* stg_stt_solve_*: n = max(10, int(t_end/max_step)) — VectorizedSolver.solve_batch's step
+                                        policy (utils/vectorized_operations.py:55-57) instead of SimpleLLGSSolver's        */
 
 /* Raw physical parameters of one device parameter set (FP64, SI units). Mirrors the `device_params` dict read by
  * SimpleLLGSSolver._compute_dmdt/_compute_effective_field (physics/simple_solver.py:310-315, 358-380) plus the env
@@ -392,6 +394,16 @@ int stg_vcma_anisotropy_f64(const StgDeviceParams* p, const double* d_voltage, d
  * (offset + row, call_index). */
 int stg_thermal_field_f64(double strength, double decay, double* d_state, double* d_out, uint64_t seed, uint64_t offset,
                           uint64_t call_index, int64_t n, void* stream);
+
+/* EnergyLandscape.compute_energy / compute_energy_gradient (physics/energy_landscape.py:36-104) for n states: m is
+ * normalised, E = Zeeman + uniaxial + demag, gradient = H_app + H_anis + H_demag. Either output may be NULL. */
+typedef struct StgEnergyParams {
+    double mu0, saturation_magnetization, volume, uniaxial_anisotropy;
+    double easy_axis[3];             /* as given                                   */
+    double demag_factors[3];         /* params['demag_factors'], default (0, 0, 1) */
+} StgEnergyParams;
+int stg_energy_landscape_f64(const StgEnergyParams* p, const double* d_m, const double* d_happ, int32_t happ_rows,
+                             double* d_energy, double* d_gradient, int64_t n, void* stream);
 
 /* FMA-pipe throughput probe (bench.py's measured FP32/FP64 roofline denominator): blocks*256 threads x iters*64 FMAs.
  * d_out: >= blocks*256 elements of the probed type (never written in practice). */

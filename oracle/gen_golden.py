@@ -323,6 +323,43 @@ def gen_array():
     print("wrote array_env.npz")
 
 
+def gen_next():
+    """Adjacent components of SURVEY §8(f): VectorizedSolver.solve_batch, EnergyLandscape, LLGSSolver.find_stable_states."""
+    _import_reference()
+    from spin_torque_gym.utils.vectorized_operations import VectorizedSolver
+    from spin_torque_gym.physics.energy_landscape import EnergyLandscape
+    rng = np.random.default_rng(31)
+    n = 12
+    m0 = rng.normal(size=(n, 3))
+    m0 /= np.linalg.norm(m0, axis=1, keepdims=True)
+    plist = []
+    for i in range(n):
+        p = _stt_params(damping=float(rng.uniform(0.005, 0.05)), uniaxial_anisotropy=float(rng.uniform(0.8e6, 1.6e6)),
+                        saturation_magnetization=float(rng.uniform(6e5, 9e5)))
+        if i % 3 == 0:
+            p['easy_axis'] = np.array([0.2 * i / n, -0.1, 1.0])
+        plist.append(p)
+    out = dict(m0=m0)
+    res = VectorizedSolver().solve_batch(m0, (0, 1.5e-10), plist, dt=1e-12)
+    out['vec/m'] = np.array([r['m'] for r in res])
+    out['vec/t'] = res[0]['t']
+    res2 = VectorizedSolver().solve_batch(m0, (0, 3e-12), plist[:1] * n, dt=1e-12)       # T < 10 dt -> 10 steps
+    out['vec_short/m'] = np.array([r['m'] for r in res2])
+    for k in ('damping', 'uniaxial_anisotropy', 'saturation_magnetization'):
+        out[f'vec/{k}'] = np.array([p[k] for p in plist])
+    out['vec/easy_axis'] = np.array([np.asarray(p['easy_axis'], float) for p in plist])
+    lp = _stt_params(demag_factors=np.array([0.1, 0.3, 0.6]), easy_axis=np.array([0.0, 0.6, 0.8]))
+    land = EnergyLandscape(lp)
+    happ = rng.normal(size=(n, 3)) * 1e4
+    mm = rng.normal(size=(n, 3))
+    out['land/m'] = mm; out['land/happ'] = happ
+    out['land/energy'] = np.array([land.compute_energy(mm[i], happ[i]) for i in range(n)])
+    out['land/grad'] = np.array([land.compute_energy_gradient(mm[i], happ[i]) for i in range(n)])
+    out['land/energy0'] = np.array([land.compute_energy(mm[i]) for i in range(n)])
+    np.savez_compressed(os.path.join(GOLD, "next.npz"), **out)
+    print("wrote next.npz")
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["stt", "multi", "array", "rk45", "devices"]
     os.makedirs(GOLD, exist_ok=True)

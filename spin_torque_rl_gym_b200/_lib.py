@@ -17,6 +17,7 @@ F_AUTORESET = 0x04
 F_EULER = 0x08
 F_SORTED = 0x10
 F_AXIS_Z = 0x20
+F_VECTORIZED_PLAN = 0x40
 DEV_STT, DEV_SOT, DEV_VCMA = 0, 1, 2
 NSTATS = 8
 STAT_NAMES = ("steps", "substeps", "terminated", "truncated", "energy", "reward", "guard", "episode_length")
@@ -127,6 +128,11 @@ class StgArrayStepArgs(C.Structure):
                 ("array_offset", C.c_uint64), ("n_arrays", C.c_int64), ("action_stride", C.c_int32), ("flags", C.c_uint32)]
 
 
+class StgEnergyParams(C.Structure):
+    _fields_ = [("mu0", C.c_double), ("saturation_magnetization", C.c_double), ("volume", C.c_double),
+                ("uniaxial_anisotropy", C.c_double), ("easy_axis", c_double3), ("demag_factors", c_double3)]
+
+
 # every symbol include/stg.h declares: (name, restype, argtypes)
 SYMBOLS = {
     "stg_abi_version": (C.c_int, []),
@@ -151,6 +157,8 @@ SYMBOLS = {
     "stg_vcma_anisotropy_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "stg_thermal_field_f64": (C.c_int, [C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                         C.c_uint64, C.c_int64, C.c_void_p]),
+    "stg_energy_landscape_f64": (C.c_int, [C.POINTER(StgEnergyParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                           C.c_void_p, C.c_int64, C.c_void_p]),
     "stg_probe_fma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 

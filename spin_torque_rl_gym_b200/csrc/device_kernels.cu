@@ -103,6 +103,33 @@ __global__ void __launch_bounds__(256) thermal_field_kernel(double strength, dou
     out[3 * i] = strength * x; out[3 * i + 1] = strength * y; out[3 * i + 2] = strength * z;
 }
 
+// EnergyLandscape.compute_energy / compute_energy_gradient (physics/energy_landscape.py:36-104) for n states
+__global__ void __launch_bounds__(256) energy_landscape_kernel(const __grid_constant__ StgEnergyParams p, const double* m,
+                                                               const double* happ, int happ_rows, double* energy,
+                                                               double* grad, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double mx = m[3 * i], my = m[3 * i + 1], mz = m[3 * i + 2];
+    const double nrm = sqrt(mx * mx + my * my + mz * mz);
+    mx /= nrm; my /= nrm; mz /= nrm;
+    const int64_t hr = happ ? (happ_rows == 1 ? 0 : i) : 0;
+    const double hx = happ ? happ[3 * hr] : 0.0, hy = happ ? happ[3 * hr + 1] : 0.0, hz = happ ? happ[3 * hr + 2] : 0.0;
+    const double c = mx * p.easy_axis[0] + my * p.easy_axis[1] + mz * p.easy_axis[2];
+    if (energy) {
+        const double ez = -p.mu0 * p.saturation_magnetization * p.volume * (mx * hx + my * hy + mz * hz);
+        const double ea = -p.uniaxial_anisotropy * p.volume * (c * c);
+        const double ed = 0.5 * p.mu0 * (p.saturation_magnetization * p.saturation_magnetization) * p.volume *
+                          (p.demag_factors[0] * (mx * mx) + p.demag_factors[1] * (my * my) + p.demag_factors[2] * (mz * mz));
+        energy[i] = ez + ea + ed + 0.0;
+    }
+    if (grad) {
+        const double hk = (2.0 * p.uniaxial_anisotropy / (p.mu0 * p.saturation_magnetization)) * c;
+        grad[3 * i] = hx + hk * p.easy_axis[0] + (-p.saturation_magnetization * p.demag_factors[0] * mx);
+        grad[3 * i + 1] = hy + hk * p.easy_axis[1] + (-p.saturation_magnetization * p.demag_factors[1] * my);
+        grad[3 * i + 2] = hz + hk * p.easy_axis[2] + (-p.saturation_magnetization * p.demag_factors[2] * mz);
+    }
+}
+
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace stg
@@ -161,5 +188,14 @@ extern "C" int stg_thermal_field_f64(double strength, double decay, double* d_st
     if (n == 0) return STG_OK;
     thermal_field_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(strength, decay, d_state, d_out, seed, offset,
                                                                         call_index, n);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int stg_energy_landscape_f64(const StgEnergyParams* p, const double* d_m, const double* d_happ, int32_t happ_rows,
+                                        double* d_energy, double* d_gradient, int64_t n, void* stream) {
+    if (!p || !d_m || (!d_energy && !d_gradient)) return STG_E_NULL;
+    if (n < 0 || (d_happ && happ_rows != 1 && happ_rows != n)) return STG_E_SIZE;
+    if (n == 0) return STG_OK;
+    energy_landscape_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*p, d_m, d_happ, happ_rows, d_energy, d_gradient, n);
     return (int)cudaGetLastError();
 }

@@ -325,7 +325,14 @@ STG_HD void solve_body(const StgSttSolveArgs& a, int64_t e) {
     guard_normalise<R>(mx, my, mz, guard);                       // :119
     int nsub = 0;
     if (t_end > 0.0 && (!AXIS_Z || f[FI_AXISZ] != 0.0)) {        // t_end <= t_start: trivial solution (:122-123)
-        const StepPlan plan = substep_plan(t_end, f[FI_MAXSTEP_DT]);
+        StepPlan plan = substep_plan(t_end, f[FI_MAXSTEP_DT]);
+        if (a.flags & STG_F_VECTORIZED_PLAN) {   // utils/vectorized_operations.py:55-57
+            const double q = ddiv(t_end, f[FI_MAXSTEP_DT]);
+            int nv = (q < 2.0e9) ? (int)q : 2000000000;
+            if (nv < 10) nv = 10;
+            plan.n = nv;
+            plan.dt = ddiv(t_end, (double)nv);
+        }
         nsub = plan.n;
         Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
         const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;

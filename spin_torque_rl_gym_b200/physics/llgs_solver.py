@@ -159,3 +159,19 @@ class LLGSSolver:
             raise RuntimeError("LLGS integration failed: trajectory buffer overflow")
         return {"t": traj[:, 0], "m": traj[:, 1:4], "energy": traj[:, 4], "torques": traj[:, 5], "success": status == 0,
                 "n_accepted": rows - 1, "n_rejected": int(r["n_rejected"][0])}
+
+    def find_stable_states(self, device_params: Dict[str, Any], n_trials: int = 100, threshold: float = 1e-6,
+                           relax_time: float = 10e-9, seed: Optional[int] = None) -> np.ndarray:
+        """Relax `n_trials` random starts for 10 ns without current / field / noise in ONE launch and return the distinct end
+        states (physics/llgs_solver.py:264-305)."""
+        rng = np.random.default_rng(seed)
+        m0 = rng.normal(0, 1, (n_trials, 3))
+        m0 /= np.linalg.norm(m0, axis=1, keepdims=True)
+        r = self.solve_batch(m0, relax_time, device_params, current=0.0, thermal_noise=False)
+        ok = r["success"].cpu().numpy()
+        finals = r["m"].cpu().numpy()[ok]
+        stable = []
+        for m in finals:
+            if all(np.linalg.norm(m - s) >= threshold for s in stable):
+                stable.append(m)
+        return np.array(stable) if stable else np.array([[0, 0, 1]])
