@@ -111,7 +111,7 @@ def make_actions(n, seed):
 
 
 ENV_KW = dict(device_type="stt_mram", max_current=1.1e-6, temperature=300.0, include_thermal_fluctuations=True,
-              integrator="rk4", autoreset=True)
+              integrator="rk4", autoreset=True, sort_by_substeps=False)   # fixed pulse duration: nothing to sort
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -329,6 +329,11 @@ def main():
             variant("substeps_per_s_65536_envs", 65536)
             variant("substeps_per_s_f64_thermal", n_local // 4, dtype=torch.float64)
             variant("substeps_per_s_f64_thermal_off", n_local // 4, dtype=torch.float64, include_thermal_fluctuations=False)
+            try:       # BASELINE configs[2], configs[3] and the ragged-duration variant of configs[1] (tools/bench_extra.py)
+                from tools.bench_extra import collect
+                extras["other_configs"] = collect(dev)
+            except Exception as exc:  # noqa: BLE001 - secondary numbers must never break the contract line
+                extras["other_configs_error"] = repr(exc)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

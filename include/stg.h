@@ -215,9 +215,10 @@ int stg_stt_reset(const StgSttResetArgs* args, void* stream);
 
 /* Counting sort of envs by substep count (descending) so that warps are homogeneous when pulse durations differ
  * (physics/simple_solver.py:137-139 gives n in [10, 5000]). d_perm [n] int32 out; d_work >= STG_SORT_WORK_INTS int32
- * scratch (zeroed by the call). */
+ * scratch (zeroed by the call). When every env has the same substep count the identity permutation is written, so the
+ * sorted launch keeps coalesced accesses. The order inside one bin is unspecified; results never depend on it. */
 #define STG_SORT_BINS 8192
-#define STG_SORT_WORK_INTS STG_SORT_BINS
+#define STG_SORT_WORK_INTS (STG_SORT_BINS + 8)
 int stg_stt_sort_by_substeps(const StgSttFolded* d_table, int32_t n_sets, const int32_t* d_param_index,
                              const float* d_action, int32_t* d_perm, int32_t* d_work, int64_t n_envs, void* stream);
 

@@ -22,7 +22,7 @@ DEV_STT, DEV_SOT, DEV_VCMA = 0, 1, 2
 NSTATS = 8
 STAT_NAMES = ("steps", "substeps", "terminated", "truncated", "energy", "reward", "guard", "episode_length")
 FOLDED_DOUBLES = 40
-SORT_WORK_INTS = 8192
+SORT_WORK_INTS = 8192 + 8
 OBS_DIM = 12
 
 

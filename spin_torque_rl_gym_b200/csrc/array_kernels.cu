@@ -10,7 +10,8 @@
 
 namespace stg {
 
-constexpr int kArrayBlock = 64;
+constexpr int kArrayBlock = 32;     // one warp per crossbar array; 24 CTAs (= arrays) resident per SM hide the FP64 latency
+constexpr int kArrayMinBlocks = 24;
 
 __device__ __forceinline__ void array_draw_pattern(const StgArrayStepArgs& a, int64_t arr, uint32_t episode, int nd,
                                                    double* pattern) {
@@ -39,7 +40,7 @@ __device__ __forceinline__ void array_store_obs(float* obs, const double* patter
     }
 }
 
-__global__ void __launch_bounds__(kArrayBlock) array_step_kernel(const __grid_constant__ StgArrayStepArgs a) {
+__global__ void __launch_bounds__(kArrayBlock, kArrayMinBlocks) array_step_kernel(const __grid_constant__ StgArrayStepArgs a) {
     extern __shared__ double smem[];
     const int nd = a.params.n_rows * a.params.n_cols;
     double* pattern = smem;                 // [nd][3]
@@ -52,14 +53,33 @@ __global__ void __launch_bounds__(kArrayBlock) array_step_kernel(const __grid_co
     const double* gt = a.d_target + arr * nd * 3;
     for (int q = threadIdx.x; q < nd * 3; q += blockDim.x) { pattern[q] = gp[q]; target[q] = gt[q]; }
     __syncthreads();
+    const StgArrayParams& p = a.params;
+    __shared__ double s_prev, s_energy, s_sim, s_mean;
+    __shared__ ArrayAction s_act;
+    // per-device dot products / norms in parallel, NumPy-ordered sums by lane 0 (bit-identical to the sequential form)
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) scratch[i] = dot_u(pattern + 3 * i, target + 3 * i);
+    __syncthreads();
     if (threadIdx.x == 0) {
-        const StgArrayParams& p = a.params;
-        const double prev = array_similarity(pattern, target, nd, scratch);
-        const ArrayAction act = array_parse_action(p, a.d_action + arr * a.action_stride);
-        const double energy = array_apply_action(p, a.d_coupling, pattern, act);
-        const double sim = array_similarity(pattern, target, nd, scratch);
+        s_prev = ddiv(numpy_sum(scratch, nd), (double)nd);
+        s_act = array_parse_action(p, a.d_action + arr * a.action_stride);
+        s_energy = array_apply_action(p, a.d_coupling, pattern, s_act);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) scratch[i] = dot_u(pattern + 3 * i, target + 3 * i);
+    __syncthreads();
+    if (threadIdx.x == 0) s_sim = ddiv(numpy_sum(scratch, nd), (double)nd);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) scratch[i] = norm_u(pattern + 3 * i);
+    __syncthreads();
+    if (threadIdx.x == 0) s_mean = ddiv(numpy_sum(scratch, nd), (double)nd);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) { const double d = dadd(scratch[i], -s_mean); scratch[i] = dmul(d, d); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double prev = s_prev, energy = s_energy, sim = s_sim;
+        const ArrayAction act = s_act;
         const bool success = sim >= p.success_threshold;
-        const double sd = array_magnitude_std(pattern, nd, scratch);
+        const double sd = sqrt(ddiv(numpy_sum(scratch, nd), (double)nd));
         const double reward = array_reward(p, success, sim, energy, dadd(sim, -prev), sd);
         const int step = a.d_step_count[arr] + 1;
         const double tot = dadd(a.d_total_energy[arr], energy);

@@ -59,7 +59,10 @@ struct Philox {
     STG_HD void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const {
         uint32_t a = k0, b = k1;
 #pragma unroll
-        for (int r = 0; r < 10; ++r) {
+#ifndef STG_PHILOX_ROUNDS
+#define STG_PHILOX_ROUNDS 10
+#endif
+        for (int r = 0; r < STG_PHILOX_ROUNDS; ++r) {
             uint32_t h0, l0, h1, l1;
             mulhilo(0xD2511F53u, c0, h0, l0);
             mulhilo(0xCD9E8D57u, c2, h1, l1);
@@ -93,7 +96,9 @@ STG_HD float fast_sqrt(float x) {
 #endif
 }
 STG_HD void fast_sincos(float ang, float& s, float& c) {   // angle in radians, [0, 2 pi)
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(STG_EXP_NO_SINCOS)
+    s = ang * 0.1f; c = 1.0f - s;      // timing experiment only
+#elif defined(__CUDA_ARCH__)
     s = __sinf(ang);
     c = __cosf(ang);
 #else
@@ -128,16 +133,43 @@ STG_HD void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
     box_muller_scaled(u0, u1, -1.3862943611198906f, n0, n1);
 }
 
-// 12 samples N(0, scale^2) for the 4 stages of RK4 substep `sub` of env-step `step` of env `gid` (3 Philox calls)
+// radius uniform from the top 23 bits (no int->float conversion): a in (0, 1], tail of the normals out to 5.65 sigma
+STG_HD float bits_to_open_unit(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return 2.0f - __uint_as_float(0x3f800000u | (x >> 9));
+#else
+    union { uint32_t u; float f; } v;
+    v.u = 0x3f800000u | (x >> 9);
+    return 2.0f - v.f;
+#endif
+}
+// Box-Muller pair from one 32-bit word `w` (23-bit radius uniform in its top bits, 9 angle bits in its low bits) plus 10 more
+// angle bits `extra` (19-bit angle = 524,288 directions)
+STG_HD void box_muller_packed(uint32_t w, uint32_t extra10, float neg2ln2_scale2, float& n0, float& n1) {
+    const float r = fast_sqrt(neg2ln2_scale2 * fast_lg2(bits_to_open_unit(w)));
+    const uint32_t ang_bits = ((w & 0x1ffu) << 23) | ((extra10 & 0x3ffu) << 13);   // 19 bits in the top of a word
+    float s, c;
+    fast_sincos(bits_to_angle(ang_bits), s, c);
+    n0 = r * c;
+    n1 = r * s;
+}
+
+// 12 samples N(0, scale^2) for the 4 stages of RK4 substep `sub` of env-step `step` of env `gid`.
+// Bit budget: TWO Philox4x32-10 blocks (256 bits) per substep = 6 Box-Muller pairs x (23-bit radius + 19-bit angle). The
+// integer multiplies of Philox are the most expensive instructions of the thermal kernel (ncu: 39 % of its time with three
+// blocks per substep), so the third block that full 32-bit uniforms would need is not spent.
 STG_HD void philox_normals12(const Philox& ph, uint64_t gid, uint32_t step, uint32_t sub, float neg2ln2_scale2,
                              float xi[12]) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        uint32_t o[4];
-        ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u + (uint32_t)c, o);
-        box_muller_scaled(o[0], o[1], neg2ln2_scale2, xi[4 * c + 0], xi[4 * c + 1]);
-        box_muller_scaled(o[2], o[3], neg2ln2_scale2, xi[4 * c + 2], xi[4 * c + 3]);
-    }
+    uint32_t a[4], b[4];
+    ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u, a);
+    ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u + 1u, b);
+    // words a0..a3, b0, b1 carry (radius, 9 angle bits); b2, b3 carry 6 x 10 further angle bits
+    box_muller_packed(a[0], b[2], neg2ln2_scale2, xi[0], xi[1]);
+    box_muller_packed(a[1], b[2] >> 10, neg2ln2_scale2, xi[2], xi[3]);
+    box_muller_packed(a[2], b[2] >> 20, neg2ln2_scale2, xi[4], xi[5]);
+    box_muller_packed(a[3], b[3], neg2ln2_scale2, xi[6], xi[7]);
+    box_muller_packed(b[0], b[3] >> 10, neg2ln2_scale2, xi[8], xi[9]);
+    box_muller_packed(b[1], b[3] >> 20, neg2ln2_scale2, xi[10], xi[11]);
 }
 STG_HD void philox_normals4(const Philox& ph, uint64_t gid, uint32_t step, uint32_t sub, uint32_t lane,
                             float neg2ln2_scale2, float xi[4]) {

@@ -57,9 +57,16 @@ struct LlgRhs {
     // llgs_rhs (physics/llgs_solver.py:92-126) generalised with the SOT terms (devices/sot_mram.py:163-194)
     STG_HD V3 operator()(double t, V3 y) {
         const StgLlgParams& q = *p;
-        V3 m = {0.0, 0.0, 1.0};                               // :96-101
-        const double nrm = sqrt(dot3(y, y));
-        if (nrm > 1e-12) { m.x = y.x / nrm; m.y = y.y / nrm; m.z = y.z / nrm; }
+        V3 m = {0.0, 0.0, 1.0};                               // :96-101 (y * (1/|y|): <= 1 ulp from NumPy's y / |y|)
+        const double n2 = dot3(y, y);
+        if (n2 > 1e-24) {
+#if defined(__CUDA_ARCH__)
+            const double inv = rsqrt(n2);
+#else
+            const double inv = 1.0 / sqrt(n2);
+#endif
+            m.x = y.x * inv; m.y = y.y * inv; m.z = y.z * inv;
+        }
         const double cur = (t <= t_pulse) ? J : 0.0;
         const V3 e = {q.easy_axis[0], q.easy_axis[1], q.easy_axis[2]};
         const double s = hk * dot3(m, e);
@@ -86,14 +93,15 @@ struct LlgRhs {
         ++n_eval;
         V3 tau = {0.0, 0.0, 0.0};
         if (!(fabs(cur) < 1e-12)) {                            // :221-222
-            const V3 ph3 = {q.p_hat[0], q.p_hat[1], q.p_hat[2]};
-            const V3 mxp = cross3(m, ph3);
-            const V3 dl = (q.c_dl_p * cur) * cross3(m, mxp);
-            const V3 fl = (q.c_fl_p * cur) * mxp;
-            const V3 sg = {q.sigma[0], q.sigma[1], q.sigma[2]};
-            const V3 sdl = (q.c_dl_s * cur) * cross3(sg, m);
-            const V3 sfl = (q.c_fl_s * cur) * sg;
-            tau = dl + fl + sdl + sfl;
+            if (q.c_dl_p != 0.0 || q.c_fl_p != 0.0) {          // Slonczewski pair (uniform branch per parameter set)
+                const V3 ph3 = {q.p_hat[0], q.p_hat[1], q.p_hat[2]};
+                const V3 mxp = cross3(m, ph3);
+                tau = tau + (q.c_dl_p * cur) * cross3(m, mxp) + (q.c_fl_p * cur) * mxp;
+            }
+            if (q.c_dl_s != 0.0 || q.c_fl_s != 0.0) {          // spin-orbit pair
+                const V3 sg = {q.sigma[0], q.sigma[1], q.sigma[2]};
+                tau = tau + (q.c_dl_s * cur) * cross3(sg, m) + (q.c_fl_s * cur) * sg;
+            }
         }
         V3 dm = (-q.gamma) * cross3(m, h);                     // :121-124
         dm = dm + q.alpha * cross3(m, dm);

@@ -8,7 +8,10 @@
 
 namespace stg {
 
-__global__ void __launch_bounds__(64) llgs_rk45_kernel(const __grid_constant__ StgRk45Args a) {
+#ifndef STG_RK45_MINBLOCKS
+#define STG_RK45_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(64, STG_RK45_MINBLOCKS) llgs_rk45_kernel(const __grid_constant__ StgRk45Args a) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < a.n_envs) rk45_body(a, e);
 }

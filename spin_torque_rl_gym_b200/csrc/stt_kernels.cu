@@ -137,11 +137,15 @@ __global__ void sort_hist_kernel(const StgSttFolded* table, const int32_t* pidx,
 }
 __global__ void sort_scan_kernel(int32_t* hist) {   // one block of 1024 threads, 8 bins each: exclusive scan in place
     __shared__ int32_t s[1024];
+    __shared__ int32_t s_nonempty;
     const int t = threadIdx.x;
+    if (t == 0) s_nonempty = 0;
+    __syncthreads();
     int32_t loc[8];
-    int32_t sum = 0;
+    int32_t sum = 0, ne = 0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { loc[q] = hist[t * 8 + q]; sum += loc[q]; }
+    for (int q = 0; q < 8; ++q) { loc[q] = hist[t * 8 + q]; sum += loc[q]; ne += loc[q] != 0; }
+    if (ne) atomicAdd(&s_nonempty, ne);
     s[t] = sum;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {
@@ -153,13 +157,18 @@ __global__ void sort_scan_kernel(int32_t* hist) {   // one block of 1024 threads
     int32_t run = s[t] - sum;
 #pragma unroll
     for (int q = 0; q < 8; ++q) { hist[t * 8 + q] = run; run += loc[q]; }
+    if (t == 0) hist[STG_SORT_BINS] = s_nonempty;   // number of distinct substep counts
 }
 __global__ void sort_scatter_kernel(const StgSttFolded* table, const int32_t* pidx, const float* action, int32_t* hist,
                                     int32_t* perm, int64_t n) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) {
-        const int pos = atomicAdd(hist + action_bin(table, pidx, action, e), 1);
-        perm[pos] = (int32_t)e;
+        if (hist[STG_SORT_BINS] <= 1) {   // every env integrates the same number of substeps: keep the coalesced identity order
+            perm[e] = (int32_t)e;
+        } else {
+            const int pos = atomicAdd(hist + action_bin(table, pidx, action, e), 1);
+            perm[pos] = (int32_t)e;
+        }
     }
 }
 
@@ -344,7 +353,7 @@ extern "C" int stg_stt_sort_by_substeps(const StgSttFolded* d_table, int32_t n_s
     if (n_envs < 0 || n_sets <= 0 || n_envs > 2147483647LL) return STG_E_SIZE;
     if (n_envs == 0) return STG_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t err = cudaMemsetAsync(d_work, 0, sizeof(int32_t) * STG_SORT_BINS, s);
+    cudaError_t err = cudaMemsetAsync(d_work, 0, sizeof(int32_t) * STG_SORT_WORK_INTS, s);
     if (err != cudaSuccess) return (int)err;
     const unsigned grid = (unsigned)((n_envs + 255) / 256);
     sort_hist_kernel<<<grid, 256, 0, s>>>(d_table, d_param_index, d_action, d_work, n_envs);

@@ -305,7 +305,8 @@ class SpinTorqueVectorEnv:
             flags |= _lib.F_THERMAL_PHILOX
         stream = self._stream()
         with torch.cuda.device(self.device):
-            do_sort = self._sort_mode is True
+            # 'auto': the counting sort costs three tiny launches; ragged pulse durations run ~2x faster sorted
+            do_sort = self._sort_mode is True or (self._sort_mode == "auto" and N >= 4096)
             if do_sort:
                 _lib.check(self._lib.stg_stt_sort_by_substeps(
                     self._table.data_ptr(), self._n_sets, _lib.ptr(self._param_index), act.data_ptr(),

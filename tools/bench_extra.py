@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Secondary workloads of BASELINE.json (configs[2], [3]) and the ragged-duration variant of configs[1], device-timed.
+
+    python tools/bench_extra.py            # prints one JSON line
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import spin_torque_rl_gym_b200 as stg  # noqa: E402
+from spin_torque_rl_gym_b200 import params as P  # noqa: E402
+from spin_torque_rl_gym_b200.physics import LLGSSolver  # noqa: E402
+
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def collect(dev=None):
+    dev = dev or torch.device("cuda", 0)
+    out = {}
+    rng = np.random.default_rng(0)
+    # ---- configs[2]: SOT + VCMA mix, adaptive RK45 (atol 1e-9, rtol 1e-6), 262,144 envs ---------------------------------
+    n = 262144
+    sot = P.default_device_parameters("sot_mram"); sot.update(aspect_ratio=2.0, spin_hall_angle=0.3)
+    vcma = P.default_device_parameters("vcma_mram"); vcma.update(aspect_ratio=1.5)
+    m0 = torch.from_numpy(rng.normal(size=(n, 3))).to(dev)
+    pidx = torch.arange(n, device=dev, dtype=torch.int32) % 2
+    cur = torch.where(pidx == 0, torch.from_numpy(rng.uniform(-3e11, 3e11, n)).to(dev), torch.zeros(n, dtype=torch.float64, device=dev))
+    volt = torch.where(pidx == 1, torch.from_numpy(rng.uniform(-2.5, 2.5, n)).to(dev), torch.zeros(n, dtype=torch.float64, device=dev))
+    t_end = torch.full((n,), 1e-10, dtype=torch.float64, device=dev)
+    solver = LLGSSolver(device=dev)
+    res = {}
+
+    def rk():
+        res["r"] = solver.solve_batch(m0, t_end, [sot, vcma], current=cur, voltage=volt, param_index=pidx,
+                                      device_type=["sot_mram", "vcma_mram"])
+    ms = timed(rk, reps=3, warm=1)
+    attempts = float((res["r"]["n_accepted"] + res["r"]["n_rejected"]).sum())
+    out["rk45_mix_262144"] = {"ms_per_solve": ms, "attempted_steps_per_s": attempts / (ms * 1e-3),
+                              "rhs_evals_per_s": float(res["r"]["n_rhs"].sum()) / (ms * 1e-3),
+                              "accepted_per_env": attempts / n, "fp64_tflops_algorithmic": attempts * 766 / (ms * 1e-3) / 1e12}
+    # ---- configs[3]: 16,384 8x8 dipolar crossbars --------------------------------------------------------------------------
+    A = 16384
+    for mode in ("individual", "row", "global"):
+        env = stg.SpinTorqueArrayVectorEnv(num_envs=A, array_size=(8, 8), action_mode=mode, device=dev, rng_seed=1)
+        env.reset(seed=1)
+        k = 2 if mode == "global" else 3
+        act = torch.zeros(A, k, dtype=torch.float32, device=dev)
+        if mode == "global":
+            act[:, 0] = torch.from_numpy(rng.uniform(-2e6, 2e6, A)).to(dev); act[:, 1] = 2e-9
+        else:
+            hi = 63 if mode == "individual" else 7
+            act[:, 0] = torch.from_numpy(rng.uniform(0, hi, A)).to(dev)
+            act[:, 1] = torch.from_numpy(rng.uniform(-2e6, 2e6, A)).to(dev); act[:, 2] = 2e-9
+        ms = timed(lambda: env.step(act), reps=10, warm=3)
+        out[f"array_8x8_{mode}_16384"] = {"ms_per_step": ms, "array_steps_per_s": A / (ms * 1e-3),
+                                          "hbm_gbs_algorithmic": A * 64 * 96 / (ms * 1e-3) / 1e9}
+    # ---- configs[1] with ragged durations T ~ U(1e-12, 5e-9): unsorted vs sorted launch -------------------------------------
+    N = 1 << 20
+    act = torch.zeros(N, 2, dtype=torch.float32, device=dev)
+    act[:, 0] = torch.from_numpy(rng.uniform(-1.1e-6, 1.1e-6, N)).to(dev)
+    act[:, 1] = torch.from_numpy(rng.uniform(1e-12, 5e-9, N)).to(dev)
+    for sort in (False, True):
+        env = stg.SpinTorqueVectorEnv(num_envs=N, device=dev, max_current=1.1e-6, include_thermal_fluctuations=True,
+                                      rng_seed=2, sort_by_substeps=sort)
+        env.reset(seed=2)
+        ms = timed(lambda: env.step(act), reps=5, warm=2)
+        sub = float(env._n_sub.sum())
+        out[f"ragged_T_uniform_{'sorted' if sort else 'unsorted'}"] = {"ms_per_step": ms, "substeps_per_s": sub / (ms * 1e-3)}
+    return out
+
+
+if __name__ == "__main__":
+    print(json.dumps(collect()))
