@@ -130,10 +130,27 @@ __global__ void __launch_bounds__(128) stt_env_reset_kernel(const __grid_constan
 }
 
 // ---- counting sort of envs by substep count (descending) -------------------------------------------------------------
+// Warp-aggregated atomics: lanes that fall into the same bin elect a leader which issues ONE atomicAdd for the group
+// (with a fixed pulse duration all 1M envs share a bin; un-aggregated that is 1M serialised atomics on one address).
+__device__ __forceinline__ int warp_aggregated_inc(int32_t* counters, int bin, bool valid) {
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    int pos = 0;
+    if (valid) {
+        const unsigned peers = __match_any_sync(active, bin);
+        const int leader = __ffs(peers) - 1;
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(counters + bin, __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        pos = base + __popc(peers & ((1u << lane) - 1u));
+    }
+    return pos;
+}
 __global__ void sort_hist_kernel(const StgSttFolded* table, const int32_t* pidx, const float* action, int32_t* hist,
                                  int64_t n) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) atomicAdd(hist + action_bin(table, pidx, action, e), 1);
+    const bool valid = e < n;
+    warp_aggregated_inc(hist, valid ? action_bin(table, pidx, action, e) : 0, valid);
 }
 __global__ void sort_scan_kernel(int32_t* hist) {   // one block of 1024 threads, 8 bins each: exclusive scan in place
     __shared__ int32_t s[1024];
@@ -162,14 +179,13 @@ __global__ void sort_scan_kernel(int32_t* hist) {   // one block of 1024 threads
 __global__ void sort_scatter_kernel(const StgSttFolded* table, const int32_t* pidx, const float* action, int32_t* hist,
                                     int32_t* perm, int64_t n) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) {
-        if (hist[STG_SORT_BINS] <= 1) {   // every env integrates the same number of substeps: keep the coalesced identity order
-            perm[e] = (int32_t)e;
-        } else {
-            const int pos = atomicAdd(hist + action_bin(table, pidx, action, e), 1);
-            perm[pos] = (int32_t)e;
-        }
+    const bool valid = e < n;
+    if (hist[STG_SORT_BINS] <= 1) {   // every env integrates the same number of substeps: keep the coalesced identity order
+        if (valid) perm[e] = (int32_t)e;
+        return;
     }
+    const int pos = warp_aggregated_inc(hist, valid ? action_bin(table, pidx, action, e) : 0, valid);
+    if (valid) perm[pos] = (int32_t)e;
 }
 
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>

@@ -330,3 +330,28 @@ def test_invalid_solver_params_keep_magnetisation(cuda_device):
     assert _torch().equal(env.magnetization, m0)
     assert int(info["status"].min()) == 2 and np.isfinite(r.cpu().numpy()).all()
     assert float(info["step_energy"].min()) > 0
+
+
+@pytest.mark.parametrize("n", [1, 31, 65, 1000])
+def test_odd_batch_sizes_and_extreme_actions(n, cuda_device):
+    """Batch sizes that are not multiples of the 64-thread CTA, durations at both clamps (10 and 5000 substeps), currents at
+    both clamps, against the C oracle."""
+    from oracle.c_oracle import COracleEnv
+    jm = 1.1e-6
+    rng = np.random.default_rng(n)
+    m0 = rng.normal(size=(n, 3))
+    tgt = np.tile([0.0, 0.0, -1.0], (n, 1))
+    act = np.stack([rng.uniform(-jm, jm, n), rng.uniform(1e-12, 6e-10, n)], 1).astype(np.float32)
+    act[0] = [5 * jm, 1.0]              # both clamped: J -> max_current, T -> max_duration (5000 substeps, capped below)
+    act[-1] = [-5 * jm, 0.0]            # T -> 1e-12 (100 substeps of 1e-14)
+    env = _make(n, "f64", cuda_device, max_current=jm, max_duration=2e-9, include_thermal_fluctuations=False)
+    ora = COracleEnv(n, max_current=jm, max_duration=2e-9, include_thermal=False, nthreads=2)
+    env.reset(options={"initial_state": m0, "target_state": tgt})
+    ora.reset(m0, tgt)
+    o, r, te, tr, info = env.step(act.copy())
+    oo, orr, ote, otr = ora.step(act)
+    assert np.array_equal(info["n_sub"].cpu().numpy(), ora.n_sub)
+    assert int(info["n_sub"][-1]) == 100 and (n == 1 or int(info["n_sub"][0]) == 2000)
+    assert np.abs(env.magnetization.cpu().numpy() - ora.m).max() < 1e-6
+    assert np.abs(o.cpu().numpy() - oo).max() < 1e-6 and np.allclose(r.cpu().numpy(), orr, rtol=1e-6, atol=1e-6)
+    assert o.shape == (n, 12) and float(o[-1, 10]) == -1.0 and (n == 1 or float(o[0, 10]) == 1.0)
