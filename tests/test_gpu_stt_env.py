@@ -355,3 +355,41 @@ def test_odd_batch_sizes_and_extreme_actions(n, cuda_device):
     assert np.abs(env.magnetization.cpu().numpy() - ora.m).max() < 1e-6
     assert np.abs(o.cpu().numpy() - oo).max() < 1e-6 and np.allclose(r.cpu().numpy(), orr, rtol=1e-6, atol=1e-6)
     assert o.shape == (n, 12) and float(o[-1, 10]) == -1.0 and (n == 1 or float(o[0, 10]) == 1.0)
+
+
+def test_device_mix_param_index(cuda_device):
+    """Three parameter sets (STT / SOT / VCMA resistance forms, different damping / anisotropy / volume) selected per env through
+    param_index: each env must behave exactly like a single-set env of its own kind, and the resistance-dependent outputs
+    (Joule energy, obs[6]) must follow the device formulas of the oracle (devices/*:compute_resistance)."""
+    import torch
+    from oracle import devices_oracle as DO
+    from spin_torque_rl_gym_b200 import SpinTorqueVectorEnv, params as P
+    jm, n = 1.1e-6, 96
+    stt = P.default_device_parameters("stt_mram")
+    sot = dict(P.default_device_parameters("sot_mram"), polarization=0.6, reference_magnetization=np.array([0.0, 0.0, 1.0]))
+    vcma = dict(P.default_device_parameters("vcma_mram"), polarization=0.5, volume=2e-23)
+    types, plist = ["stt_mram", "sot_mram", "vcma_mram"], [stt, sot, vcma]
+    rng = np.random.default_rng(1)
+    m0 = rng.normal(size=(n, 3))
+    tgt = np.tile([0.0, 0.0, 1.0], (n, 1))
+    act = np.stack([rng.uniform(-jm, jm, n), rng.uniform(1e-11, 4e-10, n)], 1).astype(np.float32)
+    pidx = np.arange(n) % 3
+    kw = dict(max_current=jm, include_thermal_fluctuations=False, autoreset=False, dtype=torch.float64, device=cuda_device)
+    mix = SpinTorqueVectorEnv(num_envs=n, device_type=types, device_params=plist, param_index=pidx, **kw)
+    mix.reset(options={"initial_state": m0, "target_state": tgt})
+    o, r, te, tr, info = mix.step(act.copy())
+    m0n = m0 / np.linalg.norm(m0, axis=1, keepdims=True)
+    for k, (t, p) in enumerate(zip(types, plist)):
+        sel = pidx == k
+        one = SpinTorqueVectorEnv(num_envs=int(sel.sum()), device_type=t, device_params=p, **kw)
+        one.reset(options={"initial_state": m0[sel], "target_state": tgt[sel]})
+        o1, r1, *_ , i1 = one.step(act[sel].copy())
+        assert torch.equal(o[torch.as_tensor(sel)], o1) and torch.equal(r[torch.as_tensor(sel)], r1)
+        res_before = DO.resistance(t, p, m0n[sel])
+        J = np.clip(act[sel, 0].astype(np.float64), -jm, jm)
+        T = np.clip(act[sel, 1].astype(np.float64), 1e-12, 5e-9)
+        e_ref = (J * res_before * p.get("area", 1e-14)) ** 2 / res_before * T
+        assert np.allclose(i1["step_energy"].cpu().numpy(), e_ref, rtol=1e-12)
+        m_after = one.magnetization.cpu().numpy()
+        assert np.allclose(o1.cpu().numpy()[:, 6], DO.resistance(t, p, m_after) / p["resistance_parallel"], rtol=1e-6)
+        assert int(i1["status"].max()) == 0 and float((m_after - m0n[sel]).__abs__().max()) > 1e-6
