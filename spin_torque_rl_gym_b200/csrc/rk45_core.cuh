@@ -11,9 +11,6 @@
 
 #include "../../include/stg.h"
 #include "llgs_core.cuh"
-#ifdef STG_DEBUG_RK45
-#include <cstdio>
-#endif
 
 namespace stg {
 
@@ -189,9 +186,6 @@ STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
         r[0] = tt; r[1] = m.x; r[2] = m.y; r[3] = m.z; r[4] = en; r[5] = tq;
     };
     record(0, t, y);
-#ifdef STG_DEBUG_RK45
-    printf("rk45 e=%lld tb=%g rtol=%g atol=%g max_step=%g J=%g tp=%g hk=%g flags=%u\n", (long long)e, tb, rtol, atol, max_step, f.J, f.t_pulse, f.hk, a.flags);
-#endif
 
     if (tb > t0) {
         V3 fk = f(t, y);                                        // rk.py:94
@@ -212,65 +206,58 @@ STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
             else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
             h_abs = fmin(fmin(100.0 * h0, h1), fmin(interval, max_step));
         }
-        // solve_ivp main loop: step until t == t_bound (ivp.py), RungeKutta._step_impl (rk.py:111-167)
-#ifdef STG_DEBUG_RK45
-        printf("rk45 h_abs=%g fk=(%g %g %g) n_eval=%d\n", h_abs, fk.x, fk.y, fk.z, f.n_eval);
-#endif
+        // solve_ivp main loop: step until t == t_bound (ivp.py), RungeKutta._step_impl (rk.py:111-167).
+        // SciPy nests "while not step_accepted" inside the stepping loop; here ONE flat loop performs one attempt per iteration
+        // for every lane that is still integrating, so the lanes of a warp stay converged on the six RHS evaluations whether
+        // their previous attempt was accepted or rejected (nested loops make the whole warp pay for every lane's rejection).
         const int64_t max_attempts = a.max_attempts > 0 ? a.max_attempts : 1000000;
         int64_t attempts = 0;
+        bool new_step = true, rejected = false;
+        double min_step = 0.0;
         while (t != tb && status == 0) {
-            const double min_step = 10.0 * ulp_above(t);
-            if (h_abs > max_step) h_abs = max_step;
-            else if (h_abs < min_step) h_abs = min_step;
-            bool accepted = false, rejected = false;
-            V3 y_new = y, f_new = fk;
-            double t_new = t;
-            while (!accepted) {
-                if (h_abs < min_step) { status |= 1; break; }   // TOO_SMALL_STEP
-                if (++attempts > max_attempts) { status |= 4; break; }
-                double h = h_abs;
-                t_new = t + h;
-                if (t_new - tb > 0.0) t_new = tb;
-                h = t_new - t;
-                h_abs = fabs(h);
-                // rk_step (rk.py:14-72)
-                const V3 k1 = fk;
-                const V3 k2 = f(t + T::c2 * h, y + h * (T::a21 * k1));
-                const V3 k3 = f(t + T::c3 * h, y + h * (T::a31 * k1 + T::a32 * k2));
-                const V3 k4 = f(t + T::c4 * h, y + h * (T::a41 * k1 + T::a42 * k2 + T::a43 * k3));
-                const V3 k5 = f(t + T::c5 * h, y + h * (T::a51 * k1 + T::a52 * k2 + T::a53 * k3 + T::a54 * k4));
-                const V3 k6 = f(t + h, y + h * (T::a61 * k1 + T::a62 * k2 + T::a63 * k3 + T::a64 * k4 + T::a65 * k5));
-                y_new = y + h * (T::b1 * k1 + T::b3 * k3 + T::b4 * k4 + T::b5 * k5 + T::b6 * k6);
-                f_new = f(t + h, y_new);
-                const V3 err = h * (T::e1 * k1 + T::e3 * k3 + T::e4 * k4 + T::e5 * k5 + T::e6 * k6 + T::e7 * f_new);
-                const V3 mx = vabs_max(y, y_new);
-                const double en = rms3({err.x / (atol + mx.x * rtol), err.y / (atol + mx.y * rtol), err.z / (atol + mx.z * rtol)});
-#ifdef STG_DEBUG_RK45
-                if (attempts < 4) printf("rk45 attempt %lld h=%g en=%g t_new=%g\n", (long long)attempts, h, en, t_new);
-#endif
-                if (en < 1.0) {
-                    double factor = (en == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(en, -0.2));
-                    if (rejected) factor = fmin(1.0, factor);
-                    h_abs *= factor;
-                    accepted = true;
-                } else if (en >= 1.0) {
-                    h_abs *= fmax(0.2, 0.9 * pow(en, -0.2));
-                    rejected = true;
-                    ++n_rej;
-                } else {               // NaN error norm: SciPy would loop forever shrinking nothing; flag and stop
-                    status |= 8;
-                    break;
-                }
+            if (new_step) {                                   // head of _step_impl
+                min_step = 10.0 * ulp_above(t);
+                if (h_abs > max_step) h_abs = max_step;
+                else if (h_abs < min_step) h_abs = min_step;
+                rejected = false;
+                new_step = false;
             }
-            if (!accepted) break;
-            t = t_new; y = y_new; fk = f_new;
-            ++n_acc;
-            record(n_acc, t, y);
+            if (h_abs < min_step) { status |= 1; break; }     // TOO_SMALL_STEP
+            if (++attempts > max_attempts) { status |= 4; break; }
+            double h = h_abs;
+            double t_new = t + h;
+            if (t_new - tb > 0.0) t_new = tb;
+            h = t_new - t;
+            h_abs = fabs(h);
+            // rk_step (rk.py:14-72)
+            const V3 k1 = fk;
+            const V3 k2 = f(t + T::c2 * h, y + h * (T::a21 * k1));
+            const V3 k3 = f(t + T::c3 * h, y + h * (T::a31 * k1 + T::a32 * k2));
+            const V3 k4 = f(t + T::c4 * h, y + h * (T::a41 * k1 + T::a42 * k2 + T::a43 * k3));
+            const V3 k5 = f(t + T::c5 * h, y + h * (T::a51 * k1 + T::a52 * k2 + T::a53 * k3 + T::a54 * k4));
+            const V3 k6 = f(t + h, y + h * (T::a61 * k1 + T::a62 * k2 + T::a63 * k3 + T::a64 * k4 + T::a65 * k5));
+            const V3 y_new = y + h * (T::b1 * k1 + T::b3 * k3 + T::b4 * k4 + T::b5 * k5 + T::b6 * k6);
+            const V3 f_new = f(t + h, y_new);
+            const V3 err = h * (T::e1 * k1 + T::e3 * k3 + T::e4 * k4 + T::e5 * k5 + T::e6 * k6 + T::e7 * f_new);
+            const V3 mx = vabs_max(y, y_new);
+            const double en = rms3({err.x / (atol + mx.x * rtol), err.y / (atol + mx.y * rtol), err.z / (atol + mx.z * rtol)});
+            if (en < 1.0) {
+                double factor = (en == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(en, -0.2));
+                if (rejected) factor = fmin(1.0, factor);
+                h_abs *= factor;
+                t = t_new; y = y_new; fk = f_new;
+                ++n_acc;
+                new_step = true;
+                record(n_acc, t, y);
+            } else if (en >= 1.0) {
+                h_abs *= fmax(0.2, 0.9 * pow(en, -0.2));
+                rejected = true;
+                ++n_rej;
+            } else {               // NaN error norm: SciPy would never terminate; flag and stop
+                status |= 8;
+            }
         }
     }
-#ifdef STG_DEBUG_RK45
-    printf("rk45 end t=%g n_acc=%d n_rej=%d status=%d n_eval=%d ptrs %p %p %p\n", t, n_acc, n_rej, status, f.n_eval, (void*)a.d_n_accepted, (void*)a.d_n_rhs, (void*)a.d_t_reached);
-#endif
     a.d_y_out[3 * e] = y.x; a.d_y_out[3 * e + 1] = y.y; a.d_y_out[3 * e + 2] = y.z;
     if (a.d_n_accepted) a.d_n_accepted[e] = n_acc;
     if (a.d_n_rejected) a.d_n_rejected[e] = n_rej;

@@ -79,10 +79,24 @@ class LLGSSolver:
                    for t, p in zip(types, plist)]
         table = torch.from_numpy(_params.llg_table(structs)).to(dev)
         pidx = None
+        order = None
         if param_index is not None:
             pidx = torch.as_tensor(param_index, dtype=torch.int32).to(dev).contiguous()
+            philox = thermal_noise and noise is None      # Philox counters use the trajectory index: keep the caller's order
+            if len(structs) > 1 and n >= 64 and not philox:
+                # group trajectories of the same parameter set into the same warps (interleaved device classes leave most
+                # lanes of a warp idle); inputs are gathered through `order`, outputs scattered back below
+                order = torch.argsort(pidx, stable=True)
+                pidx = pidx[order].contiguous()
+                m0 = m0[order].contiguous()
         elif len(structs) != 1:
             raise ValueError("several parameter sets need a param_index")
+        if order is not None:
+            _arr = arr
+
+            def arr(x, shape, fill=None):                      # noqa: F811 - per-trajectory inputs follow the grouping
+                t = _arr(x, shape, fill)
+                return t if t is None else t[order].contiguous()
         a = _lib.StgRk45Args()
         t_end_t = arr(t_end, (n,))
         keep = [table, pidx, m0, t_end_t]
@@ -123,6 +137,10 @@ class LLGSSolver:
         with torch.cuda.device(dev):
             _lib.check(self._lib.stg_llgs_rk45_f64(C.byref(a), torch.cuda.current_stream(dev).cuda_stream),
                        "stg_llgs_rk45_f64")
+        if order is not None:
+            inv = torch.empty_like(order)
+            inv[order] = torch.arange(n, device=dev)
+            out = {k: v[inv].contiguous() for k, v in out.items()}
         out["m"] = out["y"] / out["y"].norm(dim=1, keepdim=True)
         out["success"] = out["status"] == 0
         self._keep = keep
