@@ -208,11 +208,12 @@ STG_HD void env_step_body(const StgSttStepArgs& a, int64_t e, EnvStepResult& r) 
     const bool valid = f[FI_VALID] != 0.0 && (!AXIS_Z || f[FI_AXISZ] != 0.0);
     if (valid) {
         guard_normalise<R>(nx, ny, nz, guard);                                 // SimpleLLGSSolver.solve :119
-        Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+        // Philox stream of this env-step: key = (seed_lo, seed_hi ^ episode), counter = (global env id, step, 4*substep + block)
+        // -> every (env, episode, step, substep) draws from its own counter block, independent of the batch partitioning
+        Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ (uint32_t)a.state.episode[e]};
         const uint64_t gid = a.env_offset + (uint64_t)e;
         const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
-        // Philox stream position: (episode, step) packed so that every env-step of every episode is distinct
-        const uint32_t step_id = ((uint32_t)a.state.episode[e] << 12) ^ (uint32_t)step;
+        const uint32_t step_id = (uint32_t)step;
         if (f[FI_HTH] > 0.0 || NOISE == 0) {
             integrate<R, AXIS_Z, NOISE, EULER>(f, J, nx, ny, nz, plan.n, plan.dt, T, T, ph, gid, step_id, nrow, nullptr, guard);
         } else {
