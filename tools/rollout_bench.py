@@ -39,8 +39,10 @@ def policy(obs):
 
 
 col = stg.RolloutCollector(env, n_steps=a.n_steps)
-col.collect(lambda o: policy(o)) if False else None
+warm = stg.RolloutCollector(env, n_steps=2, store_observations=False)
+warm.collect(policy)                       # warm-up: lazy NCCL communicator setup, first-launch overheads
 env.reset(seed=7)
+env.stats_tensor().zero_()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
