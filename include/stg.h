@@ -49,6 +49,8 @@ extern "C" {
 #define STG_F_EULER 0x08u            /* SimpleLLGSSolver(method='euler') instead of 'rk4'                          */
 #define STG_F_SORTED 0x10u           /* d_perm holds an env permutation (e.g. sorted by substep count)             */
 #define STG_F_AXIS_Z 0x20u           /* caller asserts stg_stt_all_axis_z(): kernels drop structurally-zero terms   */
+#define STG_F_NO_PAIR 0x80u          /* stg_stt_step_f32: one env per thread instead of the packed two-envs-per-thread FFMA2
+                                        kernel (identical results; for comparisons)                                 */
 #define STG_F_VECTORIZED_PLAN 0x40u  /* stg_stt_solve_*: n = max(10, int(t_end/max_step)) — VectorizedSolver.solve_batch's step
                                         policy (utils/vectorized_operations.py:55-57) instead of SimpleLLGSSolver's        */
 
@@ -407,7 +409,8 @@ int stg_energy_landscape_f64(const StgEnergyParams* p, const double* d_m, const 
                              double* d_energy, double* d_gradient, int64_t n, void* stream);
 
 /* FMA-pipe throughput probe (bench.py's measured FP32/FP64 roofline denominator): blocks*256 threads x iters*64 FMAs.
- * d_out: >= blocks*256 elements of the probed type (never written in practice). */
+ * f64 = 0: FFMA, 1: DFMA, 2: packed FFMA2 (iters*64 instructions = iters*128 FMAs per thread).
+ * d_out: >= blocks*256 elements of the probed type (8 bytes each for modes 1, 2; never written in practice). */
 int stg_probe_fma(void* d_out, int32_t blocks, int32_t iters, int32_t f64, void* stream);
 
 #ifdef __cplusplus

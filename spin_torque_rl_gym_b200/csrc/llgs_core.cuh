@@ -171,6 +171,26 @@ STG_HD void philox_normals12(const Philox& ph, uint64_t gid, uint32_t step, uint
     box_muller_packed(b[0], b[3] >> 10, neg2ln2_scale2, xi[8], xi[9]);
     box_muller_packed(b[1], b[3] >> 20, neg2ln2_scale2, xi[10], xi[11]);
 }
+// same stream, written straight into one half (H = 0: .x, 1: .y) of 12 packed pairs (two-envs-per-thread kernels)
+template <int H, typename P2>
+STG_HD void philox_normals12_half(const Philox& ph, uint64_t gid, uint32_t step, uint32_t sub, float neg2ln2_scale2,
+                                  P2* nz) {
+    uint32_t a[4], b[4];
+    ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u, a);
+    ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u + 1u, b);
+    float n0, n1;
+#define STG_BM_PAIR(k, w, e)                                              \
+    box_muller_packed(w, e, neg2ln2_scale2, n0, n1);                       \
+    if (H == 0) { nz[2 * (k)].x = n0; nz[2 * (k) + 1].x = n1; }            \
+    else { nz[2 * (k)].y = n0; nz[2 * (k) + 1].y = n1; }
+    STG_BM_PAIR(0, a[0], b[2])
+    STG_BM_PAIR(1, a[1], b[2] >> 10)
+    STG_BM_PAIR(2, a[2], b[2] >> 20)
+    STG_BM_PAIR(3, a[3], b[3])
+    STG_BM_PAIR(4, b[0], b[3] >> 10)
+    STG_BM_PAIR(5, b[1], b[3] >> 20)
+#undef STG_BM_PAIR
+}
 STG_HD void philox_normals4(const Philox& ph, uint64_t gid, uint32_t step, uint32_t sub, uint32_t lane,
                             float neg2ln2_scale2, float xi[4]) {
     uint32_t o[4];
@@ -427,14 +447,147 @@ STG_HD void substep_ref(const StepConsts<R>& c, ScaledState& st, const R* aH, co
     guard_normalise<R>(st, guard);
 }
 
+// ---- FP32 lane packs --------------------------------------------------------------------------------------------------
+// The fast path is written once over a pack type P: `float` (one env per thread) or `F2` (two envs per thread in the two
+// halves of a 64-bit register pair, executed by Blackwell's packed FFMA2 / FMUL2 / FADD2: one issue slot for two FMAs).
+// Every operation is an explicit IEEE fma / mul / add per component, so both packs produce bit-identical results.
+#if defined(__CUDA_ARCH__)
+typedef float2 F2;
+#else
+struct F2 { float x, y; };
+#endif
+STG_HD F2 mk2(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return make_float2(a, b);
+#else
+    return F2{a, b};
+#endif
+}
+template <typename P> struct Pk;
+template <> struct Pk<float> {
+    static STG_HD float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    static STG_HD float mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        return __fmul_rn(a, b);
+#else
+        volatile float r = a * b; return r;
+#endif
+    }
+    static STG_HD float add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        return __fadd_rn(a, b);
+#else
+        volatile float r = a + b; return r;
+#endif
+    }
+    static STG_HD float neg(float a) { return -a; }
+    static STG_HD float bc(float v) { return v; }
+};
+template <> struct Pk<F2> {
+    static STG_HD F2 fma(F2 a, F2 b, F2 c) {
+#if defined(__CUDA_ARCH__)
+        return __ffma2_rn(a, b, c);
+#else
+        return F2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)};
+#endif
+    }
+    static STG_HD F2 mul(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__)
+        return __fmul2_rn(a, b);
+#else
+        volatile float x = a.x * b.x, y = a.y * b.y; return F2{x, y};
+#endif
+    }
+    static STG_HD F2 add(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__)
+        return __fadd2_rn(a, b);
+#else
+        volatile float x = a.x + b.x, y = a.y + b.y; return F2{x, y};
+#endif
+    }
+    static STG_HD F2 neg(F2 a) { return mk2(-a.x, -a.y); }   // folded into the operand modifier of the consuming FFMA2
+    static STG_HD F2 bc(float v) { return mk2(v, v); }
+};
+
+// constants of the fast path in pack form (hi/lo pairs, see StepConsts)
+template <typename P>
+struct PackConsts {
+    P c_hi, c_lo, ac_hi, ac_lo, al;
+};
+
+// deterministic stage, e = z^ (same algebra as stage_z): 14 pack operations (+1 when SCALED)
+template <typename P, bool SCALED>
+STG_HD void stage_zp(const PackConsts<P>& c, P mx, P my, P mz, P aH, P aL, P nq, P& kx, P& ky, P& kz) {
+    using K = Pk<P>;
+    const P bz = K::fma(c.c_lo, mz, K::mul(c.c_hi, mz));
+    const P w = K::add(K::fma(c.ac_hi, mz, aH), K::fma(c.ac_lo, mz, aL));
+    const P u = K::mul(mz, w);
+    const P s2 = K::fma(mx, mx, K::mul(my, my));
+    kx = K::fma(mx, u, K::mul(my, bz));
+    ky = K::fma(my, u, K::mul(K::neg(mx), bz));
+    kz = SCALED ? K::mul(K::mul(s2, w), nq) : K::mul(s2, K::neg(w));       // nq = -inv_s^2
+}
+// thermal part: k += m x bn + alpha m x (m x bn)
+template <typename P>
+STG_HD void stage_noisep(const PackConsts<P>& c, P mx, P my, P mz, P bx, P by, P bz, P& kx, P& ky, P& kz) {
+    using K = Pk<P>;
+    const P px = K::fma(my, bz, K::mul(K::neg(mz), by));
+    const P py = K::fma(mz, bx, K::mul(K::neg(mx), bz));
+    const P pz = K::fma(mx, by, K::mul(K::neg(my), bx));
+    const P qx = K::fma(my, pz, K::mul(K::neg(mz), py));
+    const P qy = K::fma(mz, px, K::mul(K::neg(mx), pz));
+    const P qz = K::fma(mx, py, K::mul(K::neg(my), px));
+    kx = K::add(kx, K::fma(c.al, qx, px));
+    ky = K::add(ky, K::fma(c.al, qy, py));
+    kz = K::add(kz, K::fma(c.al, qz, pz));
+}
+
 // ---- fast RK4 substep: FP32 stages, e = z^ -------------------------------------------------------------------------------
 // Working copy (fx, fy, fz) in FP32, master in FP64. All constants carry the factor 1/6 (k' = k/6), so
 //     stage inputs are  m + 3 k1', m + 3 k2', m + 6 k3'  and the increment is  k1' + 2 (k2' + k3') + k4'.
 // The per-substep renormalisation m/|m| of the reference is applied as a first-order-exact correction computed in FP32:
 //     d = |m + inc|^2 - 1 = inc . (2 m + inc),   1/sqrt(1+d) - 1 = rho(d),   m_new = m + [inc + rho (m + inc)]
 // and only the bracket (small) is added to the FP64 master, so the master keeps ~1e-15 resolution while no FP64 sqrt/div
-// and only three F2F conversions are needed per substep. Every 8 substeps the master is renormalised exactly in FP64 and
-// the working copy is refreshed from it (integrate_fast below), which bounds the drift of both.
+// and only F2F conversions are needed per substep. The master is renormalised exactly in FP64 every STG_RESYNC_MASK+1
+// substeps (integrate() in stt_env_core.cuh), which bounds the drift.
+// Outputs: the correction `corr` to add to the master and d (callers fall back to the exact path when |d| >= 2^-6).
+template <typename P, bool THERMAL, bool SCALED>
+STG_HD void rk4_fast(const PackConsts<P>& c, P fx, P fy, P fz, P nq, P q, P aH1, P aL1, P aH2, P aL2, P aH4, P aL4,
+                     const P* nz, P& ix, P& iy, P& iz, P& cx, P& cy, P& cz, P& d) {
+    using K = Pk<P>;
+    const P three = K::bc(3.0f), six = K::bc(6.0f), two = K::bc(2.0f);
+    P k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
+    stage_zp<P, SCALED>(c, fx, fy, fz, aH1, aL1, nq, k1x, k1y, k1z);
+    if (THERMAL) stage_noisep<P>(c, fx, fy, fz, nz[0], nz[1], nz[2], k1x, k1y, k1z);
+    {
+        const P x = K::fma(three, k1x, fx), y = K::fma(three, k1y, fy), z = K::fma(three, k1z, fz);
+        stage_zp<P, SCALED>(c, x, y, z, aH2, aL2, nq, k2x, k2y, k2z);
+        if (THERMAL) stage_noisep<P>(c, x, y, z, nz[3], nz[4], nz[5], k2x, k2y, k2z);
+    }
+    {
+        const P x = K::fma(three, k2x, fx), y = K::fma(three, k2y, fy), z = K::fma(three, k2z, fz);
+        stage_zp<P, SCALED>(c, x, y, z, aH2, aL2, nq, k3x, k3y, k3z);
+        if (THERMAL) stage_noisep<P>(c, x, y, z, nz[6], nz[7], nz[8], k3x, k3y, k3z);
+    }
+    {
+        const P x = K::fma(six, k3x, fx), y = K::fma(six, k3y, fy), z = K::fma(six, k3z, fz);
+        stage_zp<P, SCALED>(c, x, y, z, aH4, aL4, nq, k4x, k4y, k4z);
+        if (THERMAL) stage_noisep<P>(c, x, y, z, nz[9], nz[10], nz[11], k4x, k4y, k4z);
+    }
+    ix = K::add(K::fma(two, K::add(k2x, k3x), k1x), k4x);
+    iy = K::add(K::fma(two, K::add(k2y, k3y), k1y), k4y);
+    iz = K::add(K::fma(two, K::add(k2z, k3z), k1z), k4z);
+    const P ux = K::add(fx, ix), uy = K::add(fy, iy), uz = K::add(fz, iz);      // un-normalised new vector
+    const P dxy = K::fma(ix, K::add(fx, ux), K::mul(iy, K::add(fy, uy)));
+    const P dz = K::mul(iz, K::add(fz, uz));
+    d = SCALED ? K::fma(q, dxy, dz) : K::add(dz, dxy);
+    // rho = (1+d)^(-1/2) - 1 for |d| < 2^-6: truncation error < 0.28 d^4 (1.6e-8 relative to rho)
+    const P rho = K::mul(d, K::fma(d, K::fma(d, K::bc(-0.3125f), K::bc(0.375f)), K::bc(-0.5f)));
+    cx = K::fma(rho, ux, ix);
+    cy = K::fma(rho, uy, iy);
+    cz = K::fma(rho, uz, iz);
+}
+
 struct FastState {
     ScaledState st;
     float fx, fy, fz, q;
@@ -442,48 +595,13 @@ struct FastState {
 STG_HD void fast_resync(FastState& s) {
     s.fx = (float)s.st.sx; s.fy = (float)s.st.sy; s.fz = (float)s.st.z; s.q = s.st.inv_s2f;
 }
-
-template <bool THERMAL, bool SCALED>
-STG_HD void substep_fast(const StepConsts<float>& c, FastState& s, float aH1, float aL1, float aH2, float aL2, float aH4,
-                         float aL4, const float* nz, int& guard) {
-    const float fx = s.fx, fy = s.fy, fz = s.fz, q = s.q;
-    float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
-    stage_z<float, SCALED>(c, fx, fy, fz, aH1, aL1, q, k1x, k1y, k1z);
-    if (THERMAL) stage_noise<float>(c, fx, fy, fz, nz[0], nz[1], nz[2], k1x, k1y, k1z);
-    {
-        const float x = fx + 3.0f * k1x, y = fy + 3.0f * k1y, z = fz + 3.0f * k1z;
-        stage_z<float, SCALED>(c, x, y, z, aH2, aL2, q, k2x, k2y, k2z);
-        if (THERMAL) stage_noise<float>(c, x, y, z, nz[3], nz[4], nz[5], k2x, k2y, k2z);
-    }
-    {
-        const float x = fx + 3.0f * k2x, y = fy + 3.0f * k2y, z = fz + 3.0f * k2z;
-        stage_z<float, SCALED>(c, x, y, z, aH2, aL2, q, k3x, k3y, k3z);
-        if (THERMAL) stage_noise<float>(c, x, y, z, nz[6], nz[7], nz[8], k3x, k3y, k3z);
-    }
-    {
-        const float x = fx + 6.0f * k3x, y = fy + 6.0f * k3y, z = fz + 6.0f * k3z;
-        stage_z<float, SCALED>(c, x, y, z, aH4, aL4, q, k4x, k4y, k4z);
-        if (THERMAL) stage_noise<float>(c, x, y, z, nz[9], nz[10], nz[11], k4x, k4y, k4z);
-    }
-    const float ix = k1x + 2.0f * (k2x + k3x) + k4x;
-    const float iy = k1y + 2.0f * (k2y + k3y) + k4y;
-    const float iz = k1z + 2.0f * (k2z + k3z) + k4z;
-    const float ux = fx + ix, uy = fy + iy, uz = fz + iz;                 // un-normalised new vector
-    const float dxy = ix * (fx + ux) + iy * (fy + uy);
-    const float d = SCALED ? iz * (fz + uz) + q * dxy : iz * (fz + uz) + dxy;
+// apply the result of rk4_fast to one env's FP64 master (exact path when the norm change is large or non-finite)
+STG_HD void fast_apply(FastState& s, float ix, float iy, float iz, float cx, float cy, float cz, float d, int& guard) {
     if (fabsf(d) < 0.015625f) {
-        // rho = (1+d)^(-1/2) - 1, |d| < 2^-6: truncation error < 0.28 d^4 = 1.6e-8 (relative to rho)
-        const float rho = d * (-0.5f + d * (0.375f + d * -0.3125f));
-        s.st.sx += (double)(ix + rho * ux);
-        s.st.sy += (double)(iy + rho * uy);
-        s.st.z += (double)(iz + rho * uz);
-#if STG_FAST_COPY_FROM_MASTER
+        s.st.sx += (double)cx;
+        s.st.sy += (double)cy;
+        s.st.z += (double)cz;
         s.fx = (float)s.st.sx; s.fy = (float)s.st.sy; s.fz = (float)s.st.z;
-#else
-        s.fx = ux + rho * ux;
-        s.fy = uy + rho * uy;
-        s.fz = uz + rho * uz;
-#endif
     } else {
         // large or non-finite norm change (diverging parameters): exact FP64 path with the reference's guard
         s.st.sx += (double)ix;
@@ -492,6 +610,18 @@ STG_HD void substep_fast(const StepConsts<float>& c, FastState& s, float aH1, fl
         guard_normalise<float>(s.st, guard);
         fast_resync(s);
     }
+}
+template <typename P>
+STG_HD void pack_consts(const StepConsts<float>& a, const StepConsts<float>& b, PackConsts<P>& c);
+template <>
+STG_HD void pack_consts<float>(const StepConsts<float>& a, const StepConsts<float>&, PackConsts<float>& c) {
+    c.c_hi = a.c_hi; c.c_lo = a.c_lo; c.ac_hi = a.ac_hi; c.ac_lo = a.ac_lo; c.al = a.al_hi;
+}
+template <>
+STG_HD void pack_consts<F2>(const StepConsts<float>& a, const StepConsts<float>& b, PackConsts<F2>& c) {
+    c.c_hi = mk2(a.c_hi, b.c_hi); c.c_lo = mk2(a.c_lo, b.c_lo);
+    c.ac_hi = mk2(a.ac_hi, b.ac_hi); c.ac_lo = mk2(a.ac_lo, b.ac_lo);
+    c.al = mk2(a.al_hi, b.al_hi);
 }
 
 // ---- step plan (physics/simple_solver.py:137-139), evaluated exactly like NumPy does in FP64 -------------------------

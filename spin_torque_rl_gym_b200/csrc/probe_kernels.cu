@@ -23,13 +23,35 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(T* out, int iters, T a, 
     if (s == (T)12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true; keeps the chains alive
 }
 
+// packed FP32x2 variant (Blackwell FFMA2): 8 independent chains of float2 per thread = 128 FMAs per loop iteration
+__global__ void __launch_bounds__(256) fma2_probe_kernel(float2* out, int iters, float a, float b) {
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    float2 x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = make_float2((float)threadIdx.x + u, (float)threadIdx.x - u);
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = __ffma2_rn(x[u], a2, b2);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += x[u].x + x[u].y;
+    if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = make_float2(s, s);
+}
+
 }  // namespace stg
 
 // Launches blocks*256 threads, each executing iters*64 FMAs. flops = blocks*256*iters*64*2.
 extern "C" int stg_probe_fma(void* d_out, int32_t blocks, int32_t iters, int32_t f64, void* stream) {
     if (!d_out) return STG_E_NULL;
     if (blocks <= 0 || iters <= 0) return STG_E_SIZE;
-    if (f64)
+    if (f64 == 2)   // FP32x2 packed: blocks*256 threads x iters*64 FFMA2 = iters*128 FMAs per thread
+        stg::fma2_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((float2*)d_out, iters, 0.999999f, 1e-7f);
+    else if (f64)
         stg::fma_probe_kernel<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((double*)d_out, iters, 0.999999, 1e-7);
     else
         stg::fma_probe_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((float*)d_out, iters, 0.999999f, 1e-7f);

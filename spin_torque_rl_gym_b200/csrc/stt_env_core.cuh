@@ -52,6 +52,8 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
     if constexpr (FAST) {
         StepConsts<float> c;
         make_consts<float>(f, dt, J, 1.0 / 6.0, c);
+        PackConsts<float> pc;
+        pack_consts<float>(c, c, pc);
         const float nscale = -1.3862943611198906f * c.cth * c.cth;      // -2 ln2 * (G h_th / 6)^2
         FastState s;
         s.st = ScaledState{mx, my, mz, 1.0, 1.0, 1.0f};
@@ -72,7 +74,10 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
 #pragma unroll
                 for (int q = 0; q < 12; ++q) nz[q] = c.cth * (float)noise_row[(int64_t)i * 12 + q];
             }
-            substep_fast<TH, SCALED>(c, s, aH1, aL1, aH2, aL2, aH4, aL4, TH ? nz : nullptr, guard);
+            float ix, iy, iz, cx, cy, cz, d;
+            rk4_fast<float, TH, SCALED>(pc, s.fx, s.fy, s.fz, -s.q, s.q, aH1, aL1, aH2, aL2, aH4, aL4, TH ? nz : nullptr,
+                                        ix, iy, iz, cx, cy, cz, d);
+            fast_apply(s, ix, iy, iz, cx, cy, cz, d, guard);
             if ((i & STG_RESYNC_MASK) == STG_RESYNC_MASK || traj) {
                 guard_normalise<float>(s.st, guard);      // exact FP64 renormalisation of the master
                 if (SCALED) rescale(s.st);
@@ -126,6 +131,104 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
         }
         mx = st.sx * st.inv_s; my = st.sy * st.inv_s; mz = st.z;
     }
+}
+
+// Two envs per thread through the packed FP32x2 path (FP32 stages, e = z^, RK4; NOISE 0 or 1). Env A lives in the .x halves,
+// env B in the .y halves. The envs may have different substep counts: the thread runs to the longer one with the finished
+// env's constants zeroed (its increments are then exactly 0) and its periodic / final renormalisations skipped, so each env's
+// result is bit-identical to the one-env-per-thread path whatever its partner is.
+struct PairEnv {
+    const double* f;
+    double J, dt, t_pulse;
+    int n;
+    uint32_t key_hi, step_id;
+    uint64_t gid;
+};
+// apply the packed rk4_fast result to ONE env (H = 0: .x halves, 1: .y halves) of a pair: FP64 master + its half of the
+// packed FP32 working copy
+template <int H>
+STG_HD void pair_apply(ScaledState& st, F2& fx, F2& fy, F2& fz, F2& q, F2& nq, const F2& ix, const F2& iy, const F2& iz,
+                       const F2& cx, const F2& cy, const F2& cz, const F2& d, int& guard) {
+    const float dd = H ? d.y : d.x;
+    if (fabsf(dd) < 0.015625f) {
+        st.sx += (double)(H ? cx.y : cx.x);
+        st.sy += (double)(H ? cy.y : cy.x);
+        st.z += (double)(H ? cz.y : cz.x);
+    } else {
+        st.sx += (double)(H ? ix.y : ix.x);
+        st.sy += (double)(H ? iy.y : iy.x);
+        st.z += (double)(H ? iz.y : iz.x);
+        guard_normalise<float>(st, guard);
+        if (H) { q.y = st.inv_s2f; nq.y = -st.inv_s2f; } else { q.x = st.inv_s2f; nq.x = -st.inv_s2f; }
+    }
+    if (H) { fx.y = (float)st.sx; fy.y = (float)st.sy; fz.y = (float)st.z; }
+    else { fx.x = (float)st.sx; fy.x = (float)st.sy; fz.x = (float)st.z; }
+}
+template <int H, bool SCALED>
+STG_HD void pair_renorm(ScaledState& st, F2& fx, F2& fy, F2& fz, F2& q, F2& nq, int& guard) {
+    guard_normalise<float>(st, guard);
+    if (SCALED) rescale(st);
+    if (H) { fx.y = (float)st.sx; fy.y = (float)st.sy; fz.y = (float)st.z; q.y = st.inv_s2f; nq.y = -st.inv_s2f; }
+    else { fx.x = (float)st.sx; fy.x = (float)st.sy; fz.x = (float)st.z; q.x = st.inv_s2f; nq.x = -st.inv_s2f; }
+}
+
+template <int NOISE>
+STG_HD void integrate_pair(const PairEnv& A, const PairEnv& B, uint32_t seed_lo, double* mA, double* mB, int& guardA,
+                           int& guardB) {
+    constexpr bool TH = NOISE != 0;
+    constexpr bool SCALED = !TH;
+    StepConsts<float> ca, cb;
+    make_consts<float>(A.f, A.dt, A.J, 1.0 / 6.0, ca);
+    make_consts<float>(B.f, B.dt, B.J, 1.0 / 6.0, cb);
+    PackConsts<F2> pc;
+    pack_consts<F2>(ca, cb, pc);
+    const float nsa = -1.3862943611198906f * ca.cth * ca.cth, nsb = -1.3862943611198906f * cb.cth * cb.cth;
+    const Philox pha{seed_lo, A.key_hi}, phb{seed_lo, B.key_hi};
+    ScaledState sa{mA[0], mA[1], mA[2], 1.0, 1.0, 1.0f}, sb{mB[0], mB[1], mB[2], 1.0, 1.0, 1.0f};
+    if (SCALED) { rescale(sa); rescale(sb); }
+    // packed FP32 working copy: env A in the .x halves, env B in the .y halves
+    F2 fx = mk2((float)sa.sx, (float)sb.sx), fy = mk2((float)sa.sy, (float)sb.sy), fz = mk2((float)sa.z, (float)sb.z);
+    F2 q = mk2(sa.inv_s2f, sb.inv_s2f), nq = mk2(-sa.inv_s2f, -sb.inv_s2f);
+    const int n_max = A.n > B.n ? A.n : B.n;
+    const int edge_from = (A.n < B.n ? A.n : B.n) - 1;     // the env loop always passes t_end == t_pulse: i_safe = n - 1
+    F2 aH = mk2(ca.a_hi, cb.a_hi), aL = mk2(ca.a_lo, cb.a_lo);
+    F2 nz[12];
+    auto one = [&](int i, bool edge) {
+        F2 aH4 = aH, aL4 = aL;
+        bool runA = true, runB = true;
+        if (edge) {
+            // an env that has finished contributes exactly zero; the last substep of an env gates its k4 stage in FP64
+            runA = i < A.n; runB = i < B.n;
+            if (!runA) { pc.c_hi.x = pc.c_lo.x = pc.ac_hi.x = pc.ac_lo.x = 0.0f; aH.x = aL.x = 0.0f; }
+            if (!runB) { pc.c_hi.y = pc.c_lo.y = pc.ac_hi.y = pc.ac_lo.y = 0.0f; aH.y = aL.y = 0.0f; }
+            aH4 = aH; aL4 = aL;
+            if (runA && i == A.n - 1 && !pulse_on(i, 2, A.dt, A.t_pulse)) { aH4.x = 0.0f; aL4.x = 0.0f; }
+            if (runB && i == B.n - 1 && !pulse_on(i, 2, B.dt, B.t_pulse)) { aH4.y = 0.0f; aL4.y = 0.0f; }
+        }
+        if (NOISE == 1) {
+            philox_normals12_half<0>(pha, A.gid, A.step_id, (uint32_t)i, nsa, nz);
+            philox_normals12_half<1>(phb, B.gid, B.step_id, (uint32_t)i, nsb, nz);
+            if (edge) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) { if (!runA) nz[k].x = 0.0f; if (!runB) nz[k].y = 0.0f; }
+            }
+        }
+        F2 ix, iy, iz, cx, cy, cz, d;
+        rk4_fast<F2, TH, SCALED>(pc, fx, fy, fz, nq, q, aH, aL, aH, aL, aH4, aL4, TH ? nz : nullptr, ix, iy, iz, cx, cy, cz, d);
+        if (runA) pair_apply<0>(sa, fx, fy, fz, q, nq, ix, iy, iz, cx, cy, cz, d, guardA);
+        if (runB) pair_apply<1>(sb, fx, fy, fz, q, nq, ix, iy, iz, cx, cy, cz, d, guardB);
+        if ((i & STG_RESYNC_MASK) == STG_RESYNC_MASK) {
+            if (runA) pair_renorm<0, SCALED>(sa, fx, fy, fz, q, nq, guardA);
+            if (runB) pair_renorm<1, SCALED>(sb, fx, fy, fz, q, nq, guardB);
+        }
+    };
+    int i = 0;
+    for (; i < edge_from; ++i) one(i, false);
+    for (; i < n_max; ++i) one(i, true);
+    guard_normalise<float>(sa, guardA);
+    guard_normalise<float>(sb, guardB);
+    mA[0] = sa.sx * sa.inv_s; mA[1] = sa.sy * sa.inv_s; mA[2] = sa.z;
+    mB[0] = sb.sx * sb.inv_s; mB[1] = sb.sy * sb.inv_s; mB[2] = sb.z;
 }
 
 // observation row (envs/spin_torque_env.py:500-520) + SafetyWrapper.validate_observation (utils/monitoring.py:317-330)
@@ -184,52 +287,54 @@ struct EnvStepResult {
     int step_after;     // step count of the finished step (episode length if it ended)
 };
 
-// One env (index e of a.n_envs): reads and updates the FP64 state planes, returns the outputs in `r`.
-template <typename R, bool AXIS_Z, int NOISE, bool EULER>
-STG_HD void env_step_body(const StgSttStepArgs& a, int64_t e, EnvStepResult& r) {
+// What the first half of an env step computes for one env (loads, action parsing, step plan, normalised start state).
+struct EnvStepCtx {
+    const double* f;
+    double mx, my, mz, tx, ty, tz, total_e, J, T, prev_align;
+    double w[3];        // working magnetisation handed to / returned by the integrator
+    StepPlan plan;
+    int step, guard;
+    bool valid;
+};
+
+template <typename R, bool AXIS_Z>
+STG_HD void env_step_prologue(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c) {
+    const int64_t n = a.n_envs;
+    c.f = a.d_table[a.d_param_index ? a.d_param_index[e] : 0].v;
+    c.mx = a.state.m[e]; c.my = a.state.m[n + e]; c.mz = a.state.m[2 * n + e];
+    c.tx = a.state.target[e]; c.ty = a.state.target[n + e]; c.tz = a.state.target[2 * n + e];
+    c.total_e = a.state.total_energy[e];
+    c.step = a.state.step_count[e];
+    parse_action(a.d_action[2 * e], a.d_action[2 * e + 1], c.f[FI_MAXCUR], c.f[FI_MAXDUR], c.J, c.T);
+    c.prev_align = c.mx * c.tx + c.my * c.ty + c.mz * c.tz;                   // envs/spin_torque_env.py:338-339
+    c.plan = substep_plan(c.T, c.f[FI_MAXSTEP_DT]);
+    c.w[0] = c.mx; c.w[1] = c.my; c.w[2] = c.mz;
+    c.guard = 0;
+    c.valid = c.f[FI_VALID] != 0.0 && (!AXIS_Z || c.f[FI_AXISZ] != 0.0);
+    if (c.valid) guard_normalise<R>(c.w[0], c.w[1], c.w[2], c.guard);         // SimpleLLGSSolver.solve :119
+}
+
+// Second half: env-level renormalisation, energy, reward, flags, observation, auto-reset, state / output stores.
+STG_HD void env_step_epilogue(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c, EnvStepResult& r) {
     const int64_t n = a.n_envs;
     const bool autoreset = (a.flags & STG_F_AUTORESET) != 0;
-    const double* f = a.d_table[a.d_param_index ? a.d_param_index[e] : 0].v;
-    double mx = a.state.m[e], my = a.state.m[n + e], mz = a.state.m[2 * n + e];
-    double tx = a.state.target[e], ty = a.state.target[n + e], tz = a.state.target[2 * n + e];
-    double total_e = a.state.total_energy[e];
-    int step = a.state.step_count[e];
-    const float a0 = a.d_action[2 * e], a1 = a.d_action[2 * e + 1];
-
-    double J, T;
-    parse_action(a0, a1, f[FI_MAXCUR], f[FI_MAXDUR], J, T);
-    const double prev_align = mx * tx + my * ty + mz * tz;                     // envs/spin_torque_env.py:338-339
-    const StepPlan plan = substep_plan(T, f[FI_MAXSTEP_DT]);
-
-    // ---- integrate (utils/robust_solver.py:75 -> physics/simple_solver.py:147-179) ---------------------------------
+    const double* f = c.f;
+    const double mx = c.mx, my = c.my, mz = c.mz;
+    double tx = c.tx, ty = c.ty, tz = c.tz;
     double nx = mx, ny = my, nz = mz;
-    int guard = 0;
     int status = 0;
-    const bool valid = f[FI_VALID] != 0.0 && (!AXIS_Z || f[FI_AXISZ] != 0.0);
-    if (valid) {
-        guard_normalise<R>(nx, ny, nz, guard);                                 // SimpleLLGSSolver.solve :119
-        // Philox stream of this env-step: key = (seed_lo, seed_hi ^ episode), counter = (global env id, step, 4*substep + block)
-        // -> every (env, episode, step, substep) draws from its own counter block, independent of the batch partitioning
-        Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ (uint32_t)a.state.episode[e]};
-        const uint64_t gid = a.env_offset + (uint64_t)e;
-        const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
-        const uint32_t step_id = (uint32_t)step;
-        if (f[FI_HTH] > 0.0 || NOISE == 0) {
-            integrate<R, AXIS_Z, NOISE, EULER>(f, J, nx, ny, nz, plan.n, plan.dt, T, T, ph, gid, step_id, nrow, nullptr, guard);
-        } else {
-            integrate<R, AXIS_Z, 0, EULER>(f, J, nx, ny, nz, plan.n, plan.dt, T, T, ph, gid, step_id, nullptr, nullptr, guard);
-        }
+    if (c.valid) {
         // env-level renormalisation of the last trajectory row (envs/spin_torque_env.py:464)
-        const double inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
-        nx *= inv; ny *= inv; nz *= inv;
-        if (guard) {   // A3: a trajectory row failed validation => solver result discarded, m unchanged
+        const double inv = 1.0 / sqrt(c.w[0] * c.w[0] + c.w[1] * c.w[1] + c.w[2] * c.w[2]);
+        nx = c.w[0] * inv; ny = c.w[1] * inv; nz = c.w[2] * inv;
+        if (c.guard) {   // A3: a trajectory row failed validation => solver result discarded, m unchanged
             nx = mx; ny = my; nz = mz;
             status |= 1;
         }
     } else {
         status |= 2;
     }
-
+    const double J = c.J, T = c.T;
     // ---- Joule energy with the PRE-step m (envs/spin_torque_env.py:474-480) ------------------------------------------
     double energy = 0.0;
     if (fabs(J) > 1e-12) {
@@ -237,22 +342,22 @@ STG_HD void env_step_body(const StgSttStepArgs& a, int64_t e, EnvStepResult& r) 
         const double v = J * res * f[FI_AREA];
         energy = v * v / res * T;
     }
-    total_e += energy;
-    step += 1;
+    double total_e = c.total_e + energy;
+    int step = c.step + 1;
     const double align = nx * tx + ny * ty + nz * tz;                           // :350-353
     const bool success = align >= f[FI_SUCC];
     // CompositeReward default components in dict order (:184-207), then validate_reward (utils/monitoring.py:332-348)
     double reward = 0.0;
     reward += 10.0 * (success ? 10.0 : 0.0);
     reward += (-f[FI_WE]) * (-energy / 1e-12);
-    reward += 1.0 * (align - prev_align);
+    reward += 1.0 * (align - c.prev_align);
     if (!(fabs(reward) <= 1.7e308)) reward = -1.0;
     reward = fmin(fmax(reward, -1e6), 1e6);
     const bool truncated = step >= (int)f[FI_MAXSTEPS];                          // :371-372
 
     make_obs(f, nx, ny, nz, tx, ty, tz, step, total_e, J, T, r.obs);
-    r.reward = reward; r.energy = energy; r.n_sub = plan.n; r.status = status;
-    r.terminated = success; r.truncated = truncated; r.valid = valid; r.step_after = step;
+    r.reward = reward; r.energy = energy; r.n_sub = c.plan.n; r.status = status;
+    r.terminated = success; r.truncated = truncated; r.valid = c.valid; r.step_after = step;
     r.did_reset = false;
 
     double lj = J, lt = T;
@@ -279,8 +384,54 @@ STG_HD void env_step_body(const StgSttStepArgs& a, int64_t e, EnvStepResult& r) 
     a.out.terminated[e] = success ? 1 : 0;
     a.out.truncated[e] = truncated ? 1 : 0;
     if (a.out.step_energy) a.out.step_energy[e] = energy;
-    if (a.out.n_sub) a.out.n_sub[e] = plan.n;
+    if (a.out.n_sub) a.out.n_sub[e] = c.plan.n;
     if (a.out.status) a.out.status[e] = status;
+}
+
+// Philox stream of one env-step: key = (seed_lo, seed_hi ^ episode), counter = (global env id, step, 4*substep + block)
+// -> every (env, episode, step, substep) draws from its own counter block, independent of the batch partitioning
+template <typename R, bool AXIS_Z, int NOISE, bool EULER>
+STG_HD void env_step_integrate(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c) {
+    const Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ (uint32_t)a.state.episode[e]};
+    const uint64_t gid = a.env_offset + (uint64_t)e;
+    const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
+    const uint32_t step_id = (uint32_t)c.step;
+    if (c.f[FI_HTH] > 0.0 || NOISE == 0)
+        integrate<R, AXIS_Z, NOISE, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ph, gid, step_id,
+                                           nrow, nullptr, c.guard);
+    else
+        integrate<R, AXIS_Z, 0, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ph, gid, step_id,
+                                       nullptr, nullptr, c.guard);
+}
+
+// One env (index e of a.n_envs): reads and updates the FP64 state planes, returns the outputs in `r`.
+template <typename R, bool AXIS_Z, int NOISE, bool EULER>
+STG_HD void env_step_body(const StgSttStepArgs& a, int64_t e, EnvStepResult& r) {
+    EnvStepCtx c;
+    env_step_prologue<R, AXIS_Z>(a, e, c);
+    if (c.valid) env_step_integrate<R, AXIS_Z, NOISE, EULER>(a, e, c);
+    env_step_epilogue(a, e, c, r);
+}
+
+// Two envs (eA, eB) through the packed FP32x2 integrator (R = float, e = z^, RK4, NOISE 0 or 1).
+template <int NOISE>
+STG_HD void env_step_pair_body(const StgSttStepArgs& a, int64_t eA, int64_t eB, EnvStepResult& rA, EnvStepResult& rB) {
+    EnvStepCtx ca, cb;
+    env_step_prologue<float, true>(a, eA, ca);
+    env_step_prologue<float, true>(a, eB, cb);
+    const bool noise_ok = NOISE == 0 || (ca.f[FI_HTH] > 0.0 && cb.f[FI_HTH] > 0.0);
+    if (ca.valid && cb.valid && noise_ok) {
+        PairEnv A{ca.f, ca.J, ca.plan.dt, ca.T, ca.plan.n, (uint32_t)(a.seed >> 32) ^ (uint32_t)a.state.episode[eA],
+                  (uint32_t)ca.step, a.env_offset + (uint64_t)eA};
+        PairEnv B{cb.f, cb.J, cb.plan.dt, cb.T, cb.plan.n, (uint32_t)(a.seed >> 32) ^ (uint32_t)a.state.episode[eB],
+                  (uint32_t)cb.step, a.env_offset + (uint64_t)eB};
+        integrate_pair<NOISE>(A, B, (uint32_t)a.seed, ca.w, cb.w, ca.guard, cb.guard);
+    } else {
+        if (ca.valid) env_step_integrate<float, true, NOISE, false>(a, eA, ca);
+        if (cb.valid) env_step_integrate<float, true, NOISE, false>(a, eB, cb);
+    }
+    env_step_epilogue(a, eA, ca, rA);
+    env_step_epilogue(a, eB, cb, rB);
 }
 
 // SpinTorqueEnv.reset for one env (envs/spin_torque_env.py:250-308)

@@ -58,6 +58,7 @@ class SpinTorqueVectorEnv:
         param_index: Optional[Any] = None,
         sort_by_substeps: Union[str, bool] = "auto",
         collect_stats: bool = True,
+        pair_kernel: bool = True,
     ):
         torch = _lib.require_cuda()
         self._torch = torch
@@ -97,6 +98,7 @@ class SpinTorqueVectorEnv:
         self.autoreset = bool(autoreset)
         self.env_offset = int(env_offset)
         self.collect_stats = bool(collect_stats)
+        self.pair_kernel = bool(pair_kernel)       # FP32 / e=z / RK4: two envs per thread on packed FFMA2 (same results)
         if rng_seed is None:
             rng_seed = 0 if seed is None else int(seed)
         self.rng_seed = int(rng_seed) & 0xFFFFFFFFFFFFFFFF
@@ -291,6 +293,8 @@ class SpinTorqueVectorEnv:
             flags |= _lib.F_AXIS_Z
         if self.autoreset:
             flags |= _lib.F_AUTORESET
+        if not self.pair_kernel:
+            flags |= _lib.F_NO_PAIR
         a = _lib.StgSttStepArgs()
         if noise is not None:
             nz = torch.as_tensor(noise, dtype=torch.float64).to(self.device).contiguous()

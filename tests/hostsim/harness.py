@@ -46,7 +46,7 @@ class HostSimEnv:
     def __init__(self, num_envs, device_type="stt_mram", device_params=None, target_states=None, max_steps=100,
                  max_current=2e6, max_duration=5e-9, temperature=300.0, include_thermal_fluctuations=True,
                  success_threshold=0.9, energy_penalty_weight=0.1, f64=True, integrator="rk4", rng_seed=0,
-                 env_offset=0, autoreset=False, force_general=False):
+                 env_offset=0, autoreset=False, force_general=False, pair=True):
         N = self.N = int(num_envs)
         if device_params is None:
             device_params = P.env_default_device_params(device_type)
@@ -60,6 +60,7 @@ class HostSimEnv:
         self.integrator = integrator
         self.thermal = include_thermal_fluctuations and temperature > 0
         self.seed, self.env_offset, self.autoreset = rng_seed, env_offset, autoreset
+        self.pair = pair
         tt = np.array([[0, 0, 1.0], [0, 0, -1.0]]) if target_states is None else \
             np.array([np.asarray(t, float) / np.linalg.norm(t) for t in target_states])
         self.target_table = np.ascontiguousarray(tt)
@@ -108,6 +109,7 @@ class HostSimEnv:
         if self.integrator == "euler": flags |= _lib.F_EULER
         if self.axis_z: flags |= _lib.F_AXIS_Z
         if self.autoreset: flags |= _lib.F_AUTORESET
+        if not self.pair: flags |= _lib.F_NO_PAIR
         if noise is not None:
             noise = np.ascontiguousarray(noise, np.float64)
             flags |= _lib.F_THERMAL_INJECT; a.d_noise = _p(noise); a.noise_stride = noise.shape[1]

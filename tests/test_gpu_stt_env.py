@@ -393,3 +393,28 @@ def test_device_mix_param_index(cuda_device):
         m_after = one.magnetization.cpu().numpy()
         assert np.allclose(o1.cpu().numpy()[:, 6], DO.resistance(t, p, m_after) / p["resistance_parallel"], rtol=1e-6)
         assert int(i1["status"].max()) == 0 and float((m_after - m0n[sel]).__abs__().max()) > 1e-6
+
+
+def test_packed_pair_kernel_is_bit_identical(cuda_device):
+    """FP32 / e=z / RK4 / no noise dispatches the two-envs-per-thread FFMA2 kernel; it must reproduce the one-env-per-thread
+    kernel bit for bit (ragged substep counts, odd batch size, auto-reset, sorted and unsorted launches)."""
+    torch = _torch()
+    n, jm = 4099, 1.1e-6
+    m0, tgt, acts = _random_setup(n, 13, tmax=2e-9)
+    res = {}
+    for pair in (True, False):
+        for sort in (False, True):
+            env = _make(n, "f32", cuda_device, max_current=jm, include_thermal_fluctuations=False, autoreset=True,
+                        max_steps=2, rng_seed=4, pair_kernel=pair, sort_by_substeps=sort)
+            env.reset(options={"initial_state": m0, "target_state": tgt})
+            out = []
+            for a in acts + acts[:1]:
+                o, r, te, tr, info = env.step(a.copy())
+                out += [o.clone(), r.clone(), te.clone(), tr.clone(), info["final_observation"].clone(),
+                        env.magnetization.clone(), info["n_sub"].clone()]
+            res[(pair, sort)] = out + [env.stats_tensor().clone()]
+    ref = res[(False, False)]
+    for key, val in res.items():
+        for x, y in zip(val[:-1], ref[:-1]):
+            assert torch.equal(x, y), key
+        assert torch.allclose(val[-1], ref[-1], rtol=1e-12)          # statistics: same values, different summation order
