@@ -140,8 +140,11 @@ __device__ __forceinline__ void accumulate_stats(double* v, const EnvStepResult&
 #ifndef STG_PAIR_MINBLOCKS
 #define STG_PAIR_MINBLOCKS 8
 #endif
+#ifndef STG_PAIR_MINBLOCKS_TH
+#define STG_PAIR_MINBLOCKS_TH 1
+#endif
 template <int NOISE>
-__global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : 1) stt_env_step_pair_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : STG_PAIR_MINBLOCKS_TH) stt_env_step_pair_kernel(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) float s_obs[2 * kBlock * kObs];
     const int64_t base = (int64_t)blockIdx.x * (2 * kBlock);
     const int64_t slotA = base + 2 * threadIdx.x, slotB = slotA + 1;
@@ -309,7 +312,8 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
         if (sizeof(R) == 4 && noise == 0 && !(a.flags & (STG_F_EULER | STG_F_NO_PAIR))) {
             // two envs per thread, Blackwell packed FP32x2 arithmetic (bit-identical to the one-env-per-thread kernels).
             // Measured (profiles/README.md): +8 % without thermal noise; with the Philox stream the packed variant needs 203
-            // registers and is 5 % slower than one env per thread, so it is not dispatched there.
+            // registers and is 5 % slower than one env per thread (+4 % when capped to 168 registers), so it is not
+            // dispatched there.
             const unsigned grid = (unsigned)((a.n_envs + 2 * kBlock - 1) / (2 * kBlock));
             stt_env_step_pair_kernel<0><<<grid, kBlock, 0, s>>>(a);
             return cudaGetLastError();
