@@ -315,6 +315,19 @@ def main():
             if it:
                 best = max(best, N_SM * 16 * 256 * 4096 * 64 * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
         fma_probe_tflops = best
+        for mode, key in ((2, "ffma2_probe_tflops"), (1, "dfma_probe_tflops")):
+            best2 = 0.0
+            per_iter = 128 if mode == 2 else 64
+            buf64 = torch.empty(N_SM * 16 * 256, dtype=torch.float64, device=dev)
+            for it in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _lib.check(lib.stg_probe_fma(buf64.data_ptr(), N_SM * 16, 4096, mode, stream))
+                e1.record()
+                torch.cuda.synchronize(dev)
+                if it:
+                    best2 = max(best2, N_SM * 16 * 256 * 4096 * per_iter * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+            extras[key] = best2
         if world == 1:
             def variant(name, n, **over):
                 e = SpinTorqueVectorEnv(num_envs=n, device=dev, rng_seed=1234,
