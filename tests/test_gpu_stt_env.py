@@ -423,3 +423,39 @@ def test_packed_pair_kernel_is_bit_identical(cuda_device):
                 # kernel: FMA contraction may differ in the last bit
                 assert torch.allclose(x, y, rtol=1e-12, atol=1e-13), key
         assert torch.allclose(val[-1], ref[-1], rtol=1e-12)          # statistics: same values, different summation order
+
+
+def test_reset_seed_reproducibility_and_masked_reset(cuda_device):
+    """reset(seed) is reproducible (tests/integration/test_environment.py:77-93 of the reference), differs across seeds, and a
+    masked reset touches only the selected envs."""
+    torch = _torch()
+    n = 512
+    a = _make(n, "f32", cuda_device, rng_seed=1)
+    b = _make(n, "f32", cuda_device, rng_seed=99)
+    oa, _ = a.reset(seed=42)
+    ob, _ = b.reset(seed=42)
+    assert torch.equal(oa, ob)
+    oc, _ = b.reset(seed=43)
+    assert not torch.equal(oa, oc)
+    oa = oa.clone()
+    mask = torch.zeros(n, dtype=torch.bool, device=cuda_device)
+    mask[::3] = True
+    a.step(torch.zeros(n, 2, device=cuda_device))
+    before = a.magnetization.clone()
+    o2, _ = a.reset(mask=mask)
+    after = a.magnetization
+    assert torch.equal(after[~mask], before[~mask]) and not torch.equal(after[mask], before[mask])
+    assert torch.all(a._step_count[mask] == 0) and torch.all(a._step_count[~mask] == 1)
+    # list / numpy / host-tensor actions are all accepted and equivalent
+    e1 = _make(4, "f64", cuda_device, include_thermal_fluctuations=False, max_current=1.1e-6)
+    outs = []
+    for conv in (lambda x: x.tolist(), lambda x: x, lambda x: torch.from_numpy(x), lambda x: torch.from_numpy(x).to(cuda_device)):
+        e1.reset(options={"initial_state": np.array([0.3, 0.2, 0.9]), "target_state": np.array([0, 0, 1.0])})
+        act = np.array([[5e-7, 1e-10]] * 4, dtype=np.float32)
+        o, *_ = e1.step(conv(act))
+        outs.append(o.clone())
+    assert all(torch.equal(outs[0], x) for x in outs[1:])
+    with pytest.raises(ValueError):
+        e1.step(act, noise=np.zeros((4, 10, 3, 3)))
+    with pytest.raises(RuntimeError):
+        _make(2, "f32", cuda_device).step(act[:2])            # step before reset
