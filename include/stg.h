@@ -132,7 +132,8 @@ typedef struct StgSttStepOut {
  *   d_table        [n_sets] folded parameter sets; d_param_index [n] int32 or NULL (all envs use set 0)
  *   d_action       [n][2] f32 (J, T) as produced by the policy; clipped like SafetyWrapper + _parse_action
  *   d_noise        STG_F_THERMAL_INJECT: [n][noise_stride][S][3] f64 N(0,1) samples, S=4 (rk4) or 1 (euler), in the order
- *                  the reference draws them: (substep, stage, xyz) (physics/simple_solver.py:381)
+ *                  the reference draws them: (substep, stage, xyz) (physics/simple_solver.py:381); an env that integrates
+ *                  more than noise_stride substeps reuses the last row (no out-of-bounds read)
  *   d_perm         STG_F_SORTED: [n] int32 env indices processed by consecutive threads (stg_stt_sort_by_substeps)
  *   d_target_table STG_F_AUTORESET: [n_targets][3] f64 target_states (envs/spin_torque_env.py:117-120)
  *   seed, env_offset: Philox key / global env id of local env 0 (rank sharding keeps streams independent of #GPUs) */

@@ -33,7 +33,9 @@ STG_HD void parse_action(float a0, float a1, double max_current, double max_dura
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>
 STG_HD void integrate(const double* f, double J, double& mx, double& my, double& mz, int n, double dt, double t_pulse,
                       double t_end, const Philox& ph, uint64_t gid, uint32_t step_id, const double* noise_row, double* traj,
-                      int& guard) {
+                      int& guard, int64_t noise_rows = 0x7fffffff, int64_t traj_rows = 0x7fffffff) {
+    // injected noise: substeps beyond the caller's tensor reuse its last row instead of reading out of bounds
+    auto nrow_of = [&](int i) { return (int64_t)(i < noise_rows ? i : noise_rows - 1); };
     constexpr bool TH = NOISE != 0;
     constexpr bool FAST = sizeof(R) == 4 && AXIS_Z && !EULER;          // substep_fast (llgs_core.cuh)
     constexpr bool SCALED = sizeof(R) == 4 && AXIS_Z && !TH;            // block-scaled transverse pair
@@ -72,7 +74,7 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
                 philox_normals12(ph, gid, step_id, (uint32_t)i, nscale, nz);
             } else if (NOISE == 2) {
 #pragma unroll
-                for (int q = 0; q < 12; ++q) nz[q] = c.cth * (float)noise_row[(int64_t)i * 12 + q];
+                for (int q = 0; q < 12; ++q) nz[q] = c.cth * (float)noise_row[nrow_of(i) * 12 + q];
             }
             float ix, iy, iz, cx, cy, cz, d;
             rk4_fast<float, TH, SCALED>(pc, s.fx, s.fy, s.fz, -s.q, s.q, aH1, aL1, aH2, aL2, aH4, aL4, TH ? nz : nullptr,
@@ -83,7 +85,7 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
                 if (SCALED) rescale(s.st);
                 fast_resync(s);
             }
-            if (traj) {
+            if (traj && i + 1 < traj_rows) {
                 traj[3 * (i + 1) + 0] = s.st.sx * s.st.inv_s; traj[3 * (i + 1) + 1] = s.st.sy * s.st.inv_s;
                 traj[3 * (i + 1) + 2] = s.st.z;
             }
@@ -120,11 +122,11 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
                 }
             } else if (NOISE == 2) {
 #pragma unroll
-                for (int q = 0; q < NS; ++q) nz[q] = c.cth * (R)noise_row[(int64_t)i * NS + q];
+                for (int q = 0; q < NS; ++q) nz[q] = c.cth * (R)noise_row[nrow_of(i) * NS + q];
             }
             substep_ref<R, AXIS_Z, TH, EULER>(c, st, aH, aL, TH ? nz : nullptr, guard);
             if (SCALED && (i & 15) == 15) rescale(st);
-            if (traj) {
+            if (traj && i + 1 < traj_rows) {
                 traj[3 * (i + 1) + 0] = st.sx * st.inv_s; traj[3 * (i + 1) + 1] = st.sy * st.inv_s;
                 traj[3 * (i + 1) + 2] = st.z;
             }
@@ -398,7 +400,7 @@ STG_HD void env_step_integrate(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c
     const uint32_t step_id = (uint32_t)c.step;
     if (c.f[FI_HTH] > 0.0 || NOISE == 0)
         integrate<R, AXIS_Z, NOISE, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ph, gid, step_id,
-                                           nrow, nullptr, c.guard);
+                                           nrow, nullptr, c.guard, NOISE == 2 ? a.noise_stride : 0x7fffffff);
     else
         integrate<R, AXIS_Z, 0, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ph, gid, step_id,
                                        nullptr, nullptr, c.guard);
@@ -491,10 +493,11 @@ STG_HD void solve_body(const StgSttSolveArgs& a, int64_t e) {
         double* traj = a.d_traj ? a.d_traj + (int64_t)e * a.traj_stride * 3 : nullptr;
         if (f[FI_HTH] > 0.0 || NOISE == 0)
             integrate<R, AXIS_Z, NOISE, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph,
-                                               a.env_offset + (uint64_t)e, 0u, nrow, traj, guard);
+                                               a.env_offset + (uint64_t)e, 0u, nrow, traj, guard,
+                                               NOISE == 2 ? a.noise_stride : 0x7fffffff, traj ? a.traj_stride : 0x7fffffff);
         else
             integrate<R, AXIS_Z, 0, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph, a.env_offset + (uint64_t)e,
-                                           0u, nullptr, traj, guard);
+                                           0u, nullptr, traj, guard, 0x7fffffff, traj ? a.traj_stride : 0x7fffffff);
     }
     a.d_m_out[3 * e] = mx; a.d_m_out[3 * e + 1] = my; a.d_m_out[3 * e + 2] = mz;
     if (a.d_n_sub) a.d_n_sub[e] = nsub;
