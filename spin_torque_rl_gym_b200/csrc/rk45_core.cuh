@@ -40,6 +40,16 @@ STG_HD double rms3(V3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z) / 1.73
 // per-trajectory inputs resolved from the parameter set + the per-env controls
 struct LlgRhs {
     const StgLlgParams* p;
+    // hot parameters copied out of the table once per trajectory (the RHS is evaluated ~800 times)
+    double gamma, alpha, ex, ey, ez, msnx, msny, msnz, exch, hth, cdp, cfp, cds, cfs, sgx, sgy, sgz;
+    STG_HD void load() {
+        const StgLlgParams& q = *p;
+        gamma = q.gamma; alpha = q.alpha; ex = q.easy_axis[0]; ey = q.easy_axis[1]; ez = q.easy_axis[2];
+        msnx = -q.saturation_magnetization * q.demag_n[0]; msny = -q.saturation_magnetization * q.demag_n[1];
+        msnz = -q.saturation_magnetization * q.demag_n[2];
+        exch = q.exchange_coeff; hth = q.h_th; cdp = q.c_dl_p; cfp = q.c_fl_p; cds = q.c_dl_s; cfs = q.c_fl_s;
+        sgx = q.sigma[0]; sgy = q.sigma[1]; sgz = q.sigma[2];
+    }
     double hk;          // 2 K_eff /(mu0 Ms)
     double J, t_pulse;
     V3 happ;
@@ -53,7 +63,6 @@ struct LlgRhs {
 
     // llgs_rhs (physics/llgs_solver.py:92-126) generalised with the SOT terms (devices/sot_mram.py:163-194)
     STG_HD V3 operator()(double t, V3 y) {
-        const StgLlgParams& q = *p;
         V3 m = {0.0, 0.0, 1.0};                               // :96-101 (y * (1/|y|): <= 1 ulp from NumPy's y / |y|)
         const double n2 = dot3(y, y);
         if (n2 > 1e-24) {
@@ -65,14 +74,14 @@ struct LlgRhs {
             m.x = y.x * inv; m.y = y.y * inv; m.z = y.z * inv;
         }
         const double cur = (t <= t_pulse) ? J : 0.0;
-        const V3 e = {q.easy_axis[0], q.easy_axis[1], q.easy_axis[2]};
+        const V3 e = {ex, ey, ez};
         const double s = hk * dot3(m, e);
         V3 h = {happ.x + s * e.x, happ.y + s * e.y, happ.z + s * e.z};
-        h.x += -q.saturation_magnetization * q.demag_n[0] * m.x;
-        h.y += -q.saturation_magnetization * q.demag_n[1] * m.y;
-        h.z += -q.saturation_magnetization * q.demag_n[2] * m.z;
-        if (q.exchange_coeff != 0.0) { h.x += q.exchange_coeff * m.x; h.y += q.exchange_coeff * m.y; h.z += q.exchange_coeff * m.z; }
-        if (noise_mode != 0 && q.h_th > 0.0) {
+        h.x += msnx * m.x;                                    // -Ms N (.) m
+        h.y += msny * m.y;
+        h.z += msnz * m.z;
+        if (exch != 0.0) { h.x += exch * m.x; h.y += exch * m.y; h.z += exch * m.z; }
+        if (noise_mode != 0 && hth > 0.0) {
             double nx, ny, nz;
             if (noise_mode == 2) {
                 const int64_t k = n_eval < noise_cap ? n_eval : noise_cap - 1;
@@ -85,23 +94,23 @@ struct LlgRhs {
                 box_muller(o[2], o[3], z2, z3);
                 nx = z0; ny = z1; nz = z2;
             }
-            h.x += q.h_th * nx; h.y += q.h_th * ny; h.z += q.h_th * nz;
+            h.x += hth * nx; h.y += hth * ny; h.z += hth * nz;
         }
         ++n_eval;
         V3 tau = {0.0, 0.0, 0.0};
         if (!(fabs(cur) < 1e-12)) {                            // :221-222
-            if (q.c_dl_p != 0.0 || q.c_fl_p != 0.0) {          // Slonczewski pair (uniform branch per parameter set)
-                const V3 ph3 = {q.p_hat[0], q.p_hat[1], q.p_hat[2]};
+            if (cdp != 0.0 || cfp != 0.0) {                    // Slonczewski pair, p = z^ (uniform branch per parameter set)
+                const V3 ph3 = {p->p_hat[0], p->p_hat[1], p->p_hat[2]};
                 const V3 mxp = cross3(m, ph3);
-                tau = tau + (q.c_dl_p * cur) * cross3(m, mxp) + (q.c_fl_p * cur) * mxp;
+                tau = tau + (cdp * cur) * cross3(m, mxp) + (cfp * cur) * mxp;
             }
-            if (q.c_dl_s != 0.0 || q.c_fl_s != 0.0) {          // spin-orbit pair
-                const V3 sg = {q.sigma[0], q.sigma[1], q.sigma[2]};
-                tau = tau + (q.c_dl_s * cur) * cross3(sg, m) + (q.c_fl_s * cur) * sg;
+            if (cds != 0.0 || cfs != 0.0) {                    // spin-orbit pair
+                const V3 sg = {sgx, sgy, sgz};
+                tau = tau + (cds * cur) * cross3(sg, m) + (cfs * cur) * sg;
             }
         }
-        V3 dm = (-q.gamma) * cross3(m, h);                     // :121-124
-        dm = dm + q.alpha * cross3(m, dm);
+        V3 dm = (-gamma) * cross3(m, h);                       // :121-124
+        dm = dm + alpha * cross3(m, dm);
         return dm + tau;
     }
 
@@ -139,6 +148,9 @@ STG_HD double ulp_above(double t) {   // |nextafter(t, +inf) - t| for t >= 0 (th
     return nextafter(t, (double)INFINITY) - t;
 #endif
 }
+// en^(-1/5) of the step-size controller (rk.py:102): exp(-0.2 log en) instead of pow(), whose data-dependent special-case
+// branches diverge across the lanes of a warp; the two agree to a few ulp, far below anything that changes a decision
+STG_HD double pow_m02(double en) { return exp(-0.2 * log(en)); }
 STG_HD V3 vabs_max(V3 a, V3 b) { return {fmax(fabs(a.x), fabs(b.x)), fmax(fabs(a.y), fabs(b.y)), fmax(fabs(a.z), fabs(b.z))}; }
 
 // One trajectory of LLGSSolver.solve. Returns through the StgRk45Args output arrays of env e.
@@ -147,6 +159,7 @@ STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
     const StgLlgParams& q = a.d_table[a.d_param_index ? a.d_param_index[e] : 0];
     LlgRhs f;
     f.p = &q;
+    f.load();
     f.J = a.d_current ? a.d_current[e] : 0.0;
     f.t_pulse = a.d_t_pulse ? a.d_t_pulse[e] : 1.0e300;
     f.happ = a.d_happ ? V3{a.d_happ[3 * e], a.d_happ[3 * e + 1], a.d_happ[3 * e + 2]} : V3{0.0, 0.0, 0.0};
@@ -242,7 +255,7 @@ STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
             const V3 mx = vabs_max(y, y_new);
             const double en = rms3({err.x / (atol + mx.x * rtol), err.y / (atol + mx.y * rtol), err.z / (atol + mx.z * rtol)});
             if (en < 1.0) {
-                double factor = (en == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(en, -0.2));
+                double factor = (en == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow_m02(en));
                 if (rejected) factor = fmin(1.0, factor);
                 h_abs *= factor;
                 t = t_new; y = y_new; fk = f_new;
@@ -250,7 +263,7 @@ STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
                 new_step = true;
                 record(n_acc, t, y);
             } else if (en >= 1.0) {
-                h_abs *= fmax(0.2, 0.9 * pow(en, -0.2));
+                h_abs *= fmax(0.2, 0.9 * pow_m02(en));
                 rejected = true;
                 ++n_rej;
             } else {               // NaN error norm: SciPy would never terminate; flag and stop
