@@ -169,7 +169,12 @@ static void* run_range(void* arg) {
         int guard = 0;
         guard_normalise(mm, &guard);
         const double* nz = noise ? noise + (int64_t)i * noise_stride * S * 3 : 0;
-        Rng rng = {jb->rng_seed * 0x2545F4914F6CDD1DULL + (uint64_t)i * 0x9E3779B97F4A7C15ULL + (uint64_t)step_count[i], 0, 0.0};
+        /* independent stream per (env, step): the start state is a HASH of (seed, env, step). Seeding env i with
+         * base + i*gamma would only shift one splitmix sequence by i positions, i.e. the envs would share their noise. */
+        uint64_t h0 = jb->rng_seed ^ 0xA0761D6478BD642FULL;
+        uint64_t h1 = splitmix(&h0) ^ ((uint64_t)i * 0xE7037ED1A0B428DBULL);
+        uint64_t h2 = splitmix(&h1) ^ ((uint64_t)step_count[i] * 0x8EBC6AF09C88C6E3ULL);
+        Rng rng = {splitmix(&h2), 0, 0.0};
         const int own_noise = (!nz && hth > 0);
         double drawn[12];
         for (int s = 0; s < ns; ++s) {

@@ -459,3 +459,32 @@ def test_reset_seed_reproducibility_and_masked_reset(cuda_device):
         e1.step(act, noise=np.zeros((4, 10, 3, 3)))
     with pytest.raises(RuntimeError):
         _make(2, "f32", cuda_device).step(act[:2])            # step before reset
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_thermal_switching_probability(prec, cuda_device):
+    """North-star statistical parity: start exactly on the +z pole, drive with a destabilising current; whether (and when) the
+    magnetisation switches is decided by the thermal kicks that seed the transverse component (the switching time goes with the
+    log of the noise amplitude: a 3 % amplitude error moves these probabilities by ~0.015). P(crossed the equator) after 310
+    substeps and P(success) after 330 substeps must agree with the oracle (its own Gaussian stream) within the binomial 95 % CI."""
+    from oracle.c_oracle import COracleEnv
+    n_gpu, n_cpu, jm = 65536, 16384, 1.1e-6
+    for T, observable in ((3.1e-10, "crossed"), (3.3e-10, "success")):
+        act = np.tile(np.array([[8e-7, T]], np.float32), (n_gpu, 1))
+        env = _make(n_gpu, prec, cuda_device, max_current=jm, include_thermal_fluctuations=True, temperature=300.0,
+                    rng_seed=2024)
+        env.reset(options={"initial_state": np.array([0.0, 0.0, 1.0]), "target_state": np.array([0.0, 0.0, -1.0])})
+        o, r, te, tr, info = env.step(act)
+        ora = COracleEnv(n_cpu, max_current=jm, include_thermal=True, temperature=300.0, nthreads=os.cpu_count() or 1)
+        ora.rng_seed = 777
+        ora.reset(np.array([0.0, 0.0, 1.0]), np.array([0.0, 0.0, -1.0]))
+        _, _, ote, _ = ora.step(act[:n_cpu])
+        assert int(info["n_sub"][0]) == ora.n_sub[0]
+        if observable == "crossed":
+            p_gpu = float((env.magnetization[:, 2] < 0).double().mean())
+            p_ref = float((ora.m[:, 2] < 0).mean())
+        else:
+            p_gpu, p_ref = float(te.double().mean()), float(ote.mean())
+        assert 0.2 < p_ref < 0.8                                   # the experiment sits on the steep part of the S-curve
+        half = 1.96 * np.sqrt(p_ref * (1 - p_ref) * (1.0 / n_gpu + 1.0 / n_cpu))
+        assert abs(p_gpu - p_ref) < half, (observable, p_gpu, p_ref, half)
