@@ -351,11 +351,12 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_sample = 8192 * threads                      # ~10 s of CPU work on all host threads
+        n_sample = 8192 * threads
         cpu_port_rate(max(threads, n_sample // 64), 1, threads, thermal)
-        rate, _, dt = cpu_port_rate(n_sample, 3, threads, thermal)
+        cpu_steps = 8                                  # 131072 envs x 8 steps on 16 threads: ~13 s
+        rate, _, dt = cpu_port_rate(n_sample, cpu_steps, threads, thermal)
         cpu_baseline = {"value": rate, "unit": "LLGS substeps/s", "cores": threads, "kind": "port",
-                        "sample": f"{n_sample} envs x 3 steps x 999 RK4 substeps (thermal {'on' if thermal else 'off'}), "
+                        "sample": f"{n_sample} envs x {cpu_steps} steps x 999 RK4 substeps (thermal {'on' if thermal else 'off'}), "
                                   f"C restatement oracle/c on {threads} threads, {dt:.1f} s",
                         "python_port_substeps_per_s_1core": python_port_rate(3.0)}
 
