@@ -187,6 +187,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=N_ENVS_PER_GPU)
+    ap.add_argument("--total-envs", type=int, default=0,
+                    help="strong scaling (SURVEY 8e): fixed total env count split evenly over the ranks; the line says "
+                         "'scaling': 'strong'. Default 0 = weak scaling with --envs-per-gpu on every rank")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-thermal", action="store_true", help="secondary workload: thermal off (301 flop/substep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -217,6 +220,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     n_local = args.envs_per_gpu
+    if args.total_envs:
+        if args.total_envs % n_gpus:
+            raise SystemExit(f"--total-envs {args.total_envs} does not divide over {n_gpus} ranks")
+        n_local = args.total_envs // n_gpus
+    scaling = "strong" if args.total_envs else "weak"
     tdtype = torch.float32 if args.dtype == "f32" else torch.float64
     thermal = not args.no_thermal
     kw = dict(ENV_KW, include_thermal_fluctuations=thermal)
@@ -366,7 +374,7 @@ def main():
         line = {
             "metric": "llgs_substeps_per_sec", "value": value, "unit": "LLGS substeps/s",
             "env_steps_per_s": env_steps, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": args.dtype + " stages, f64 state", "data": "synthetic",
             "config": workload_config(n_gpus, n_local),
             "e2e": {"value": e2e_value, "unit": "LLGS substeps/s", "ms_per_step": e2e_ms / args.steps,

@@ -409,6 +409,22 @@ typedef struct StgEnergyParams {
 int stg_energy_landscape_f64(const StgEnergyParams* p, const double* d_m, const double* d_happ, int32_t happ_rows,
                              double* d_energy, double* d_gradient, int64_t n, void* stream);
 
+/* VectorizedMagneticsOperations (utils/vectorized_operations.py:288-393), n rows of 3 doubles, NumPy's operation order:
+ *   CROSS           out[n][3] = a x b                              (batch_cross_product :292-303)
+ *   DOT             out[n]    = sum(a*b, axis=1)                   (batch_dot_product   :305-316)
+ *   NORMALIZE       out[n][3] = a / max(||a||, 1e-12), b unused    (batch_normalize     :318-330)
+ *   ANIS_ENERGY     out[n]    = -p0*p1*(a.b)^2, p0 = K_u[n], p1 = volume[n], b = easy axis (batch_energy_computation :332-364)
+ *   TMR_RESISTANCE  out[n]    = max(p0 (1 + ((p1-p0)/p0)(1 - a.b)/2), p0/2), p0 = R_P[n], p1 = R_AP[n]
+ *                                                                  (batch_resistance_computation :366-393)
+ * d_b holds 1 row (broadcast) or n rows. */
+enum { STG_VEC3_CROSS = 0, STG_VEC3_DOT = 1, STG_VEC3_NORMALIZE = 2, STG_VEC3_ANIS_ENERGY = 3, STG_VEC3_TMR_RESISTANCE = 4 };
+int stg_vec3_op_f64(int32_t op, const double* d_a, const double* d_b, int32_t b_rows, const double* d_p0, const double* d_p1,
+                    double* d_out, int64_t n, void* stream);
+/* EnergyLandscape.generate_phase_diagram (physics/energy_landscape.py:282-340): out[n_fields][n_currents] =
+ * 1 if |field_i| > h_k - |beta * current_j| else 0, beta = P*2.21e5/(2 Ms V), h_k = 2 K_u/(mu0 Ms) (host doubles). */
+int stg_phase_diagram_f64(const double* d_currents, const double* d_fields, int32_t n_currents, int32_t n_fields, double beta,
+                          double h_k, double* d_out, void* stream);
+
 /* FMA-pipe throughput probe (bench.py's measured FP32/FP64 roofline denominator): blocks*256 threads x iters*64 FMAs.
  * f64 = 0: FFMA, 1: DFMA, 2: packed FFMA2 (iters*64 instructions = iters*128 FMAs per thread).
  * d_out: >= blocks*256 elements of the probed type (8 bytes each for modes 1, 2; never written in practice). */

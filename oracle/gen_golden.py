@@ -356,6 +356,62 @@ def gen_next():
     out['land/energy'] = np.array([land.compute_energy(mm[i], happ[i]) for i in range(n)])
     out['land/grad'] = np.array([land.compute_energy_gradient(mm[i], happ[i]) for i in range(n)])
     out['land/energy0'] = np.array([land.compute_energy(mm[i]) for i in range(n)])
+    # phase diagram over a (current, field) grid that straddles the h_k - |beta I| line; stability factor
+    pp = _stt_params(volume=1e-11)
+    land2 = EnergyLandscape(pp)
+    h_k = 2 * pp['uniaxial_anisotropy'] / (4 * np.pi * 1e-7 * pp['saturation_magnetization'])
+    beta = pp.get('polarization', 0.7) * 2.21e5 / (2 * pp['saturation_magnetization'] * pp['volume'])
+    i_max = 1.5 * h_k / beta
+    pd = land2.generate_phase_diagram((-i_max, i_max), (-1.2 * h_k, 1.2 * h_k), resolution=37)
+    out['phase/volume'] = 1e-11; out['phase/i_max'] = i_max; out['phase/h_max'] = 1.2 * h_k
+    for k, v in pd.items():
+        out[f'phase/{k}'] = np.asarray(v)
+    out['phase/stability_300'] = land2.compute_thermal_stability_factor(300.0)
+    out['phase/stability_77'] = land2.compute_thermal_stability_factor(77.0)
+    # energy barrier along the straight path between two tilted states of the anisotropic-demag landscape `land`
+    s0, s1 = np.array([0.1, 0.55, 0.83]), np.array([0.2, -0.6, -0.7])
+    hb = np.array([2e3, -1e3, 5e2])
+    bh, ep = land.compute_energy_barrier(s0, s1, hb, n_intermediate=41)
+    out['barrier/s0'] = s0; out['barrier/s1'] = s1; out['barrier/happ'] = hb
+    out['barrier/height'] = bh; out['barrier/path'] = ep
+    out['barrier/height_nofield'] = land.compute_energy_barrier(s0, s1)[0]
+    # VectorizedMagneticsOperations on random rows (un-normalised, one zero row for the 1e-12 floor)
+    from spin_torque_gym.utils.vectorized_operations import VectorizedMagneticsOperations as VMO
+    nv = 64
+    a = rng.normal(size=(nv, 3)) * rng.uniform(1e-3, 1e3, (nv, 1))
+    b = rng.normal(size=(nv, 3))
+    a[5] = 0.0
+    k_u = rng.uniform(0.5e6, 2e6, nv); vol = rng.uniform(1e-24, 1e-22, nv)
+    easy = rng.normal(size=(nv, 3)); easy /= np.linalg.norm(easy, axis=1, keepdims=True)
+    r_p = rng.uniform(500.0, 2000.0, nv); r_ap = r_p * rng.uniform(0.2, 3.0, nv)     # some R_AP < R_P: the R_P/2 floor binds
+    out.update({'vmo/a': a, 'vmo/b': b, 'vmo/k_u': k_u, 'vmo/volume': vol, 'vmo/easy': easy, 'vmo/r_p': r_p, 'vmo/r_ap': r_ap})
+    out['vmo/cross'] = VMO.batch_cross_product(a, b)
+    out['vmo/dot'] = VMO.batch_dot_product(a, b)
+    out['vmo/normalize'] = VMO.batch_normalize(a)
+    out['vmo/energy'] = VMO.batch_energy_computation(b, {'uniaxial_anisotropy': k_u, 'volume': vol, 'easy_axis': easy})
+    out['vmo/energy_default'] = VMO.batch_energy_computation(b, {})
+    out['vmo/energy_one_axis'] = VMO.batch_energy_computation(b, {'uniaxial_anisotropy': k_u, 'volume': vol,
+                                                                  'easy_axis': np.array([0.0, 0.6, 0.8])})
+    bn = b / np.linalg.norm(b, axis=1, keepdims=True)
+    ref = easy.copy()
+    ref[:6] = -bn[:6]; r_ap[:6] = 0.1 * r_p[:6]                  # antiparallel rows with R_AP << R_P sit on the floor
+    out['vmo/r_ap'] = r_ap
+    out['vmo/bn'] = bn; out['vmo/ref'] = ref
+    out['vmo/resistance'] = VMO.batch_resistance_computation(bn, ref, r_p, r_ap)
+    # ThermalFluctuations analytics (physics/thermal_model.py:139-336)
+    from spin_torque_gym.physics import ThermalFluctuations
+    tp = dict(volume=1.5e-25, uniaxial_anisotropy=1.1e6, damping=0.02, saturation_magnetization=7.5e5)   # Delta(300 K) ~ 40
+    th = ThermalFluctuations(temperature=320.0, seed=9)
+    barrier = 1.1e6 * 1.5e-25 * 0.5
+    out['th/barrier_J'] = barrier
+    out['th/switch_times'] = np.array([th.sample_switching_time(barrier) for _ in range(5)])
+    sweep = th.generate_temperature_sweep((50.0, 450.0), tp, n_points=23)
+    for k, v in sweep.items():
+        out[f'th/sweep/{k}'] = np.asarray(v)
+    out['th/temperature_after_sweep'] = th.temperature
+    st = th.analyze_thermal_stability(tp, time_scale=3.0)
+    for k, v in st.items():
+        out[f'th/stability/{k}'] = np.asarray(v)
     np.savez_compressed(os.path.join(GOLD, "next.npz"), **out)
     print("wrote next.npz")
 

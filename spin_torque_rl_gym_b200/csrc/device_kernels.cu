@@ -130,6 +130,59 @@ __global__ void __launch_bounds__(256) energy_landscape_kernel(const __grid_cons
     }
 }
 
+// VectorizedMagneticsOperations (utils/vectorized_operations.py:288-393): row-wise 3-vector helpers. Products and sums are
+// left unfused (dmul/dadd) and summed left to right so every result carries NumPy's roundings bit for bit.
+__global__ void __launch_bounds__(256) vec3_op_kernel(int op, const double* a, const double* b, int b_rows, const double* p0,
+                                                      const double* p1, double* out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ax = a[3 * i], ay = a[3 * i + 1], az = a[3 * i + 2];
+    double bx = 0.0, by = 0.0, bz = 0.0;
+    if (b) {
+        const int64_t r = b_rows == 1 ? 0 : i;
+        bx = b[3 * r]; by = b[3 * r + 1]; bz = b[3 * r + 2];
+    }
+    const double dot = dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz));     // np.sum(a*b, axis=1)
+    switch (op) {
+    case STG_VEC3_CROSS:                                                          // np.cross: a1*b2 - a2*b1, ...
+        out[3 * i] = dadd(dmul(ay, bz), -dmul(az, by));
+        out[3 * i + 1] = dadd(dmul(az, bx), -dmul(ax, bz));
+        out[3 * i + 2] = dadd(dmul(ax, by), -dmul(ay, bx));
+        break;
+    case STG_VEC3_DOT:
+        out[i] = dot;
+        break;
+    case STG_VEC3_NORMALIZE: {                                                    // v / max(||v||, 1e-12)
+        double nrm = sqrt(dadd(dadd(dmul(ax, ax), dmul(ay, ay)), dmul(az, az)));
+        nrm = nrm > 1e-12 ? nrm : 1e-12;
+        out[3 * i] = ddiv(ax, nrm); out[3 * i + 1] = ddiv(ay, nrm); out[3 * i + 2] = ddiv(az, nrm);
+        break;
+    }
+    case STG_VEC3_ANIS_ENERGY:                                                    // -K_u * V * (m.e)^2
+        out[i] = dmul(dmul(-p0[i], p1[i]), dmul(dot, dot));
+        break;
+    case STG_VEC3_TMR_RESISTANCE: {                                               // max(R_P (1 + tmr (1 - cos)/2), R_P/2)
+        const double rp = p0[i], rap = p1[i];
+        const double tmr = ddiv(dadd(rap, -rp), rp);
+        const double r = dmul(rp, dadd(1.0, ddiv(dmul(tmr, dadd(1.0, -dot)), 2.0)));
+        const double lo = dmul(rp, 0.5);
+        out[i] = r > lo ? r : lo;                                                 // np.maximum; NaN rows propagate below
+        if (r != r) out[i] = r;
+        break;
+    }
+    }
+}
+
+// EnergyLandscape.generate_phase_diagram (physics/energy_landscape.py:282-340): out[i][j] = |H_i| > h_k - |beta I_j|
+__global__ void __launch_bounds__(256) phase_diagram_kernel(const double* currents, const double* fields, int n_currents,
+                                                            int64_t n, double beta, double h_k, double* out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const int64_t i = g / n_currents, j = g - i * n_currents;
+    const double h_critical = dadd(h_k, -fabs(dmul(beta, currents[j])));
+    out[g] = fabs(fields[i]) > h_critical ? 1.0 : 0.0;
+}
+
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace stg
@@ -197,5 +250,26 @@ extern "C" int stg_energy_landscape_f64(const StgEnergyParams* p, const double* 
     if (n < 0 || (d_happ && happ_rows != 1 && happ_rows != n)) return STG_E_SIZE;
     if (n == 0) return STG_OK;
     energy_landscape_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*p, d_m, d_happ, happ_rows, d_energy, d_gradient, n);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int stg_vec3_op_f64(int32_t op, const double* d_a, const double* d_b, int32_t b_rows, const double* d_p0,
+                               const double* d_p1, double* d_out, int64_t n, void* stream) {
+    if (op < STG_VEC3_CROSS || op > STG_VEC3_TMR_RESISTANCE) return STG_E_ENUM;
+    if (!d_a || !d_out || (op != STG_VEC3_NORMALIZE && !d_b)) return STG_E_NULL;
+    if ((op == STG_VEC3_ANIS_ENERGY || op == STG_VEC3_TMR_RESISTANCE) && (!d_p0 || !d_p1)) return STG_E_NULL;
+    if (n < 0 || (d_b && b_rows != 1 && b_rows != n)) return STG_E_SIZE;
+    if (n == 0) return STG_OK;
+    vec3_op_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(op, d_a, d_b, b_rows, d_p0, d_p1, d_out, n);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int stg_phase_diagram_f64(const double* d_currents, const double* d_fields, int32_t n_currents, int32_t n_fields,
+                                     double beta, double h_k, double* d_out, void* stream) {
+    if (!d_currents || !d_fields || !d_out) return STG_E_NULL;
+    if (n_currents < 0 || n_fields < 0) return STG_E_SIZE;
+    const int64_t n = (int64_t)n_currents * n_fields;
+    if (n == 0) return STG_OK;
+    phase_diagram_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(d_currents, d_fields, n_currents, n, beta, h_k, d_out);
     return (int)cudaGetLastError();
 }

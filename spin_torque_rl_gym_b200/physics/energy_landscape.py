@@ -1,9 +1,10 @@
-"""Batched EnergyLandscape.compute_energy / compute_energy_gradient (reference: physics/energy_landscape.py:16-104) on the GPU:
+"""Batched EnergyLandscape.compute_energy / compute_energy_gradient / generate_phase_diagram (reference:
+physics/energy_landscape.py:16-104,282-359) on the GPU:
 the step *before* the hot path (choosing targets / parameters, phase diagrams over (J, H) grids are embarrassingly parallel)."""
 from __future__ import annotations
 
 import ctypes as C
-from typing import Any, Dict, Optional
+from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
 
@@ -20,6 +21,7 @@ class EnergyLandscape:
         self.k_u = device_params.get("uniaxial_anisotropy", 1e6)
         self.easy_axis = np.asarray(device_params.get("easy_axis", np.array([0, 0, 1])), dtype=float)
         self.demag_factors = np.asarray(device_params.get("demag_factors", np.array([0, 0, 1])), dtype=float)
+        self.k_b = 1.380649e-23
         self._device = torch.device(device)
         self._lib = _lib.load()
 
@@ -55,3 +57,39 @@ class EnergyLandscape:
     def compute_energy_gradient(self, magnetization, applied_field=None):
         """Effective field of one state or a batch (physics/energy_landscape.py:73-104)."""
         return self._call(magnetization, applied_field, False, True)
+
+    def compute_energy_barrier(self, initial_state, final_state, applied_field=None, n_intermediate: int = 50):
+        """(barrier height, energy path) along the normalised straight-line path between two states, all points in one
+        launch of the energy kernel (physics/energy_landscape.py:179-221)."""
+        a, b = np.asarray(initial_state, dtype=float), np.asarray(final_state, dtype=float)
+        t = np.linspace(0, 1, n_intermediate)[:, None]
+        path = (1 - t) * a + t * b
+        path = path / np.linalg.norm(path, axis=1, keepdims=True)
+        happ = np.zeros(3) if applied_field is None else np.asarray(applied_field, dtype=float)
+        energy_path = np.asarray(self._call(path, happ.reshape(1, 3), True, False))
+        return np.max(energy_path) - min(energy_path[0], energy_path[-1]), energy_path
+
+    def generate_phase_diagram(self, current_range: Tuple[float, float], field_range: Tuple[float, float],
+                               resolution: int = 50, save_path: Optional[str] = None) -> Dict[str, np.ndarray]:
+        """Switching map over a (current, field) grid: 1 where |H| exceeds h_k - |beta I| (physics/energy_landscape.py:282-340).
+        `switching_probability[i, j]` belongs to `fields[i]`, `currents[j]`. The reference also draws a matplotlib figure;
+        plotting is outside the path, so `save_path` is accepted and ignored."""
+        torch = _lib.require_cuda()
+        currents = np.linspace(current_range[0], current_range[1], resolution)
+        fields = np.linspace(field_range[0], field_range[1], resolution)
+        beta = self.device_params.get("polarization", 0.7) * 2.21e5 / (2 * self.ms * self.volume)
+        h_k = 2 * self.k_u / (self.mu_0 * self.ms)
+        d_i = torch.as_tensor(currents).to(self._device)
+        d_h = torch.as_tensor(fields).to(self._device)
+        out = torch.empty(resolution, resolution, dtype=torch.float64, device=self._device)
+        with torch.cuda.device(self._device):
+            _lib.check(self._lib.stg_phase_diagram_f64(
+                d_i.data_ptr(), d_h.data_ptr(), resolution, resolution, float(beta), float(h_k), out.data_ptr(),
+                torch.cuda.current_stream(self._device).cuda_stream), "stg_phase_diagram_f64")
+        return {"currents": currents, "fields": fields, "switching_probability": out.cpu().numpy()}
+
+    def compute_thermal_stability_factor(self, temperature: float = 300.0) -> float:
+        """Delta = K_u V / (k_B T) (physics/energy_landscape.py:342-359)."""
+        if temperature <= 0:
+            return float("inf")
+        return self.k_u * self.volume / (self.k_b * temperature)

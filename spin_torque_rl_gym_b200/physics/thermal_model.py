@@ -19,6 +19,7 @@ class ThermalFluctuations:
         self.k_b = 1.380649e-23
         self.mu_0 = 4 * np.pi * 1e-7
         self.seed = 0 if seed is None else int(seed)
+        self.rng = np.random.default_rng(seed)        # host stream of sample_switching_time (thermal_model.py:36)
         self.num_devices = int(num_devices)
         self._device = torch.device(device)
         self._lib = _lib.load()
@@ -66,6 +67,15 @@ class ThermalFluctuations:
         rate = attempt_frequency * math.exp(-energy_barrier / (self.k_b * self.temperature))
         return min(1 - math.exp(-rate * measurement_time), 1.0)
 
+    def sample_switching_time(self, energy_barrier: float, attempt_frequency: float = 1e9) -> float:
+        """One exponential waiting time at the Neel-Brown rate (physics/thermal_model.py:185-207)."""
+        if self.temperature <= 0:
+            return float("inf")
+        rate = attempt_frequency * np.exp(-energy_barrier / (self.k_b * self.temperature))
+        if rate <= 0:
+            return float("inf")
+        return self.rng.exponential(1.0 / rate)
+
     def compute_retention_time(self, energy_barrier: float, failure_rate: float = 1e-9,
                                attempt_frequency: float = 1e9) -> float:
         if self.temperature <= 0 or failure_rate <= 0:
@@ -86,3 +96,24 @@ class ThermalFluctuations:
             "retention_time_years": self.compute_retention_time(barrier) / (365.25 * 24 * 3600),
             "is_thermally_stable": delta > 40, "temperature_K": self.temperature,
         }
+
+    def generate_temperature_sweep(self, temp_range: Tuple[float, float], device_params: dict, n_points: int = 100) -> dict:
+        """Stability factor, one-year switching probability, retention time (years) and noise strength on a temperature
+        grid; the instance temperature is restored afterwards (physics/thermal_model.py:274-336)."""
+        year = 365.25 * 24 * 3600
+        temperatures = np.linspace(temp_range[0], temp_range[1], n_points)
+        volume = device_params.get("volume", 1e-24)
+        k_u = device_params.get("uniaxial_anisotropy", 1e6)
+        damping = device_params.get("damping", 0.01)
+        ms = device_params.get("saturation_magnetization", 800e3)
+        keep = self.temperature
+        cols = {"thermal_stability_factor": [], "switching_probability": [], "retention_time": [], "noise_strength": []}
+        for temp in temperatures:
+            self.set_temperature(temp)
+            barrier = k_u * volume
+            cols["thermal_stability_factor"].append(self.compute_thermal_barrier(k_u, volume))
+            cols["switching_probability"].append(self.compute_switching_probability(barrier, measurement_time=year))
+            cols["retention_time"].append(self.compute_retention_time(barrier) / year)
+            cols["noise_strength"].append(self.compute_noise_strength(damping, ms, volume))
+        self.set_temperature(keep)
+        return {"temperature": temperatures, **{k: np.array(v) for k, v in cols.items()}}

@@ -1,5 +1,6 @@
 """VectorizedSolver with the reference's batch API (utils/vectorized_operations.py:14-300) on the K1 solver kernel:
-explicit Euler, no current, no thermal field, `n_steps = max(10, int(T/dt))`, one parameter dict per trajectory."""
+explicit Euler, no current, no thermal field, `n_steps = max(10, int(T/dt))`, one parameter dict per trajectory; and
+VectorizedMagneticsOperations (utils/vectorized_operations.py:288-393) on the K4 row-wise kernel."""
 from __future__ import annotations
 
 import ctypes as C
@@ -83,3 +84,68 @@ class VectorizedSolver:
 
     def solve_single(self, m_initial: np.ndarray, t_span: Tuple[float, float], device_params: Dict[str, Any], **kwargs):
         return self.solve_batch(np.asarray(m_initial, dtype=float).reshape(1, -1), t_span, [device_params])[0]
+
+
+_VEC3 = {"cross": 0, "dot": 1, "normalize": 2, "anis_energy": 3, "tmr_resistance": 4}     # include/stg.h STG_VEC3_*
+
+
+def _vec3_op(op: str, a, b=None, p0=None, p1=None, device: Any = "cuda"):
+    """Run one STG_VEC3_* op. NumPy inputs come back as NumPy, CUDA tensors stay on the device."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    was_numpy = not isinstance(a, torch.Tensor)
+    dev = torch.device(device) if was_numpy else a.device
+    if dev.type != "cuda":
+        raise _lib.StgError("VectorizedMagneticsOperations runs on CUDA tensors only (there is no CPU path)")
+
+    def dev64(x, cols=None):
+        if x is None:
+            return None
+        t = torch.as_tensor(np.asarray(x, dtype=np.float64)) if not isinstance(x, torch.Tensor) else x
+        t = t.to(device=dev, dtype=torch.float64)
+        return (t.reshape(-1, cols) if cols else t.reshape(-1)).contiguous()
+
+    ta, tb = dev64(a, 3), dev64(b, 3)
+    n = ta.shape[0]
+    if tb is not None and tb.shape[0] not in (1, n):
+        raise ValueError(f"second operand has {tb.shape[0]} rows, expected 1 or {n}")
+    tp0, tp1 = dev64(p0), dev64(p1)
+    for t in (tp0, tp1):
+        if t is not None and t.numel() != n:
+            raise ValueError(f"per-row parameter has {t.numel()} entries, expected {n}")
+    out = torch.empty((n, 3) if op in ("cross", "normalize") else (n,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.stg_vec3_op_f64(_VEC3[op], ta.data_ptr(), _lib.ptr(tb), 0 if tb is None else tb.shape[0],
+                                       _lib.ptr(tp0), _lib.ptr(tp1), out.data_ptr(), n,
+                                       torch.cuda.current_stream(dev).cuda_stream), "stg_vec3_op_f64")
+    return out.cpu().numpy() if was_numpy else out
+
+
+class VectorizedMagneticsOperations:
+    """Row-wise helpers over [N,3] batches with the reference's names and argument meaning
+    (utils/vectorized_operations.py:288-393); results carry NumPy's roundings bit for bit."""
+
+    @staticmethod
+    def batch_cross_product(a_batch, b_batch):
+        return _vec3_op("cross", a_batch, b_batch)
+
+    @staticmethod
+    def batch_dot_product(a_batch, b_batch):
+        return _vec3_op("dot", a_batch, b_batch)
+
+    @staticmethod
+    def batch_normalize(vectors):
+        return _vec3_op("normalize", vectors)
+
+    @staticmethod
+    def batch_energy_computation(m_batch, params_batch: Dict[str, Any]):
+        """Anisotropy energy -K_u V (m.e)^2 per row; defaults K_u = 1e6, V = 1e-24, e = z (:332-364)."""
+        n = int(np.prod(m_batch.shape[:-1]))
+        k_u = params_batch.get("uniaxial_anisotropy", np.full(n, 1e6))
+        volume = params_batch.get("volume", np.full(n, 1e-24))
+        easy = params_batch.get("easy_axis", np.array([0.0, 0.0, 1.0]))
+        return _vec3_op("anis_energy", m_batch, easy, k_u, volume)
+
+    @staticmethod
+    def batch_resistance_computation(m_batch, reference_magnetizations, r_p_batch, r_ap_batch):
+        return _vec3_op("tmr_resistance", m_batch, reference_magnetizations, r_p_batch, r_ap_batch)
