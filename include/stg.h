@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 1
+#define STG_ABI_VERSION 2
 
 /* error codes */
 #define STG_OK 0
@@ -179,7 +179,14 @@ typedef struct StgSttResetArgs {
 /* Argument block of a batched SimpleLLGSSolver.solve for rectangular pulses (physics/simple_solver.py:71-191):
  *   d_m0 [n][3] f64; d_pulse [n][3] f64 rows (J, t_pulse, t_end): current_func(t) = J if t <= t_pulse else 0 on (0, t_end);
  *   d_m_out [n][3] f64 last trajectory row; d_traj NULL or [n][traj_stride][3] f64 (rows 0..n_sub);
- *   d_n_sub [n] int32 out (may be NULL); d_guard [n] int32 out (may be NULL): 1 if the non-finite guard fired. */
+ *   d_n_sub [n] int32 out (may be NULL); d_guard [n] int32 out (may be NULL): 1 if the non-finite guard fired.
+ * Arbitrary current_func / field_func callables cannot cross into a kernel; the host samples them at the stage times the
+ * reference evaluates them at, (t_i, t_i + dt/2, t_i + dt) with t = linspace(0, t_end, n_sub + 1), dt = t_end / n_sub
+ * (physics/simple_solver.py:137-145, 278-295), and passes the samples:
+ *   d_current_grid NULL or [grid_envs][grid_stride][3] f64       J at the three times (replaces d_pulse's J, t_pulse)
+ *   d_field_grid   NULL or [grid_envs][grid_stride][3][3] f64    H_app (A/m) at the three times (added to the table's field)
+ *   grid_envs = 1 (one grid shared by every trajectory) or n_envs; substeps beyond grid_stride reuse the last row.
+ * With either grid the solve runs the FP64 general-geometry stages (both entry points). */
 typedef struct StgSttSolveArgs {
     const StgSttFolded* d_table;
     const int32_t* d_param_index;
@@ -197,6 +204,11 @@ typedef struct StgSttSolveArgs {
     int64_t n_envs;
     int32_t n_sets;
     uint32_t flags;
+    const double* d_current_grid;
+    const double* d_field_grid;
+    int64_t grid_stride;
+    int32_t grid_envs;
+    int32_t reserved;
 } StgSttSolveArgs;
 
 int stg_abi_version(void);

@@ -412,6 +412,39 @@ def gen_next():
     st = th.analyze_thermal_stability(tp, time_scale=3.0)
     for k, v in st.items():
         out[f'th/stability/{k}'] = np.asarray(v)
+    # SimpleLLGSSolver.solve with callables that are NOT rectangular pulses / constant fields (sampled onto a
+    # per-substep grid by the replacement). Well-conditioned STT regime (J ~ 1e-6 A/m^2 at the default volume).
+    from spin_torque_gym.physics.simple_solver import SimpleLLGSSolver as RefSimple
+
+    def ref_solver(method):
+        sv = RefSimple(method=method)
+        sv.timeout = 1e9                 # no wall-clock abort
+        sv.optimizer.cache.ttl = -1      # the memo key omits current_func / field_func
+        return sv
+
+    gp = _stt_params()
+    w = 2 * np.pi / 1.7e-10
+    cur_sin = lambda t: 1.0e-6 * np.sin(w * t) + 2.0e-7                                  # noqa: E731
+    cur_steps = lambda t: 9e-7 if t < 0.8e-10 else (-6e-7 if t < 2.1e-10 else 3e-7)     # noqa: E731  three levels
+    cur_rect = lambda t: 8e-7 if t <= 1.3e-10 else 0.0                                   # noqa: E731
+    fld_rot = lambda t: 2.0e5 * np.array([np.cos(w * t), np.sin(w * t), 0.3])           # noqa: E731
+    fld_const = lambda t: np.array([1.0e5, -5.0e4, 2.0e4])                               # noqa: E731
+    gm0 = np.array([0.45, -0.3, 0.84]); gm0 /= np.linalg.norm(gm0)
+    gcases = {
+        'sin_rk4': ('rk4', (0.0, 3.0e-10), cur_sin, None),
+        'sin_constfield_rk4': ('rk4', (0.0, 3.0e-10), cur_sin, fld_const),
+        'rect_rotfield_rk4': ('rk4', (0.0, 3.0e-10), cur_rect, fld_rot),
+        'steps_rotfield_rk4': ('rk4', (0.0, 3.0e-10), cur_steps, fld_rot),
+        'steps_rotfield_euler': ('euler', (0.0, 3.0e-10), cur_steps, fld_rot),
+        'sin_rotfield_offset_rk4': ('rk4', (1.0e-10, 3.5e-10), cur_sin, fld_rot),        # t_start != 0: absolute times
+        'sin_short_rk4': ('rk4', (0.0, 4.0e-12), cur_sin, fld_rot),                      # T < 10 ps: dt = T/100
+    }
+    out['grid/m0'] = gm0
+    for name, (method, span, cf, ff) in gcases.items():
+        res = ref_solver(method).solve(gm0.copy(), span, gp, cf, ff)
+        assert res['success'], (name, res['message'])
+        out[f'grid/{name}/m'] = res['m']; out[f'grid/{name}/t'] = res['t']
+        print(name, res['n_steps'], res['m'][-1], flush=True)
     np.savez_compressed(os.path.join(GOLD, "next.npz"), **out)
     print("wrote next.npz")
 

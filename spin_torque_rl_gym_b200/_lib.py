@@ -75,7 +75,8 @@ class StgSttSolveArgs(C.Structure):
                 ("d_pulse", C.c_void_p), ("d_m_out", C.c_void_p), ("d_traj", C.c_void_p), ("traj_stride", C.c_int64),
                 ("d_n_sub", C.c_void_p), ("d_guard", C.c_void_p), ("d_noise", C.c_void_p),
                 ("noise_stride", C.c_int64), ("seed", C.c_uint64), ("env_offset", C.c_uint64), ("n_envs", C.c_int64),
-                ("n_sets", C.c_int32), ("flags", C.c_uint32)]
+                ("n_sets", C.c_int32), ("flags", C.c_uint32), ("d_current_grid", C.c_void_p), ("d_field_grid", C.c_void_p),
+                ("grid_stride", C.c_int64), ("grid_envs", C.c_int32), ("reserved", C.c_int32)]
 
 
 class StgDeviceParams(C.Structure):
@@ -167,6 +168,7 @@ SYMBOLS = {
     "stg_probe_fma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
+ABI_VERSION = 2          # include/stg.h STG_ABI_VERSION (2: StgSttSolveArgs grew the sampled current / field grids)
 _LIB: Optional[C.CDLL] = None
 
 
@@ -198,8 +200,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.stg_abi_version() != 1:
-        raise StgError("libstg.so ABI version mismatch")
+    if lib.stg_abi_version() != ABI_VERSION:
+        raise StgError(f"libstg.so ABI version {lib.stg_abi_version()} != {ABI_VERSION} expected by this package "
+                       "(stale build? run __graft_entry__.build())")
     _LIB = lib
     return lib
 

@@ -504,6 +504,98 @@ STG_HD void solve_body(const StgSttSolveArgs& a, int64_t e) {
     if (a.d_guard) a.d_guard[e] = guard;
 }
 
+// Fixed-step solve with current_func / field_func sampled by the host at the reference's stage times (include/stg.h,
+// StgSttSolveArgs): row r of jgrid holds J at (t_i, t_i + dt/2, t_i + dt), hgrid the applied field at the same times. FP64
+// general-geometry stages; a rectangular pulse (J, t_pulse) is used when only the field is sampled.
+template <int NOISE, bool EULER>
+STG_HD void integrate_grid(const double* f, double J, double& mx, double& my, double& mz, int n, double dt, double t_pulse,
+                           const double* jgrid, const double* hgrid, int64_t grid_rows, const Philox& ph, uint64_t gid,
+                           const double* noise_row, double* traj, int& guard, int64_t noise_rows, int64_t traj_rows) {
+    constexpr bool TH = NOISE != 0;
+    constexpr int NS = EULER ? 3 : 12;
+    StepConsts<double> c;
+    make_consts<double>(f, dt, 0.0, 1.0, c);
+    const double G = -f[FI_GEFF] * dt;
+    const float nscale = -1.3862943611198906f * (float)c.cth * (float)c.cth;
+    ScaledState st{mx, my, mz, 1.0, 1.0, 1.0f};
+    if (traj) { traj[0] = mx; traj[1] = my; traj[2] = mz; }
+    for (int i = 0; i < n; ++i) {
+        const int64_t r = i < grid_rows ? i : grid_rows - 1;
+        double nz[NS];
+        if (NOISE == 1) {
+            float z[12];
+            if (EULER) philox_normals4(ph, gid, 0u, (uint32_t)i, 0u, nscale, z);
+            else philox_normals12(ph, gid, 0u, (uint32_t)i, nscale, z);
+#pragma unroll
+            for (int q = 0; q < NS; ++q) nz[q] = (double)z[q];
+        } else if (NOISE == 2) {
+            const int64_t nr = i < noise_rows ? i : noise_rows - 1;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) nz[q] = c.cth * noise_row[nr * NS + q];
+        }
+        // stage s (0..3) reads the sample of time group g: 0 -> t_i, 1 -> t_i + dt/2, 2 -> t_i + dt
+        auto stage = [&](int g, int s, double x, double y, double z, double& kx, double& ky, double& kz) {
+            StepConsts<double> cg = c;
+            if (hgrid) {
+                const double* h = hgrid + (r * 3 + g) * 3;
+                cg.bax += G * h[0]; cg.bay += G * h[1]; cg.baz += G * h[2];
+            }
+            const double jt = jgrid ? jgrid[r * 3 + g] : (pulse_on(i, g, dt, t_pulse) ? J : 0.0);
+            const double a = (fabs(jt) > 1e-12) ? f[FI_AJ_PER_J] * jt * dt : 0.0;      // physics/simple_solver.py:327-331
+            stage_general<double, TH>(cg, x, y, z, a, 0.0, TH ? nz[3 * s] : 0.0, TH ? nz[3 * s + 1] : 0.0,
+                                      TH ? nz[3 * s + 2] : 0.0, kx, ky, kz);
+        };
+        const double x = st.sx, y = st.sy, z = st.z;
+        double k1x, k1y, k1z, ix, iy, iz;
+        stage(0, 0, x, y, z, k1x, k1y, k1z);
+        if (EULER) {
+            ix = k1x; iy = k1y; iz = k1z;
+        } else {
+            double k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
+            stage(1, 1, x + 0.5 * k1x, y + 0.5 * k1y, z + 0.5 * k1z, k2x, k2y, k2z);
+            stage(1, 2, x + 0.5 * k2x, y + 0.5 * k2y, z + 0.5 * k2z, k3x, k3y, k3z);
+            stage(2, 3, x + k3x, y + k3y, z + k3z, k4x, k4y, k4z);
+            ix = (k1x + 2.0 * (k2x + k3x) + k4x) / 6.0;
+            iy = (k1y + 2.0 * (k2y + k3y) + k4y) / 6.0;
+            iz = (k1z + 2.0 * (k2z + k3z) + k4z) / 6.0;
+        }
+        st.sx += ix; st.sy += iy; st.z += iz;
+        guard_normalise<double>(st, guard);
+        if (traj && i + 1 < traj_rows) { traj[3 * (i + 1)] = st.sx; traj[3 * (i + 1) + 1] = st.sy; traj[3 * (i + 1) + 2] = st.z; }
+    }
+    mx = st.sx; my = st.sy; mz = st.z;
+}
+
+template <int NOISE, bool EULER>
+STG_HD void solve_grid_body(const StgSttSolveArgs& a, int64_t e) {
+    const double* f = a.d_table[a.d_param_index ? a.d_param_index[e] : 0].v;
+    double mx = a.d_m0[3 * e], my = a.d_m0[3 * e + 1], mz = a.d_m0[3 * e + 2];
+    const double J = a.d_pulse[3 * e], t_pulse = a.d_pulse[3 * e + 1], t_end = a.d_pulse[3 * e + 2];
+    int guard = 0, nsub = 0;
+    guard_normalise<double>(mx, my, mz, guard);
+    if (t_end > 0.0) {
+        const StepPlan plan = substep_plan(t_end, f[FI_MAXSTEP_DT]);
+        nsub = plan.n;
+        Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+        const int64_t ge = a.grid_envs == 1 ? 0 : e;
+        const double* jg = a.d_current_grid ? a.d_current_grid + ge * a.grid_stride * 3 : nullptr;
+        const double* hg = a.d_field_grid ? a.d_field_grid + ge * a.grid_stride * 9 : nullptr;
+        const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
+        double* traj = a.d_traj ? a.d_traj + (int64_t)e * a.traj_stride * 3 : nullptr;
+        if (f[FI_HTH] > 0.0 || NOISE == 0)
+            integrate_grid<NOISE, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, jg, hg, a.grid_stride, ph,
+                                         a.env_offset + (uint64_t)e, nrow, traj, guard,
+                                         NOISE == 2 ? a.noise_stride : 0x7fffffff, traj ? a.traj_stride : 0x7fffffff);
+        else
+            integrate_grid<0, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, jg, hg, a.grid_stride, ph,
+                                     a.env_offset + (uint64_t)e, nullptr, traj, guard, 0x7fffffff,
+                                     traj ? a.traj_stride : 0x7fffffff);
+    }
+    a.d_m_out[3 * e] = mx; a.d_m_out[3 * e + 1] = my; a.d_m_out[3 * e + 2] = mz;
+    if (a.d_n_sub) a.d_n_sub[e] = nsub;
+    if (a.d_guard) a.d_guard[e] = guard;
+}
+
 // substep-count bin of an env's action for the counting sort (descending n_sub)
 STG_HD int action_bin(const StgSttFolded* table, const int32_t* pidx, const float* action, int64_t e) {
     const double* f = table[pidx ? pidx[e] : 0].v;

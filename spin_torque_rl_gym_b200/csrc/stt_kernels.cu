@@ -292,6 +292,13 @@ __global__ void __launch_bounds__(kBlock) stt_solve_kernel(const __grid_constant
     solve_body<R, AXIS_Z, NOISE, EULER>(a, e);
 }
 
+template <int NOISE, bool EULER>
+__global__ void __launch_bounds__(kBlock) stt_solve_grid_kernel(const __grid_constant__ SolveArgs a) {
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e >= a.n_envs) return;
+    solve_grid_body<NOISE, EULER>(a, e);
+}
+
 // ---- dispatch --------------------------------------------------------------------------------------------------------
 template <typename R, bool AXIS_Z, int NOISE>
 static cudaError_t launch_step2(const StepArgs& a, cudaStream_t s) {
@@ -336,9 +343,23 @@ static cudaError_t launch_solve2(const SolveArgs& a, uint32_t flags, cudaStream_
         stt_solve_kernel<R, AXIS_Z, NOISE, false><<<grid, kBlock, 0, s>>>(a);
     return cudaGetLastError();
 }
+template <int NOISE>
+static cudaError_t launch_solve_grid(const SolveArgs& a, uint32_t flags, cudaStream_t s) {
+    const unsigned grid = (unsigned)((a.n_envs + kBlock - 1) / kBlock);
+    if (flags & STG_F_EULER)
+        stt_solve_grid_kernel<NOISE, true><<<grid, kBlock, 0, s>>>(a);
+    else
+        stt_solve_grid_kernel<NOISE, false><<<grid, kBlock, 0, s>>>(a);
+    return cudaGetLastError();
+}
 template <typename R>
 static cudaError_t launch_solve(const SolveArgs& a, uint32_t flags, bool axis_z, cudaStream_t s) {
     const int noise = (flags & STG_F_THERMAL_INJECT) ? 2 : ((flags & STG_F_THERMAL_PHILOX) ? 1 : 0);
+    if (a.d_current_grid || a.d_field_grid) {      // host-sampled callables: FP64 general stages
+        if (noise == 0) return launch_solve_grid<0>(a, flags, s);
+        if (noise == 1) return launch_solve_grid<1>(a, flags, s);
+        return launch_solve_grid<2>(a, flags, s);
+    }
     if (axis_z) {
         if (noise == 0) return launch_solve2<R, true, 0>(a, flags, s);
         if (noise == 1) return launch_solve2<R, true, 1>(a, flags, s);
@@ -493,6 +514,9 @@ static int stt_solve_impl(const StgSttSolveArgs* args, void* stream) {
     if ((a.flags & STG_F_THERMAL_PHILOX) && (a.flags & STG_F_THERMAL_INJECT)) return STG_E_ENUM;
     if ((a.flags & STG_F_THERMAL_INJECT) && (!a.d_noise || a.noise_stride <= 0)) return STG_E_NULL;
     if (a.d_traj && a.traj_stride <= 0) return STG_E_SIZE;
+    if ((a.d_current_grid || a.d_field_grid) &&
+        (a.grid_stride <= 0 || (a.grid_envs != 1 && a.grid_envs != a.n_envs) || (a.flags & STG_F_VECTORIZED_PLAN)))
+        return STG_E_SIZE;
     if (a.n_envs == 0) return STG_OK;
     return (int)launch_solve<R>(a, a.flags, (a.flags & STG_F_AXIS_Z) != 0, (cudaStream_t)stream);
 }

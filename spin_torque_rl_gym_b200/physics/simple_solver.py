@@ -1,9 +1,10 @@
 """Batched SimpleLLGSSolver / RobustLLGSSolver (reference: physics/simple_solver.py:21-399, utils/robust_solver.py:22-345) on
 the K1 fixed-step kernels (stg_stt_solve_*). Reference signature for one trajectory; `solve_batch` for N trajectories.
 
-Python callables cannot cross into a kernel: `current_func` must be a rectangular pulse — a number, a (J, t_pulse) tuple, or a
-callable that is sampled and verified to be rectangular — and `field_func` must be constant (the env passes exactly that,
-envs/spin_torque_env.py:442-447)."""
+Python callables cannot cross into a kernel: `current_func` is a number, a (J, t_pulse) tuple, or a callable. A callable that
+samples as a rectangular pulse and a `field_func` that is constant run the fast kernels (the env passes exactly that,
+envs/spin_torque_env.py:442-447); anything else is sampled by the host at the stage times the reference evaluates it at
+(`stage_times`) and integrated by the FP64 grid kernel (include/stg.h, StgSttSolveArgs.d_current_grid / d_field_grid)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -38,7 +39,11 @@ class SimpleLLGSSolver:
 
     def solve_batch(self, m_initial, t_end, device_params: Dict[str, Any], current=0.0, t_pulse=None, applied_field=None,
                     thermal_noise: bool = False, temperature: float = 300.0, return_trajectory: bool = False, noise=None,
-                    seed: int = 0, env_offset: int = 0, device_type: str = "stt_mram") -> Dict[str, Any]:
+                    seed: int = 0, env_offset: int = 0, device_type: str = "stt_mram", current_grid=None,
+                    field_grid=None) -> Dict[str, Any]:
+        """Batched fixed-step solve. `current_grid` [n_sub,3] or [N,n_sub,3] and `field_grid` [n_sub,3,3] or [N,n_sub,3,3]
+        carry current_func / field_func sampled at the stage times (t_i, t_i+dt/2, t_i+dt), see `stage_times`; they select
+        the FP64 general-geometry kernel (include/stg.h, StgSttSolveArgs)."""
         torch = _lib.require_cuda()
         dev, f64 = self._device, torch.float64
 
@@ -82,6 +87,21 @@ class SimpleLLGSSolver:
             flags |= _lib.F_THERMAL_INJECT
         elif thermal_noise and temperature > 0:
             flags |= _lib.F_THERMAL_PHILOX
+        for name, g, tail in (("d_current_grid", current_grid, (3,)), ("d_field_grid", field_grid, (3, 3))):
+            if g is None:
+                continue
+            gt = torch.as_tensor(np.asarray(g, dtype=np.float64)) if not isinstance(g, torch.Tensor) else g.to(f64)
+            gt = gt.to(dev)
+            if gt.dim() == 1 + len(tail):
+                gt = gt[None]
+            if tuple(gt.shape[2:]) != tail or gt.shape[0] not in (1, n):
+                raise ValueError(f"{name[2:]} must be [n_sub, {tail}] or [{n}, n_sub, {tail}], got {tuple(gt.shape)}")
+            if a.grid_stride and (gt.shape[1] != a.grid_stride or gt.shape[0] != a.grid_envs):
+                raise ValueError("current_grid and field_grid must cover the same trajectories and substeps")
+            gt = gt.contiguous()
+            keep.append(gt)
+            setattr(a, name, gt.data_ptr())
+            a.grid_stride, a.grid_envs = gt.shape[1], gt.shape[0]
         a.seed, a.env_offset, a.n_envs, a.n_sets, a.flags = seed & 0xFFFFFFFFFFFFFFFF, env_offset, n, 1, flags
         fn = self._lib.stg_stt_solve_f64 if self._dtype == torch.float64 else self._lib.stg_stt_solve_f32
         with torch.cuda.device(dev):
@@ -89,6 +109,17 @@ class SimpleLLGSSolver:
         self._keep = keep
         self.solve_count += n
         return out
+
+    def stage_times(self, t0: float, t1: float) -> np.ndarray:
+        """[n_sub, 3] times the reference evaluates current_func / field_func at: t_i, t_i + dt/2, t_i + dt with
+        dt = min(max_step, T/100), n = max(10, int(T/dt)), dt = T/n, t = linspace(t0, t1, n+1)
+        (physics/simple_solver.py:137-145, 263-295; Euler uses column 0 only)."""
+        dur = t1 - t0
+        dt = min(self.max_step, dur / 100)
+        n = max(10, int(dur / dt))
+        dt = dur / n
+        t = np.linspace(t0, t1, n + 1)[:n]
+        return np.stack([t, t + dt / 2, t + dt], axis=1)
 
     def solve(self, m_initial: np.ndarray, time_span: Tuple[float, float], device_params: Dict[str, Any],
               current_func: Union[Callable[[float], float], float, Tuple[float, float], None] = None,
@@ -106,22 +137,34 @@ class SimpleLLGSSolver:
             return {"t": np.array([t0, t1]), "m": np.array([m, m]), "success": True,
                     "message": "Trivial solution (zero time span)", "solve_time": 0.0, "n_steps": 1}
         dur = t1 - t0
+        times = None
+        jgrid = hgrid = None
         if current_func is None:
             j, tp = 0.0, dur
         elif callable(current_func):
-            j, tp = _pulse_from_callable(lambda t: current_func(t + t0), dur)
+            try:
+                j, tp = _pulse_from_callable(lambda t: current_func(t + t0), dur)
+            except ValueError:      # not a rectangular pulse: sample it where the reference evaluates it
+                times = self.stage_times(t0, t1)
+                jgrid = np.array([[float(current_func(float(x))) for x in row] for row in times])
+                j, tp = 0.0, dur
         elif isinstance(current_func, (tuple, list)):
             j, tp = float(current_func[0]), float(current_func[1])
         else:
             j, tp = float(current_func), dur
         happ = (0.0, 0.0, 0.0)
         if field_func is not None:
-            happ = np.asarray(field_func(t0), dtype=float)
-            if not np.array_equal(happ, np.asarray(field_func(t1), dtype=float)):
-                raise ValueError("field_func must be constant in time for the CUDA solver")
+            times = self.stage_times(t0, t1) if times is None else times
+            hs = np.array([[np.asarray(field_func(float(x)), dtype=float) for x in row] for row in times])
+            if hs.shape[2:] != (3,):
+                raise ValueError("field_func must return a 3-vector")
+            if (hs == hs[0, 0]).all():
+                happ = hs[0, 0]                         # constant on every evaluated time: folded into the table
+            else:
+                hgrid = hs
         r = self.solve_batch(m_initial[None], np.array([dur]), device_params, current=np.array([j]),
                              t_pulse=np.array([min(tp, dur * 4)]), applied_field=happ, thermal_noise=thermal_noise,
-                             temperature=temperature, return_trajectory=True)
+                             temperature=temperature, return_trajectory=True, current_grid=jgrid, field_grid=hgrid)
         n = int(r["n_steps"][0])
         m = r["traj"][0, : n + 1].cpu().numpy()
         self.last_solve_time = time.time() - t_wall

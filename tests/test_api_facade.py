@@ -55,12 +55,60 @@ def test_simple_solver_signature_and_trajectory(cuda_device):
     r = s.solve(m0, (0, T), p, lambda t: J if t <= 1.2e-10 else 0.0)
     traj, n, _ = integrate(m0, J, 1.2e-10, prepare_params(p, False, 300.0), "rk4", return_traj=True, t_end=T)
     assert np.abs(r["m"] - traj).max() < 1e-9
-    with pytest.raises(ValueError):
-        s.solve(m0, (0, T), p, lambda t: J * t)
+    ramp = s.solve(m0, (0, T), p, lambda t: J * t / T)       # not rectangular: sampled at the stage times (grid kernel)
+    assert ramp["success"] and ramp["m"].shape == (n + 1, 3) and np.abs(np.linalg.norm(ramp["m"], axis=1) - 1).max() < 1e-12
+    assert np.abs(ramp["m"][-1] - r["m"][-1]).max() > 1e-3   # and it is not the rectangular-pulse answer
     assert s.solve(m0, (1e-9, 1e-9), p)["message"].startswith("Trivial")
     rb = RobustLLGSSolver(method="rk4", device=cuda_device)
     bad = rb.solve(m0, (0, T), default_device_parameters("sot_mram"), lambda t: J)
     assert bad["success"] is False and bad["is_fallback"] and np.array_equal(bad["m"][0], m0)
+
+
+def test_simple_solver_arbitrary_callables_vs_live_reference(cuda_device):
+    """current_func / field_func that are not a rectangular pulse / a constant are sampled by the host at the
+    reference's stage times (t_i, t_i+dt/2, t_i+dt) and integrated by the FP64 grid kernel. Goldens: the live reference's
+    SimpleLLGSSolver.solve with the same callables (oracle/gen_golden.py gen_next), 1e-6 as north_star asks for FP64."""
+    import os
+    import torch
+    from tests.helpers import GOLDEN
+    from spin_torque_rl_gym_b200.physics import SimpleLLGSSolver
+    from spin_torque_rl_gym_b200.params import default_device_parameters
+    G = np.load(os.path.join(GOLDEN, "next.npz"))
+    p = default_device_parameters("stt_mram")
+    w = 2 * np.pi / 1.7e-10
+    cur_sin = lambda t: 1.0e-6 * np.sin(w * t) + 2.0e-7                                  # noqa: E731
+    cur_steps = lambda t: 9e-7 if t < 0.8e-10 else (-6e-7 if t < 2.1e-10 else 3e-7)     # noqa: E731
+    cur_rect = lambda t: 8e-7 if t <= 1.3e-10 else 0.0                                   # noqa: E731
+    fld_rot = lambda t: 2.0e5 * np.array([np.cos(w * t), np.sin(w * t), 0.3])           # noqa: E731
+    fld_const = lambda t: np.array([1.0e5, -5.0e4, 2.0e4])                               # noqa: E731
+    cases = {
+        "sin_rk4": ("rk4", (0.0, 3.0e-10), cur_sin, None, 300),
+        "sin_constfield_rk4": ("rk4", (0.0, 3.0e-10), cur_sin, fld_const, 300),
+        "rect_rotfield_rk4": ("rk4", (0.0, 3.0e-10), cur_rect, fld_rot, 300),
+        "steps_rotfield_rk4": ("rk4", (0.0, 3.0e-10), cur_steps, fld_rot, 300),
+        "steps_rotfield_euler": ("euler", (0.0, 3.0e-10), cur_steps, fld_rot, 300),
+        "sin_rotfield_offset_rk4": ("rk4", (1.0e-10, 3.5e-10), cur_sin, fld_rot, 249),
+        "sin_short_rk4": ("rk4", (0.0, 4.0e-12), cur_sin, fld_rot, 100),
+    }
+    m0 = G["grid/m0"]
+    for name, (method, span, cf, ff, n) in cases.items():
+        for dtype in (torch.float64, torch.float32):          # both entry points run the FP64 grid stages
+            s = SimpleLLGSSolver(method=method, device=cuda_device, dtype=dtype)
+            r = s.solve(m0, span, p, cf, ff)
+            want = G[f"grid/{name}/m"]
+            assert r["success"] and r["n_steps"] == n and r["m"].shape == want.shape, name
+            assert np.array_equal(r["t"], G[f"grid/{name}/t"]), name
+            assert np.abs(r["m"] - want).max() < 1e-6, (name, np.abs(r["m"] - want).max())
+    # the sampled grids can also be passed for a whole batch: every trajectory shares one grid here
+    s = SimpleLLGSSolver(method="rk4", device=cuda_device)
+    times = s.stage_times(0.0, 3.0e-10)
+    jg = np.array([[cur_sin(x) for x in row] for row in times])
+    hg = np.array([[fld_rot(x) for x in row] for row in times])
+    rb = s.solve_batch(np.tile(m0, (1000, 1)), np.full(1000, 3.0e-10), p, current_grid=jg, field_grid=hg)
+    want = s.solve(m0, (0.0, 3.0e-10), p, cur_sin, fld_rot)["m"][-1]
+    assert np.array_equal(rb["m"].cpu().numpy(), np.tile(want, (1000, 1)))
+    with pytest.raises(ValueError):
+        s.solve_batch(m0[None], np.array([3.0e-10]), p, current_grid=jg[:, :2])
 
 
 def test_sb3_vecenv_protocol_and_rollout_collector(cuda_device):
