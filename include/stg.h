@@ -421,6 +421,15 @@ typedef struct StgEnergyParams {
 int stg_energy_landscape_f64(const StgEnergyParams* p, const double* d_m, const double* d_happ, int32_t happ_rows,
                              double* d_energy, double* d_gradient, int64_t n, void* stream);
 
+/* K5 standalone (the step kernels fuse the same reduction into their epilogue): ADD the statistics of n env-step results to
+ * d_stats [STG_NSTATS] f64 (caller zeroes it once per rollout; reference analogue: EnvironmentMonitor's rolling sums,
+ * utils/monitoring.py:89-116,180-229). Every input is [n] and may be NULL (its statistic then stays untouched, STEPS always
+ * counts n): d_reward f64, d_step_energy f64, d_terminated / d_truncated u8, d_n_sub i32 substeps of the step, d_status i32
+ * (bit0 = guard fired), d_step_count i32 step counter AFTER the step (summed into EPLEN where the episode ended). */
+int stg_stats_reduce_f64(const double* d_reward, const double* d_step_energy, const uint8_t* d_terminated,
+                         const uint8_t* d_truncated, const int32_t* d_n_sub, const int32_t* d_status, const int32_t* d_step_count,
+                         int64_t n, double* d_stats, void* stream);
+
 /* VectorizedMagneticsOperations (utils/vectorized_operations.py:288-393), n rows of 3 doubles, NumPy's operation order:
  *   CROSS           out[n][3] = a x b                              (batch_cross_product :292-303)
  *   DOT             out[n]    = sum(a*b, axis=1)                   (batch_dot_product   :305-316)

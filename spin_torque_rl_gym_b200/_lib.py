@@ -161,6 +161,8 @@ SYMBOLS = {
                                         C.c_uint64, C.c_int64, C.c_void_p]),
     "stg_energy_landscape_f64": (C.c_int, [C.POINTER(StgEnergyParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                            C.c_void_p, C.c_int64, C.c_void_p]),
+    "stg_stats_reduce_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int64, C.c_void_p, C.c_void_p]),
     "stg_vec3_op_f64": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_void_p]),
     "stg_phase_diagram_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p,

@@ -488,3 +488,44 @@ def test_thermal_switching_probability(prec, cuda_device):
         assert 0.2 < p_ref < 0.8                                   # the experiment sits on the steep part of the S-curve
         half = 1.96 * np.sqrt(p_ref * (1 - p_ref) * (1.0 / n_gpu + 1.0 / n_cpu))
         assert abs(p_gpu - p_ref) < half, (observable, p_gpu, p_ref, half)
+
+
+def test_standalone_stats_reduce_matches_fused_epilogue(cuda_device):
+    """K5 standalone (stg_stats_reduce_f64) over stored step results == the statistics the step kernel fuses into its epilogue
+    == plain NumPy sums of the same arrays (SURVEY §8b lists stg_stats_reduce in the boundary)."""
+    torch = _torch()
+    from spin_torque_rl_gym_b200 import _lib
+    from spin_torque_rl_gym_b200.parallel import all_reduce_stats, reduce_step_stats
+    n, steps = 10007, 6                                  # odd size: partial warps and a partial last CTA
+    env = _make(n, "f32", cuda_device, max_steps=4, include_thermal_fluctuations=True, autoreset=False, rng_seed=5,
+                max_current=1.1e-6)
+    env.reset(seed=5)
+    rng = np.random.default_rng(5)
+    keep = {k: [] for k in ("reward", "step_energy", "terminated", "truncated", "n_sub", "status", "step_count")}
+    for _ in range(steps):
+        a = np.stack([rng.uniform(-1.1e-6, 1.1e-6, n), rng.uniform(1e-11, 4e-10, n)], 1).astype(np.float32)
+        _, r, te, tr, info = env.step(torch.from_numpy(a).to(cuda_device))
+        for k, v in (("reward", r), ("terminated", te), ("truncated", tr), ("step_energy", info["step_energy"]),
+                     ("n_sub", info["n_sub"]), ("status", info["status"]), ("step_count", info["step_count"])):
+            keep[k].append(v.clone())
+    stored = {k: torch.stack(v) for k, v in keep.items()}                    # rollout-buffer layout [T, N]
+    fused = env.stats_tensor().cpu().numpy()
+    mine = reduce_step_stats(torch.zeros(_lib.NSTATS, dtype=torch.float64, device=cuda_device), **stored).cpu().numpy()
+    te, tr = stored["terminated"].cpu().numpy(), stored["truncated"].cpu().numpy()
+    want = np.array([n * steps, stored["n_sub"].sum().item(), te.sum(), (~te & tr).sum(),
+                     stored["step_energy"].cpu().numpy().sum(), stored["reward"].double().cpu().numpy().sum(),
+                     (stored["status"].cpu().numpy() & 1).sum(), stored["step_count"].cpu().numpy()[te | tr].sum()], dtype=float)
+    assert want[2] > 0 and want[3] > 0 and want[7] > 0                       # both kinds of episode end occur
+    assert np.allclose(mine, want, rtol=1e-12, atol=0) and np.allclose(fused, want, rtol=1e-12, atol=0)
+    assert np.array_equal(mine[[0, 1, 2, 3, 6, 7]], want[[0, 1, 2, 3, 6, 7]])        # counts are exact
+    # accumulates (does not overwrite); optional inputs leave their statistic untouched
+    acc = torch.zeros(_lib.NSTATS, dtype=torch.float64, device=cuda_device)
+    reduce_step_stats(acc, reward=stored["reward"][:3])
+    reduce_step_stats(acc, reward=stored["reward"][3:])
+    got = acc.cpu().numpy()
+    assert got[0] == n * steps and got[5] == pytest.approx(want[5], rel=1e-12) and not got[[1, 2, 3, 4, 6, 7]].any()
+    assert all_reduce_stats(torch.from_numpy(mine))["success_rate"] == pytest.approx(want[2] / (want[2] + want[3]))
+    with pytest.raises(ValueError):
+        reduce_step_stats(acc, reward=stored["reward"], n_sub=stored["n_sub"][:2])
+    with pytest.raises(ValueError):
+        reduce_step_stats(torch.zeros(_lib.NSTATS, dtype=torch.float64), reward=stored["reward"])      # CPU vector
