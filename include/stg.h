@@ -51,6 +51,8 @@ extern "C" {
 #define STG_F_AXIS_Z 0x20u           /* caller asserts stg_stt_all_axis_z(): kernels drop structurally-zero terms   */
 #define STG_F_NO_PAIR 0x80u          /* stg_stt_step_f32: one env per thread instead of the packed two-envs-per-thread FFMA2
                                         kernel (identical results; for comparisons)                                 */
+#define STG_F_ARRAY_ONE_WARP 0x100u  /* stg_array_step_f64: force the one-warp-per-array kernel (the default for 8 <= devices <= 128
+                                      * is four arrays per warp, eight lanes each; both are bit-identical) */
 #define STG_F_VECTORIZED_PLAN 0x40u  /* stg_stt_solve_*: n = max(10, int(t_end/max_step)) — VectorizedSolver.solve_batch's step
                                         policy (utils/vectorized_operations.py:55-57) instead of SimpleLLGSSolver's        */
 

@@ -19,6 +19,7 @@ F_SORTED = 0x10
 F_AXIS_Z = 0x20
 F_VECTORIZED_PLAN = 0x40
 F_NO_PAIR = 0x80
+F_ARRAY_ONE_WARP = 0x100
 DEV_STT, DEV_SOT, DEV_VCMA = 0, 1, 2
 NSTATS = 8
 STAT_NAMES = ("steps", "substeps", "terminated", "truncated", "energy", "reward", "guard", "episode_length")

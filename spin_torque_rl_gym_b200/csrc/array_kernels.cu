@@ -1,6 +1,7 @@
-// array_kernels.cu — K3 launch + C-ABI: one CTA per crossbar array. The pattern and the target live in shared memory for
-// the whole step (coalesced FP64 loads, coalesced f32 observation stores); the sequential Gauss-Seidel device update is
-// executed by one thread (its order is part of the reference's semantics), the reductions by NumPy-ordered sums.
+// array_kernels.cu — K3 launch + C-ABI. The pattern and the target live in shared memory for the whole step (coalesced FP64
+// loads, coalesced f32 observation stores); the Gauss-Seidel device update is sequential in device order (part of the
+// reference's semantics) and the reductions are NumPy-ordered sums. Default kernel for 8..128 devices: four arrays per
+// warp, eight lanes per array (array_step_kernel8); other sizes / STG_F_ARRAY_ONE_WARP: one warp per array.
 // HBM-bound: ~ (24+24) B read + (24+24) B written per device and step.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -120,6 +121,277 @@ __global__ void __launch_bounds__(kArrayBlock, kArrayMinBlocks) array_step_kerne
     array_store_obs(a.d_obs + arr * nd * 6, pattern, target, nd);
 }
 
+// ---- four arrays per warp, eight lanes per array ----------------------------------------------------------------------------
+// The one-warp kernel above executes ~4,800 warp-instructions per 8x8 array with 6 of 32 lanes active on average (ncu,
+// profiles/): every NumPy-ordered sum and the device update run on lane 0. Here a group of 8 lanes owns one array:
+//   * lane k IS accumulator r[k] of NumPy's pairwise sum (same additions in the same order); the final
+//     ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is an xor-shuffle tree (IEEE addition commutes, so every lane holds the same bits);
+//   * lanes 0..2 carry the x, y, z components through the sequential coupling sum and the ten renormalised Euler substeps
+//     (one software sqrt and one division per substep instead of one sqrt and three divisions in a single lane);
+//   * loads and stores use the whole warp over the four arrays, which are contiguous in HBM.
+// All results are bit-identical to the one-warp kernel and to the host sequence in array_core.cuh.
+constexpr int kGroupLanes = 8;
+constexpr int kGroupsPerWarp = 4;
+constexpr int kArray8MinBlocks = 12;
+
+template <typename F>
+__device__ __forceinline__ double group_numpy_sum(unsigned gmask, int l8, int n, F v) {      // 8 <= n <= 128
+    const int nfull = n - (n % 8);
+    double r = v(l8);
+    for (int i = 8; i < nfull; i += 8) r = dadd(r, v(i + l8));
+    r = dadd(r, __shfl_xor_sync(gmask, r, 1));
+    r = dadd(r, __shfl_xor_sync(gmask, r, 2));
+    r = dadd(r, __shfl_xor_sync(gmask, r, 4));
+    for (int i = nfull; i < n; ++i) r = dadd(r, v(i));
+    return r;
+}
+
+__device__ __forceinline__ double group_apply_action(const StgArrayParams& p, const double* coupling, double* pattern,
+                                                     double* rowbuf, const ArrayAction& a, unsigned gmask, int l8) {
+    const int nd = p.n_rows * p.n_cols;
+    const int c = l8 < 3 ? l8 : 0;                 // lanes 3..7 shadow component 0 so the group never diverges
+    const bool drive = fabs(a.cur) > 1e-12;
+    double energy = 0.0;
+    for (int q = 0; q < a.count; ++q) {
+        const int i = a.first + q * a.stride;
+        double* m = pattern + 3 * i;
+        double h[3];
+        array_intrinsic_field(p, m, h);
+        if (coupling) {
+            const double* row = coupling + (int64_t)i * nd;
+            for (int j = l8; j < nd; j += kGroupLanes) rowbuf[j] = row[j];
+            __syncwarp(gmask);
+            double hcv = 0.0;
+            for (int j = 0; j < nd; ++j) {
+                if (j == i) continue;
+                hcv = dadd(hcv, dmul(rowbuf[j], pattern[3 * j + c]));
+            }
+            h[0] = dadd(h[0], __shfl_sync(gmask, hcv, 0, kGroupLanes));
+            h[1] = dadd(h[1], __shfl_sync(gmask, hcv, 1, kGroupLanes));
+            h[2] = dadd(h[2], __shfl_sync(gmask, hcv, 2, kGroupLanes));
+        } else {
+            for (int k = 0; k < 3; ++k) h[k] = dadd(h[k], 0.0);
+        }
+        if (drive) {      // _simulate_device_dynamics (envs/array_env.py:497-531), see array_device_dynamics
+            const double m0[3] = {m[0], m[1], m[2]};
+            const double z[3] = {0.0, 0.0, 1.0};
+            double mp[3], mmp[3], dm[3], mdm[3];
+            cross_u(m0, z, mp);
+            cross_u(m0, mp, mmp);
+            const double pre = dmul(0.1, a.cur);
+            cross_u(m0, h, dm);
+            for (int k = 0; k < 3; ++k) dm[k] = dmul(-2.21e5, dm[k]);
+            cross_u(m0, dm, mdm);
+            // component of this lane by selects (a runtime index would push the vectors to local memory)
+            auto pick = [c](const double* v) { return c == 0 ? v[0] : (c == 1 ? v[1] : v[2]); };
+            const double dc = dadd(dadd(pick(dm), dmul(0.01, pick(mdm))), dmul(pre, pick(mmp)));
+            const double dt = ddiv(a.dur, 10.0);
+            double mc = pick(m0);
+            for (int s = 0; s < 10; ++s) {
+                mc = dadd(mc, dmul(dc, dt));
+                const double sq = dmul(mc, mc);
+                const double n = sqrt(dadd(dadd(__shfl_sync(gmask, sq, 0, kGroupLanes), __shfl_sync(gmask, sq, 1, kGroupLanes)),
+                                           __shfl_sync(gmask, sq, 2, kGroupLanes)));
+                mc = ddiv(mc, n);
+            }
+            __syncwarp(gmask);
+            if (l8 < 3) m[l8] = mc;
+            __syncwarp(gmask);
+            const double r = array_resistance(p, m);          // resistance of the UPDATED magnetisation (:447-461)
+            const double v = dmul(dmul(a.cur, r), p.area);
+            energy = dadd(energy, dmul(ddiv(dmul(v, v), r), a.dur));
+        }
+        __syncwarp(gmask);
+    }
+    return energy;
+}
+
+__device__ __forceinline__ void group_draw_pattern(const StgArrayStepArgs& a, int64_t arr, uint32_t episode, int nd,
+                                                   double* pattern, int l8) {
+    Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+    const uint64_t gid = a.array_offset + (uint64_t)arr;
+    for (int i = l8; i < nd; i += kGroupLanes) {
+        uint32_t o[4];
+        float z0, z1, z2, z3;
+        uint32_t attempt = 0;
+        do {
+            ph((uint32_t)gid, (uint32_t)(gid >> 32), episode, ((uint32_t)i << 4) + attempt, o);
+            box_muller(o[0], o[1], z0, z1);
+            box_muller(o[2], o[3], z2, z3);
+            ++attempt;
+        } while (z0 * z0 + z1 * z1 + z2 * z2 < 1e-12f && attempt < 8);
+        const double n = sqrt((double)z0 * z0 + (double)z1 * z1 + (double)z2 * z2);
+        pattern[3 * i] = z0 / n; pattern[3 * i + 1] = z1 / n; pattern[3 * i + 2] = z2 / n;
+    }
+}
+
+// two f32 packed into the bit pattern of one f64 slot: observations are built IN PLACE over the target rows (a device's six
+// f32 outputs overlay exactly its own three f64 target values), written through the same double-typed array
+__device__ __forceinline__ double pack2f(float lo, float hi) { return __hiloint2double(__float_as_int(hi), __float_as_int(lo)); }
+
+// ND_T: devices per array at compile time (0 = runtime), lets the copy loops unroll so every load is in flight before the
+// first use. VEC: 16-byte global/shared accesses (even device count, 16-byte aligned buffers; checked at launch).
+template <int ND_T, bool VEC>
+__global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const __grid_constant__ StgArrayStepArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const StgArrayParams& p = a.params;
+    const int nd = ND_T ? ND_T : p.n_rows * p.n_cols;
+    const int per = 8 * nd;                          // doubles per array: pattern 3nd, target 3nd, scratch nd, coupling row nd
+    const int lane = threadIdx.x, g = lane >> 3, l8 = lane & 7;
+    const unsigned gmask = 0xFFu << (8 * g);
+    const int64_t arr0 = (int64_t)blockIdx.x * kGroupsPerWarp;
+    const int64_t left = a.n_arrays - arr0;
+    const int narr = left < kGroupsPerWarp ? (int)left : kGroupsPerWarp;
+    const bool valid = g < narr;
+    const int64_t arr = arr0 + g;
+    // per-array scalars first: their latency hides behind the bulk load
+    float act_raw[3] = {0.0f, 0.0f, 0.0f};
+    int step_prev = 0;
+    double tot_prev = 0.0;
+    if (valid) {
+        const float* ga = a.d_action + arr * a.action_stride;
+        act_raw[0] = ga[0]; act_raw[1] = ga[1];
+        if (p.action_mode != STG_ARRAY_GLOBAL) act_raw[2] = ga[2];
+        step_prev = a.d_step_count[arr];
+        tot_prev = a.d_total_energy[arr];
+    }
+    double* gp0 = a.d_pattern + arr0 * nd * 3;
+    const double* gt0 = a.d_target + arr0 * nd * 3;
+    if (VEC) {
+        const int n2 = 3 * nd / 2;                   // 16-byte words per array and tensor
+        const double2* gp2 = reinterpret_cast<const double2*>(gp0);
+        const double2* gt2 = reinterpret_cast<const double2*>(gt0);
+#pragma unroll
+        for (int ar = 0; ar < kGroupsPerWarp; ++ar) {
+            if (ar < narr) {
+                double2* sp = reinterpret_cast<double2*>(smem + ar * per);
+                double2* st = reinterpret_cast<double2*>(smem + ar * per + 3 * nd);
+#pragma unroll
+                for (int q = lane; q < n2; q += 32) { sp[q] = gp2[ar * n2 + q]; st[q] = gt2[ar * n2 + q]; }
+            }
+        }
+    } else {
+        for (int ar = 0; ar < narr; ++ar)
+            for (int q = lane; q < 3 * nd; q += 32) {
+                smem[ar * per + q] = gp0[ar * 3 * nd + q];
+                smem[ar * per + 3 * nd + q] = gt0[ar * 3 * nd + q];
+            }
+    }
+    __syncwarp();
+    double* pattern = smem + g * per;
+    double* target = pattern + 3 * nd;
+    double* scratch = target + 3 * nd;
+    double* rowbuf = scratch + nd;
+    bool reset = false;
+    double st_v[STG_NSTATS];
+#pragma unroll
+    for (int q = 0; q < STG_NSTATS; ++q) st_v[q] = 0.0;
+    if (valid) {
+        const double fnd = (double)nd;
+        auto dots = [&](int i) { return dot_u(pattern + 3 * i, target + 3 * i); };
+        const double prev = ddiv(group_numpy_sum(gmask, l8, nd, dots), fnd);
+        const ArrayAction act = array_parse_action(p, act_raw);
+        const double energy = group_apply_action(p, a.d_coupling, pattern, rowbuf, act, gmask, l8);
+        const double sim = ddiv(group_numpy_sum(gmask, l8, nd, dots), fnd);
+        for (int i = l8; i < nd; i += kGroupLanes) scratch[i] = norm_u(pattern + 3 * i);
+        __syncwarp(gmask);
+        const double mean = ddiv(group_numpy_sum(gmask, l8, nd, [&](int i) { return scratch[i]; }), fnd);
+        const double var = group_numpy_sum(gmask, l8, nd, [&](int i) { const double d = dadd(scratch[i], -mean); return dmul(d, d); });
+        const double sd = sqrt(ddiv(var, fnd));
+        const bool success = sim >= p.success_threshold;
+        const double reward = array_reward(p, success, sim, energy, dadd(sim, -prev), sd);
+        const int step = step_prev + 1;
+        const bool trunc = step >= p.max_steps;
+        reset = (a.flags & STG_F_AUTORESET) && (success || trunc);
+        if (l8 == 0) {
+            a.d_reward[arr] = reward;
+            a.d_terminated[arr] = success ? 1 : 0;
+            a.d_truncated[arr] = trunc ? 1 : 0;
+            if (a.d_step_energy) a.d_step_energy[arr] = energy;
+            if (a.d_similarity) a.d_similarity[arr] = sim;
+            a.d_step_count[arr] = reset ? 0 : step;
+            a.d_total_energy[arr] = reset ? 0.0 : dadd(tot_prev, energy);
+            st_v[STG_STAT_STEPS] = 1.0;
+            st_v[STG_STAT_SUBSTEPS] = 10.0 * act.count;
+            st_v[STG_STAT_TERMINATED] = success ? 1.0 : 0.0;
+            st_v[STG_STAT_TRUNCATED] = (!success && trunc) ? 1.0 : 0.0;
+            st_v[STG_STAT_ENERGY] = energy;
+            st_v[STG_STAT_REWARD] = reward;
+            st_v[STG_STAT_EPLEN] = (success || trunc) ? (double)step : 0.0;
+        }
+        // observation rows [p_x p_y p_z t_x t_y t_z] as f32, in place over the target rows
+        for (int d = l8; d < nd; d += kGroupLanes) {
+            const double t0 = target[3 * d], t1 = target[3 * d + 1], t2 = target[3 * d + 2];
+            target[3 * d] = pack2f((float)pattern[3 * d], (float)pattern[3 * d + 1]);
+            target[3 * d + 1] = pack2f((float)pattern[3 * d + 2], (float)t0);
+            target[3 * d + 2] = pack2f((float)t1, (float)t2);
+        }
+        __syncwarp(gmask);
+        if (reset) {
+            if (a.d_final_obs) {       // pre-reset observation
+                double* fo = reinterpret_cast<double*>(a.d_final_obs + arr * nd * 6);
+                for (int q = l8; q < 3 * nd; q += kGroupLanes) fo[q] = target[q];
+            }
+            const uint32_t ep = (uint32_t)a.d_episode[arr] + 1u;
+            __syncwarp(gmask);
+            if (l8 == 0) a.d_episode[arr] = (int32_t)ep;
+            group_draw_pattern(a, arr, ep, nd, pattern, l8);
+            for (int d = l8; d < nd; d += kGroupLanes) {      // refresh the pattern half of the rows, keep the f32 target half
+                const float t0 = __int_as_float(__double2hiint(target[3 * d + 1]));
+                target[3 * d] = pack2f((float)pattern[3 * d], (float)pattern[3 * d + 1]);
+                target[3 * d + 1] = pack2f((float)pattern[3 * d + 2], t0);
+            }
+        }
+    }
+    // statistics: the four group leaders are reduced in the warp, one atomic per statistic and warp (K5 input)
+    if (a.d_stats) {
+#pragma unroll
+        for (int q = 0; q < STG_NSTATS; ++q) {
+            double v = st_v[q];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane == 0 && v != 0.0) atomicAdd(a.d_stats + q, v);
+        }
+    }
+    const unsigned reset_bits = __ballot_sync(0xffffffffu, reset && l8 == 0);      // bit 8*ar: array ar of this warp was reset
+    __syncwarp();
+    // the four arrays are contiguous in HBM: whole-warp coalesced stores of patterns, observations, final-observation zeros
+    const bool zero_final = (a.flags & STG_F_AUTORESET) && a.d_final_obs;
+    if (VEC) {
+        const int n2 = 3 * nd / 2;
+        double2* gp2 = reinterpret_cast<double2*>(gp0);
+        double2* go2 = reinterpret_cast<double2*>(a.d_obs + arr0 * nd * 6);
+        double2* gf2 = zero_final ? reinterpret_cast<double2*>(a.d_final_obs + arr0 * nd * 6) : nullptr;
+#pragma unroll
+        for (int ar = 0; ar < kGroupsPerWarp; ++ar) {
+            if (ar < narr) {
+                const double2* sp = reinterpret_cast<const double2*>(smem + ar * per);
+                const double2* so = reinterpret_cast<const double2*>(smem + ar * per + 3 * nd);
+                const bool zf = zero_final && !((reset_bits >> (8 * ar)) & 1u);
+#pragma unroll
+                for (int q = lane; q < n2; q += 32) {
+                    gp2[ar * n2 + q] = sp[q];
+                    go2[ar * n2 + q] = so[q];
+                    if (zf) gf2[ar * n2 + q] = make_double2(0.0, 0.0);
+                }
+            }
+        }
+    } else {
+        for (int ar = 0; ar < narr; ++ar) {
+            const double* pat = smem + ar * per;
+            const double* so = pat + 3 * nd;
+            double* go = reinterpret_cast<double*>(a.d_obs + (arr0 + ar) * nd * 6);      // 6 f32 = 3 f64 slots per device
+            const bool zf = zero_final && !((reset_bits >> (8 * ar)) & 1u);
+            double* gf = zf ? reinterpret_cast<double*>(a.d_final_obs + (arr0 + ar) * nd * 6) : nullptr;
+            for (int q = lane; q < 3 * nd; q += 32) {
+                gp0[ar * 3 * nd + q] = pat[q];
+                go[q] = so[q];
+                if (zf) gf[q] = 0.0;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kArrayBlock) array_reset_kernel(const __grid_constant__ StgArrayStepArgs a,
                                                                    const uint8_t* mask, const double* pattern0) {
     extern __shared__ double smem[];
@@ -171,6 +443,27 @@ extern "C" int stg_array_step_f64(const StgArrayStepArgs* args, void* stream) {
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(stg::array_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
+    }
+    // four arrays per warp, eight lanes each. The observation rows are written as 8-byte words (6 f32 per device = 3 words),
+    // so d_obs / d_final_obs must be 8-byte aligned for this kernel; anything else takes the one-warp kernel.
+    const auto aligned = [](const void* q, uintptr_t n) { return (reinterpret_cast<uintptr_t>(q) & (n - 1)) == 0; };
+    if (nd >= 8 && nd <= 128 && !(a.flags & STG_F_ARRAY_ONE_WARP) && aligned(a.d_obs, 8) &&
+        (!a.d_final_obs || aligned(a.d_final_obs, 8))) {
+        const size_t smem8 = sizeof(double) * 8 * (size_t)nd * stg::kGroupsPerWarp;               // <= 32 KB
+        const unsigned grid = (unsigned)((a.n_arrays + stg::kGroupsPerWarp - 1) / stg::kGroupsPerWarp);
+        const bool vec = nd % 2 == 0 && aligned(a.d_pattern, 16) && aligned(a.d_target, 16) && aligned(a.d_obs, 16) &&
+                         (!a.d_final_obs || aligned(a.d_final_obs, 16));
+        static bool carveout_set = false;
+        if (!carveout_set) {       // shared-memory-heavy split so >= 12 CTAs x 16 KB are resident per SM
+            cudaFuncSetAttribute(stg::array_step_kernel8<64, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(stg::array_step_kernel8<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(stg::array_step_kernel8<0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            carveout_set = true;
+        }
+        if (vec && nd == 64) stg::array_step_kernel8<64, true><<<grid, 32, smem8, (cudaStream_t)stream>>>(a);
+        else if (vec) stg::array_step_kernel8<0, true><<<grid, 32, smem8, (cudaStream_t)stream>>>(a);
+        else stg::array_step_kernel8<0, false><<<grid, 32, smem8, (cudaStream_t)stream>>>(a);
+        return (int)cudaGetLastError();
     }
     stg::array_step_kernel<<<(unsigned)a.n_arrays, stg::kArrayBlock, smem, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();

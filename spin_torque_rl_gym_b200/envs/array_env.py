@@ -56,8 +56,9 @@ class SpinTorqueArrayVectorEnv:
                  action_mode: str = "individual", observation_mode: str = "array", success_threshold: float = 0.9,
                  energy_penalty_weight: float = 0.1, render_mode: Optional[str] = None, seed: Optional[int] = None, *,
                  device: Union[str, Any] = "cuda", rng_seed: Optional[int] = None, array_offset: int = 0,
-                 autoreset: bool = True, collect_stats: bool = True):
+                 autoreset: bool = True, collect_stats: bool = True, one_warp_kernel: bool = False):
         torch = _lib.require_cuda()
+        self.one_warp_kernel = bool(one_warp_kernel)      # STG_F_ARRAY_ONE_WARP: A/B against the four-arrays-per-warp kernel
         self._torch = torch
         self._lib = _lib.load()
         if action_mode not in _lib.ARRAY_MODES:
@@ -173,7 +174,7 @@ class SpinTorqueArrayVectorEnv:
         a.d_stats = self._stats.data_ptr() if self.collect_stats else None
         a.seed, a.array_offset, a.n_arrays = self.rng_seed, self.array_offset, self.num_envs
         a.action_stride = self._adim
-        a.flags = _lib.F_AUTORESET if self.autoreset else 0
+        a.flags = (_lib.F_AUTORESET if self.autoreset else 0) | (_lib.F_ARRAY_ONE_WARP if self.one_warp_kernel else 0)
         return a
 
     def _stream(self):

@@ -148,3 +148,40 @@ def test_cuda_array_env_batch_vs_oracle_and_full_size(cuda_device):
     st = big.episode_stats()
     assert st["steps"] == 4 * N and st["terminated"] + st["truncated"] == ended and ended >= N
     assert torch.all(info["step_count"] == 0)            # max_steps=4 truncated every array in the last step
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["individual", "row", "column", "global"])
+def test_cuda_array_kernels_bit_identical(mode, cuda_device):
+    """The default kernel (four arrays per warp, eight lanes each: NumPy's pairwise accumulators live in the lanes) and the
+    one-warp-per-array kernel produce the same bits: state, observation, reward, energy, similarity, flags, statistics.
+    Grids cover a multiple of 8 (8x8), remainders (3x3 = 8+1, 4x5 = 16+4, 10x12 = 120), both fall-back sizes (2x3 < 8,
+    12x12 > 128) and batches that are not a multiple of 4; auto-reset on, so reset draws are compared too."""
+    import torch
+    from spin_torque_rl_gym_b200 import SpinTorqueArrayVectorEnv
+    for size, n in (((8, 8), 1003), ((3, 3), 257), ((4, 5), 130), ((10, 12), 66), ((2, 3), 33), ((12, 12), 9)):
+        rng = np.random.default_rng(100 * ["individual", "row", "column", "global"].index(mode) + 10 * size[0] + size[1])
+        envs = [SpinTorqueArrayVectorEnv(num_envs=n, array_size=size, action_mode=mode, device=cuda_device, max_steps=3,
+                                         rng_seed=7, autoreset=True, one_warp_kernel=flag) for flag in (False, True)]
+        for e in envs:
+            e.reset(seed=7)
+        assert torch.equal(envs[0].current_pattern, envs[1].current_pattern)
+        nd = size[0] * size[1]
+        for s in range(5):
+            if mode == "global":
+                act = np.stack([rng.uniform(-2e6, 2e6, n), rng.uniform(0, 5e-9, n)], 1)
+            else:
+                hi = {"individual": nd, "row": size[0], "column": size[1]}[mode]
+                act = np.stack([rng.uniform(-0.5, hi + 0.5, n), rng.uniform(-2e6, 2e6, n), rng.uniform(0, 5e-9, n)], 1)
+            act[::7, -2 if mode != "global" else 1] = 0.0              # |J| <= 1e-12: device untouched, no energy
+            act = act.astype(np.float32)
+            outs = [e.step(act.copy()) for e in envs]
+            (o0, r0, te0, tr0, i0), (o1, r1, te1, tr1, i1) = outs
+            assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(te0, te1) and torch.equal(tr0, tr1), (size, s)
+            assert torch.equal(envs[0].current_pattern, envs[1].current_pattern), (size, s)
+            for k in ("step_energy", "pattern_similarity", "step_count", "final_observation"):
+                assert torch.equal(i0[k], i1[k]), (size, s, k)
+        s0, s1 = envs[0].episode_stats(), envs[1].episode_stats()
+        for k in ("steps", "substeps", "terminated", "truncated", "episode_length"):
+            assert s0[k] == s1[k], (size, k)
+        assert s0["energy"] == pytest.approx(s1["energy"], rel=1e-12) and s0["truncated"] > 0
