@@ -223,6 +223,26 @@ def require_cuda():
     return torch
 
 
+class _NullGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_GUARD = _NullGuard()
+
+
+def device_guard(torch, device):
+    """`torch.cuda.device(device)` only when it is not already the current device (the context switch costs several
+    microseconds per call, which is visible in small-batch env steps)."""
+    idx = device.index
+    if idx is None or torch.cuda.current_device() == idx:
+        return _NULL_GUARD
+    return torch.cuda.device(device)
+
+
 def ptr(t) -> Optional[int]:
     """Device pointer of a torch tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kArrayBlock, kArrayMinBlocks) array_step_kerne
 // All results are bit-identical to the one-warp kernel and to the host sequence in array_core.cuh.
 constexpr int kGroupLanes = 8;
 constexpr int kGroupsPerWarp = 4;
-constexpr int kArray8MinBlocks = 12;
+constexpr int kArray8MinBlocks = 15;     // 14.3 KB of shared memory per CTA at 8x8: 15 CTAs resident, 4096 CTAs < 2 waves
 
 template <typename F>
 __device__ __forceinline__ double group_numpy_sum(unsigned gmask, int l8, int n, F v) {      // 8 <= n <= 128
@@ -146,25 +146,45 @@ __device__ __forceinline__ double group_numpy_sum(unsigned gmask, int l8, int n,
     return r;
 }
 
+// Sequential in-place update of the affected devices by one 8-lane group (array_apply_action in array_core.cuh is the
+// one-thread form). The coupling row of device q+1 is fetched into registers while device q is integrated, so the
+// L2 latency of the row never sits on the dependent chain; rowbuf is the group's scratch region (free until the norms).
+template <int ND_T>
 __device__ __forceinline__ double group_apply_action(const StgArrayParams& p, const double* coupling, double* pattern,
                                                      double* rowbuf, const ArrayAction& a, unsigned gmask, int l8) {
-    const int nd = p.n_rows * p.n_cols;
+    constexpr int RN = ND_T ? ND_T / kGroupLanes : 16;          // row values per lane (nd <= 128)
+    const int nd = ND_T ? ND_T : p.n_rows * p.n_cols;
     const int c = l8 < 3 ? l8 : 0;                 // lanes 3..7 shadow component 0 so the group never diverges
     const bool drive = fabs(a.cur) > 1e-12;
     double energy = 0.0;
+    double rn[RN];
+    auto fetch_row = [&](int i) {
+        const double* row = coupling + (int64_t)i * nd;
+#pragma unroll
+        for (int k = 0; k < RN; ++k) {
+            const int j = l8 + kGroupLanes * k;
+            rn[k] = (ND_T || j < nd) ? row[j] : 0.0;
+        }
+    };
+    if (coupling && a.count > 0) fetch_row(a.first);
     for (int q = 0; q < a.count; ++q) {
         const int i = a.first + q * a.stride;
         double* m = pattern + 3 * i;
         double h[3];
         array_intrinsic_field(p, m, h);
         if (coupling) {
-            const double* row = coupling + (int64_t)i * nd;
-            for (int j = l8; j < nd; j += kGroupLanes) rowbuf[j] = row[j];
+#pragma unroll
+            for (int k = 0; k < RN; ++k) {
+                const int j = l8 + kGroupLanes * k;
+                if (ND_T || j < nd) rowbuf[j] = rn[k];
+            }
             __syncwarp(gmask);
+            if (q + 1 < a.count) fetch_row(i + a.stride);       // in flight during this device's update
             double hcv = 0.0;
+#pragma unroll 8
             for (int j = 0; j < nd; ++j) {
-                if (j == i) continue;
-                hcv = dadd(hcv, dmul(rowbuf[j], pattern[3 * j + c]));
+                const double t = dmul(rowbuf[j], pattern[3 * j + c]);
+                hcv = (j == i) ? hcv : dadd(hcv, t);
             }
             h[0] = dadd(h[0], __shfl_sync(gmask, hcv, 0, kGroupLanes));
             h[1] = dadd(h[1], __shfl_sync(gmask, hcv, 1, kGroupLanes));
@@ -236,7 +256,7 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
     extern __shared__ __align__(16) double smem[];
     const StgArrayParams& p = a.params;
     const int nd = ND_T ? ND_T : p.n_rows * p.n_cols;
-    const int per = 8 * nd;                          // doubles per array: pattern 3nd, target 3nd, scratch nd, coupling row nd
+    const int per = 7 * nd + (nd & 1);               // doubles per array: pattern 3nd, target 3nd, scratch / coupling row nd
     const int lane = threadIdx.x, g = lane >> 3, l8 = lane & 7;
     const unsigned gmask = 0xFFu << (8 * g);
     const int64_t arr0 = (int64_t)blockIdx.x * kGroupsPerWarp;
@@ -280,8 +300,7 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
     __syncwarp();
     double* pattern = smem + g * per;
     double* target = pattern + 3 * nd;
-    double* scratch = target + 3 * nd;
-    double* rowbuf = scratch + nd;
+    double* scratch = target + 3 * nd;              // coupling row during the device update, per-device norms afterwards
     bool reset = false;
     double st_v[STG_NSTATS];
 #pragma unroll
@@ -291,7 +310,7 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
         auto dots = [&](int i) { return dot_u(pattern + 3 * i, target + 3 * i); };
         const double prev = ddiv(group_numpy_sum(gmask, l8, nd, dots), fnd);
         const ArrayAction act = array_parse_action(p, act_raw);
-        const double energy = group_apply_action(p, a.d_coupling, pattern, rowbuf, act, gmask, l8);
+        const double energy = group_apply_action<ND_T>(p, a.d_coupling, pattern, scratch, act, gmask, l8);
         const double sim = ddiv(group_numpy_sum(gmask, l8, nd, dots), fnd);
         for (int i = l8; i < nd; i += kGroupLanes) scratch[i] = norm_u(pattern + 3 * i);
         __syncwarp(gmask);
@@ -449,7 +468,7 @@ extern "C" int stg_array_step_f64(const StgArrayStepArgs* args, void* stream) {
     const auto aligned = [](const void* q, uintptr_t n) { return (reinterpret_cast<uintptr_t>(q) & (n - 1)) == 0; };
     if (nd >= 8 && nd <= 128 && !(a.flags & STG_F_ARRAY_ONE_WARP) && aligned(a.d_obs, 8) &&
         (!a.d_final_obs || aligned(a.d_final_obs, 8))) {
-        const size_t smem8 = sizeof(double) * 8 * (size_t)nd * stg::kGroupsPerWarp;               // <= 32 KB
+        const size_t smem8 = sizeof(double) * (7 * (size_t)nd + (nd & 1)) * stg::kGroupsPerWarp;   // <= 28 KB
         const unsigned grid = (unsigned)((a.n_arrays + stg::kGroupsPerWarp - 1) / stg::kGroupsPerWarp);
         const bool vec = nd % 2 == 0 && aligned(a.d_pattern, 16) && aligned(a.d_target, 16) && aligned(a.d_obs, 16) &&
                          (!a.d_final_obs || aligned(a.d_final_obs, 16));

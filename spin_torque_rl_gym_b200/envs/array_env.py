@@ -59,6 +59,7 @@ class SpinTorqueArrayVectorEnv:
                  autoreset: bool = True, collect_stats: bool = True, one_warp_kernel: bool = False):
         torch = _lib.require_cuda()
         self.one_warp_kernel = bool(one_warp_kernel)      # STG_F_ARRAY_ONE_WARP: A/B against the four-arrays-per-warp kernel
+        self._args_cache = None
         self._torch = torch
         self._lib = _lib.load()
         if action_mode not in _lib.ARRAY_MODES:
@@ -87,6 +88,8 @@ class SpinTorqueArrayVectorEnv:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.StgError("SpinTorqueArrayVectorEnv requires a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         if device_params is None:
             device_params = _params.default_device_parameters("stt_mram")     # envs/array_env.py:155-171
         _params.check_device_constructible(device_type, device_params)
@@ -161,6 +164,12 @@ class SpinTorqueArrayVectorEnv:
         self.observation_space = batch_box(self.single_observation_space, N)
 
     def _args(self) -> _lib.StgArrayStepArgs:
+        """Argument block of both entry points. Every buffer is allocated once in the constructor, so the block is built
+        once and only the fields that can change between calls (seed, flags, action pointer) are rewritten."""
+        a = self._args_cache
+        if a is not None:
+            a.seed = self.rng_seed
+            return a
         a = _lib.StgArrayStepArgs()
         a.params = self._params_struct
         a.d_coupling = _lib.ptr(self._coupling)
@@ -175,6 +184,10 @@ class SpinTorqueArrayVectorEnv:
         a.seed, a.array_offset, a.n_arrays = self.rng_seed, self.array_offset, self.num_envs
         a.action_stride = self._adim
         a.flags = (_lib.F_AUTORESET if self.autoreset else 0) | (_lib.F_ARRAY_ONE_WARP if self.one_warp_kernel else 0)
+        self._args_cache = a
+        # zero-copy bool views of the u8 flag buffers (a .bool() per step is an extra kernel launch each)
+        self._terminated_b = self._terminated.view(self._torch.bool)
+        self._truncated_b = self._truncated.view(self._torch.bool)
         return a
 
     def _stream(self):
@@ -222,14 +235,14 @@ class SpinTorqueArrayVectorEnv:
             act = self._action_dev
         a = self._args()
         a.d_action = act.data_ptr()
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(torch, self.device):
             _lib.check(self._lib.stg_array_step_f64(C.byref(a), self._stream()), "stg_array_step_f64")
         self.gpu_launches += 1
         info = {"step_energy": self._step_energy, "pattern_similarity": self._similarity,
                 "total_energy": self._total_energy, "step_count": self._step_count}
         if self.autoreset:
             info["final_observation"] = self._final_obs
-        return self._obs, self._reward, self._terminated.bool(), self._truncated.bool(), info
+        return self._obs, self._reward, self._terminated_b, self._truncated_b, info
 
     @property
     def current_pattern(self):

@@ -73,6 +73,7 @@ class SpinTorqueVectorEnv:
                              "the default CompositeReward (envs/spin_torque_env.py:184-207) is fused")
         if integrator not in ("rk4", "euler"):
             raise ValueError(f"unknown integrator {integrator!r}")
+        self._step_args_cache = None
         self.num_envs = int(num_envs)
         if self.num_envs <= 0:
             raise ValueError("num_envs must be positive")
@@ -205,6 +206,39 @@ class SpinTorqueVectorEnv:
     def _stream(self) -> int:
         return self._torch.cuda.current_stream(self.device).cuda_stream
 
+    def _step_args(self) -> _lib.StgSttStepArgs:
+        """Argument block of stg_stt_step_*. Every buffer is allocated once in the constructor (load_state_dict copies in
+        place), so the block is built once; step() rewrites only the per-call fields (action, noise, permutation, seed, flags)."""
+        a = self._step_args_cache
+        if a is not None:
+            return a
+        torch = self._torch
+        a = _lib.StgSttStepArgs()
+        a.d_table = self._table.data_ptr()
+        a.d_param_index = _lib.ptr(self._param_index)
+        a.state = self._state_struct()
+        o = a.out
+        o.obs = self._obs.data_ptr()
+        o.reward = self._reward.data_ptr()
+        o.terminated = self._terminated.data_ptr()
+        o.truncated = self._truncated.data_ptr()
+        o.step_energy = self._step_energy.data_ptr()
+        o.n_sub = self._n_sub.data_ptr()
+        o.status = self._status.data_ptr()
+        o.final_obs = self._final_obs.data_ptr() if self.autoreset else None
+        o.stats = self._stats.data_ptr() if self.collect_stats else None
+        a.d_target_table = self._target_table.data_ptr()
+        a.n_targets = self._target_table.shape[0]
+        a.env_offset = self.env_offset
+        a.n_envs = self.num_envs
+        a.n_sets = self._n_sets
+        self._step_fn = self._lib.stg_stt_step_f32 if self.dtype == torch.float32 else self._lib.stg_stt_step_f64
+        # zero-copy bool views of the u8 flag buffers (a .bool() per step is an extra kernel launch each)
+        self._terminated_b = self._terminated.view(torch.bool)
+        self._truncated_b = self._truncated.view(torch.bool)
+        self._step_args_cache = a
+        return a
+
     def _as_device_f64(self, x, shape):
         torch = self._torch
         t = torch.as_tensor(x, dtype=torch.float64) if not isinstance(x, torch.Tensor) else x.to(torch.float64)
@@ -295,7 +329,8 @@ class SpinTorqueVectorEnv:
             flags |= _lib.F_AUTORESET
         if not self.pair_kernel:
             flags |= _lib.F_NO_PAIR
-        a = _lib.StgSttStepArgs()
+        a = self._step_args()
+        a.d_noise, a.noise_stride, a.d_perm = None, 0, None
         if noise is not None:
             nz = torch.as_tensor(noise, dtype=torch.float64).to(self.device).contiguous()
             S = 1 if self.integrator == "euler" else 4
@@ -308,39 +343,20 @@ class SpinTorqueVectorEnv:
         elif self.include_thermal and self.temperature > 0:
             flags |= _lib.F_THERMAL_PHILOX
         stream = self._stream()
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(torch, self.device):
             # 'auto': the counting sort costs three tiny launches; ragged pulse durations run ~2x faster sorted
             do_sort = self._sort_mode is True or (self._sort_mode == "auto" and N >= 4096)
             if do_sort:
                 _lib.check(self._lib.stg_stt_sort_by_substeps(
-                    self._table.data_ptr(), self._n_sets, _lib.ptr(self._param_index), act.data_ptr(),
+                    a.d_table, self._n_sets, a.d_param_index, act.data_ptr(),
                     self._perm.data_ptr(), self._sort_work.data_ptr(), N, stream), "stg_stt_sort_by_substeps")
                 self.gpu_launches += 3
                 flags |= _lib.F_SORTED
                 a.d_perm = self._perm.data_ptr()
-            a.d_table = self._table.data_ptr()
-            a.d_param_index = _lib.ptr(self._param_index)
-            a.state = self._state_struct()
             a.d_action = act.data_ptr()
-            o = a.out
-            o.obs = self._obs.data_ptr()
-            o.reward = self._reward.data_ptr()
-            o.terminated = self._terminated.data_ptr()
-            o.truncated = self._truncated.data_ptr()
-            o.step_energy = self._step_energy.data_ptr()
-            o.n_sub = self._n_sub.data_ptr()
-            o.status = self._status.data_ptr()
-            o.final_obs = self._final_obs.data_ptr() if self.autoreset else None
-            o.stats = self._stats.data_ptr() if self.collect_stats else None
-            a.d_target_table = self._target_table.data_ptr()
-            a.n_targets = self._target_table.shape[0]
             a.seed = self.rng_seed
-            a.env_offset = self.env_offset
-            a.n_envs = N
-            a.n_sets = self._n_sets
             a.flags = flags
-            fn = self._lib.stg_stt_step_f32 if self.dtype == torch.float32 else self._lib.stg_stt_step_f64
-            _lib.check(fn(C.byref(a), stream), "stg_stt_step")
+            _lib.check(self._step_fn(C.byref(a), stream), "stg_stt_step")
         self.gpu_launches += 1
         info = {
             "step_energy": self._step_energy, "n_sub": self._n_sub, "status": self._status,
@@ -348,7 +364,7 @@ class SpinTorqueVectorEnv:
         }
         if self.autoreset:
             info["final_observation"] = self._final_obs
-        return self._obs, self._reward, self._terminated.bool(), self._truncated.bool(), info
+        return self._obs, self._reward, self._terminated_b, self._truncated_b, info
 
     # ------------------------------------------------------------------------------------------------------------------
     @property
