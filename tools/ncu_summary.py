@@ -27,6 +27,8 @@ def main():
     with open(out, "w") as f:
         f.write(f"Kernel Name,{d['Kernel Name'][0]},\nBlock Size,{d['Block Size'][0]},\nGrid Size,{d['Grid Size'][0]},\n")
         for k in sorted(d):
+            if any(x in k for x in (".max.", ".min.", ".sum.pct_of_peak", ".sum.per_cycle", "_elapsed")) and not k.startswith("dram__"):
+                continue          # one representative per counter: .avg (or the plain .sum for totals)
             if k.startswith(KEEP) and d[k][0] not in ("", "n/a"):
                 f.write(f"{k},{d[k][0].replace(',', '')},{d[k][1]}\n")
     print(f"wrote {out}")
