@@ -50,8 +50,12 @@ stats = col.collect(policy)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
+if world > 1:                               # device time, maximum over ranks
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
 if rank == 0:
-    print(json.dumps({"envs_total": a.envs * world, "n_steps": a.n_steps, "rollout_ms": ms,
+    print(json.dumps({"n_gpus": world, "envs_total": a.envs * world, "n_steps": a.n_steps, "rollout_ms": ms,
                       "env_steps_per_s": a.envs * world * a.n_steps / (ms * 1e-3),
                       "substeps_per_s": stats["substeps"] / (ms * 1e-3),
                       "buffer_gb": (col.observations.numel() * 4 + col.actions.numel() * 4 + col.rewards.numel() * 4
