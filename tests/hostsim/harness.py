@@ -125,3 +125,35 @@ class HostSimEnv:
         a.seed, a.env_offset, a.n_envs, a.n_sets, a.flags = self.seed, self.env_offset, self.N, 1, flags
         lib().hostsim_stt_step(C.byref(a), 1 if self.f64 else 0)
         return self.obs.copy(), self.reward.copy(), self.terminated.astype(bool), self.truncated.astype(bool)
+
+
+def host_solve(m0, t_end, device_params, method="rk4", current=0.0, t_pulse=None, current_grid=None, field_grid=None,
+               max_step=1e-12, f64=True):
+    """SimpleLLGSSolver.solve_batch's kernel call on the host build of the kernel bodies: returns (trajectory [N, rows, 3],
+    n_sub [N]). Grids as in StgSttSolveArgs ([n_sub,3] / [n_sub,3,3], shared by every trajectory)."""
+    m0 = np.ascontiguousarray(np.asarray(m0, dtype=np.float64).reshape(-1, 3))
+    n = m0.shape[0]
+    te = np.broadcast_to(np.asarray(t_end, dtype=np.float64), (n,))
+    tp = te if t_pulse is None else np.broadcast_to(np.asarray(t_pulse, dtype=np.float64), (n,))
+    pulse = np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(current, dtype=np.float64), (n,)), tp, te], 1))
+    st = P.make_param_struct("stt_mram", device_params, max_steps=1, max_current=1.0, max_duration=1.0, temperature=300.0,
+                             thermal=False, success_threshold=0.9, energy_penalty_weight=0.1, applied_field=(0, 0, 0),
+                             max_step=max_step)
+    table = P.fold([st])
+    rows = int(np.ceil(float(te.max()) / min(max_step, float(te.max()) / 100))) + 16
+    traj = np.zeros((n, rows, 3))
+    out, nsub, guard = np.zeros((n, 3)), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    a = _lib.StgSttSolveArgs()
+    a.d_table, a.d_m0, a.d_pulse, a.d_m_out = table.ctypes.data, m0.ctypes.data, pulse.ctypes.data, out.ctypes.data
+    a.d_traj, a.traj_stride, a.d_n_sub, a.d_guard = traj.ctypes.data, rows, nsub.ctypes.data, guard.ctypes.data
+    keep = []
+    for name, g in (("d_current_grid", current_grid), ("d_field_grid", field_grid)):
+        if g is not None:
+            g = np.ascontiguousarray(np.asarray(g, dtype=np.float64))
+            keep.append(g)
+            setattr(a, name, g.ctypes.data)
+            a.grid_stride, a.grid_envs = g.shape[0], 1
+    a.n_envs, a.n_sets = n, 1
+    a.flags = (_lib.F_EULER if method == "euler" else 0) | (_lib.F_AXIS_Z if P.all_axis_z(table) else 0)
+    lib().hostsim_stt_solve(C.byref(a), 1 if f64 else 0)
+    return traj, nsub

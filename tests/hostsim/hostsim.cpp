@@ -98,7 +98,20 @@ static void solve_noise(const StgSttSolveArgs& a) {
     else if (a.flags & STG_F_THERMAL_PHILOX) solve_all<R, AXIS_Z, 1>(a);
     else solve_all<R, AXIS_Z, 0>(a);
 }
+template <int NOISE>
+static void solve_grid_all(const StgSttSolveArgs& a) {      // mirrors launch_solve_grid in stt_kernels.cu
+    for (int64_t e = 0; e < a.n_envs; ++e) {
+        if (a.flags & STG_F_EULER) solve_grid_body<NOISE, true>(a, e);
+        else solve_grid_body<NOISE, false>(a, e);
+    }
+}
 extern "C" int hostsim_stt_solve(const StgSttSolveArgs* a, int f64) {
+    if (a->d_current_grid || a->d_field_grid) {             // host-sampled callables: FP64 general stages
+        if (a->flags & STG_F_THERMAL_INJECT) solve_grid_all<2>(*a);
+        else if (a->flags & STG_F_THERMAL_PHILOX) solve_grid_all<1>(*a);
+        else solve_grid_all<0>(*a);
+        return 0;
+    }
     FtzScope ftz(!f64);
     const bool z = (a->flags & STG_F_AXIS_Z) != 0;
     if (f64) { if (z) solve_noise<double, true>(*a); else solve_noise<double, false>(*a); }
