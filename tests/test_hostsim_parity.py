@@ -257,3 +257,30 @@ def test_sampled_callables_grid_solver_vs_live_reference():
         traj, nsub = host_solve(G["grid/m0"], t1 - t0, p, method=method, current_grid=jg, field_grid=hg)
         want = G[f"grid/{name}/m"]
         assert nsub[0] == n and np.abs(traj[0, : n + 1] - want).max() < 1e-6, (name, np.abs(traj[0, : n + 1] - want).max())
+
+
+def test_stage_times_agree_with_the_kernel_plan():
+    """The host samples callables on `stage_times`; the kernel integrates `substep_plan(T)` substeps. Both must pick the same
+    n for every duration (float32 pulse lengths included), and the times must be the floats the reference passes to
+    current_func: t[i], t[i] + dt/2, t[i] + dt with t = linspace(t0, t1, n + 1) (physics/simple_solver.py:137-145, 278-295)."""
+    import types
+    from oracle.stt_oracle import substep_plan
+    from tests.hostsim.harness import host_solve
+    from spin_torque_rl_gym_b200.params import default_device_parameters
+    from spin_torque_rl_gym_b200.physics.simple_solver import SimpleLLGSSolver
+    ns = types.SimpleNamespace(max_step=1e-12)
+    rng = np.random.default_rng(12)
+    durs = np.concatenate([rng.uniform(1e-12, 5e-9, 200).astype(np.float32).astype(np.float64),
+                           [1e-9, 5e-9, 2.5e-10, 9.99e-11, 1e-10, 1.0000001e-10, 3.3e-12, 1e-12, 7e-13]])
+    for T in durs:
+        times = SimpleLLGSSolver.stage_times(ns, 0.0, float(T))
+        n, dt = substep_plan(float(T))[:2]
+        assert times.shape == (n, 3), T
+        t = np.linspace(0.0, float(T), n + 1)[:n]
+        assert np.array_equal(times[:, 0], t) and np.array_equal(times[:, 1], t + dt / 2) and np.array_equal(times[:, 2], t + dt)
+    # and the kernel body really runs that many substeps when it is handed the grid
+    p = default_device_parameters("stt_mram")
+    for T in (3.3e-12, 9.99e-11, float(np.float32(1e-9)), 2.5000000000000003e-10):
+        times = SimpleLLGSSolver.stage_times(ns, 0.0, T)
+        _, nsub = host_solve([0.3, 0.2, 0.9], T, p, current_grid=np.full(times.shape, 5e-7))
+        assert nsub[0] == times.shape[0], T
