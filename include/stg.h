@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 2
+#define STG_ABI_VERSION 3
 
 /* error codes */
 #define STG_OK 0
@@ -115,7 +115,7 @@ typedef struct StgSttStepOut {
     int32_t* status;     /* [n]     0 ok; bit0 non-finite/zero-norm guard fired (m kept); bit1 solver
                                     validation failed (solver_valid==0)                               */
     float* final_obs;    /* [n][12] with STG_F_AUTORESET: observation before the reset (terminal_observation) */
-    double* stats;       /* [STG_NSTATS] accumulated with atomics (episode statistics, K5 input)       */
+    double* stats;       /* [STG_STAT_REPLICAS][STG_NSTATS] accumulated with atomics (K5 input), see below */
 } StgSttStepOut;
 
 /* stats vector layout (all doubles, SUM-reducible across ranks) */
@@ -128,6 +128,12 @@ typedef struct StgSttStepOut {
 #define STG_STAT_GUARD 6        /* env-steps whose guard fired       */
 #define STG_STAT_EPLEN 7        /* sum of lengths of ended episodes  */
 #define STG_NSTATS 8
+/* The step kernels ADD into d_stats with FP64 atomics. A single 64-byte vector puts every atomic of a launch on one L2 line
+ * (measured on the crossbar step, 16,384 arrays: 114,688 atomics on one line took the step from 43 us to 91 us; the 1M-env
+ * K1 step, whose atomics are spread over 14 ms, did not change), so the buffer holds STG_STAT_REPLICAS copies of the vector
+ * and CTA b adds to copy b % STG_STAT_REPLICAS. A statistic is the column sum over the
+ * copies (stg_stats_fold_f64). The caller zeroes the whole buffer once per rollout. */
+#define STG_STAT_REPLICAS 256
 
 /* Argument block of one batched env step. Host struct (passed by pointer, copied into the kernel's parameter space);
  * every d_* member is a device pointer.
@@ -360,7 +366,7 @@ typedef struct StgArrayStepArgs {
     double* d_step_energy;
     double* d_similarity;
     float* d_final_obs;
-    double* d_stats;                 /* [STG_NSTATS] or NULL                                                        */
+    double* d_stats;                 /* [STG_STAT_REPLICAS][STG_NSTATS] (see StgSttStepOut.stats) or NULL           */
     uint64_t seed;
     uint64_t array_offset;
     int64_t n_arrays;
@@ -424,13 +430,17 @@ int stg_energy_landscape_f64(const StgEnergyParams* p, const double* d_m, const 
                              double* d_energy, double* d_gradient, int64_t n, void* stream);
 
 /* K5 standalone (the step kernels fuse the same reduction into their epilogue): ADD the statistics of n env-step results to
- * d_stats [STG_NSTATS] f64 (caller zeroes it once per rollout; reference analogue: EnvironmentMonitor's rolling sums,
+ * d_stats [STG_NSTATS] f64 (ONE vector, not the replicated buffer of the step kernels: this kernel reduces inside each CTA and
+ * issues one atomic set per CTA; caller zeroes it once per rollout; reference analogue: EnvironmentMonitor's rolling sums,
  * utils/monitoring.py:89-116,180-229). Every input is [n] and may be NULL (its statistic then stays untouched, STEPS always
  * counts n): d_reward f64, d_step_energy f64, d_terminated / d_truncated u8, d_n_sub i32 substeps of the step, d_status i32
  * (bit0 = guard fired), d_step_count i32 step counter AFTER the step (summed into EPLEN where the episode ended). */
 int stg_stats_reduce_f64(const double* d_reward, const double* d_step_energy, const uint8_t* d_terminated,
                          const uint8_t* d_truncated, const int32_t* d_n_sub, const int32_t* d_status, const int32_t* d_step_count,
                          int64_t n, double* d_stats, void* stream);
+/* Column sums of the replicated statistics buffer of the step kernels: d_out[q] (+)= sum_r d_replicas[r][q], q < STG_NSTATS
+ * (accumulate != 0 adds to d_out, 0 overwrites). d_out is what one all-reduce(SUM) per rollout exchanges between ranks. */
+int stg_stats_fold_f64(const double* d_replicas, double* d_out, int32_t accumulate, void* stream);
 
 /* VectorizedMagneticsOperations (utils/vectorized_operations.py:288-393), n rows of 3 doubles, NumPy's operation order:
  *   CROSS           out[n][3] = a x b                              (batch_cross_product :292-303)

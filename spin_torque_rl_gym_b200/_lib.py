@@ -22,6 +22,7 @@ F_NO_PAIR = 0x80
 F_ARRAY_ONE_WARP = 0x100
 DEV_STT, DEV_SOT, DEV_VCMA = 0, 1, 2
 NSTATS = 8
+STAT_REPLICAS = 256      # include/stg.h STG_STAT_REPLICAS: the step kernels spread their atomics over this many copies
 STAT_NAMES = ("steps", "substeps", "terminated", "truncated", "energy", "reward", "guard", "episode_length")
 FOLDED_DOUBLES = 40
 SORT_WORK_INTS = 8192 + 8
@@ -164,6 +165,7 @@ SYMBOLS = {
                                            C.c_void_p, C.c_int64, C.c_void_p]),
     "stg_stats_reduce_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int64, C.c_void_p, C.c_void_p]),
+    "stg_stats_fold_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "stg_vec3_op_f64": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_void_p]),
     "stg_phase_diagram_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p,
@@ -171,7 +173,7 @@ SYMBOLS = {
     "stg_probe_fma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
-ABI_VERSION = 2          # include/stg.h STG_ABI_VERSION (2: StgSttSolveArgs grew the sampled current / field grids)
+ABI_VERSION = 3          # include/stg.h STG_ABI_VERSION (2: sampled current / field grids; 3: replicated statistics buffer)
 _LIB: Optional[C.CDLL] = None
 
 

@@ -95,13 +95,14 @@ __global__ void __launch_bounds__(kArrayBlock, kArrayMinBlocks) array_step_kerne
         a.d_total_energy[arr] = reset ? 0.0 : tot;
         s_flags[0] = reset ? 1 : 0;
         if (a.d_stats) {
-            atomicAdd(a.d_stats + STG_STAT_STEPS, 1.0);
-            atomicAdd(a.d_stats + STG_STAT_SUBSTEPS, 10.0 * act.count);
-            if (success) atomicAdd(a.d_stats + STG_STAT_TERMINATED, 1.0);
-            else if (trunc) atomicAdd(a.d_stats + STG_STAT_TRUNCATED, 1.0);
-            atomicAdd(a.d_stats + STG_STAT_ENERGY, energy);
-            atomicAdd(a.d_stats + STG_STAT_REWARD, reward);
-            if (success || trunc) atomicAdd(a.d_stats + STG_STAT_EPLEN, (double)step);
+            double* st = a.d_stats + (blockIdx.x % STG_STAT_REPLICAS) * STG_NSTATS;
+            atomicAdd(st + STG_STAT_STEPS, 1.0);
+            atomicAdd(st + STG_STAT_SUBSTEPS, 10.0 * act.count);
+            if (success) atomicAdd(st + STG_STAT_TERMINATED, 1.0);
+            else if (trunc) atomicAdd(st + STG_STAT_TRUNCATED, 1.0);
+            atomicAdd(st + STG_STAT_ENERGY, energy);
+            atomicAdd(st + STG_STAT_REWARD, reward);
+            if (success || trunc) atomicAdd(st + STG_STAT_EPLEN, (double)step);
         }
     }
     __syncthreads();
@@ -134,10 +135,12 @@ constexpr int kGroupLanes = 8;
 constexpr int kGroupsPerWarp = 4;
 constexpr int kArray8MinBlocks = 15;     // 14.3 KB of shared memory per CTA at 8x8: 15 CTAs resident, 4096 CTAs < 2 waves
 
-template <typename F>
-__device__ __forceinline__ double group_numpy_sum(unsigned gmask, int l8, int n, F v) {      // 8 <= n <= 128
+template <int ND_T, typename F>
+__device__ __forceinline__ double group_numpy_sum(unsigned gmask, int l8, int n_rt, F v) {      // 8 <= n <= 128
+    const int n = ND_T ? ND_T : n_rt;
     const int nfull = n - (n % 8);
     double r = v(l8);
+#pragma unroll
     for (int i = 8; i < nfull; i += 8) r = dadd(r, v(i + l8));
     r = dadd(r, __shfl_xor_sync(gmask, r, 1));
     r = dadd(r, __shfl_xor_sync(gmask, r, 2));
@@ -181,7 +184,7 @@ __device__ __forceinline__ double group_apply_action(const StgArrayParams& p, co
             __syncwarp(gmask);
             if (q + 1 < a.count) fetch_row(i + a.stride);       // in flight during this device's update
             double hcv = 0.0;
-#pragma unroll 8
+#pragma unroll 16
             for (int j = 0; j < nd; ++j) {
                 const double t = dmul(rowbuf[j], pattern[3 * j + c]);
                 hcv = (j == i) ? hcv : dadd(hcv, t);
@@ -308,14 +311,15 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
     if (valid) {
         const double fnd = (double)nd;
         auto dots = [&](int i) { return dot_u(pattern + 3 * i, target + 3 * i); };
-        const double prev = ddiv(group_numpy_sum(gmask, l8, nd, dots), fnd);
+        const double prev = ddiv(group_numpy_sum<ND_T>(gmask, l8, nd, dots), fnd);
         const ArrayAction act = array_parse_action(p, act_raw);
         const double energy = group_apply_action<ND_T>(p, a.d_coupling, pattern, scratch, act, gmask, l8);
-        const double sim = ddiv(group_numpy_sum(gmask, l8, nd, dots), fnd);
+        const double sim = ddiv(group_numpy_sum<ND_T>(gmask, l8, nd, dots), fnd);
+#pragma unroll
         for (int i = l8; i < nd; i += kGroupLanes) scratch[i] = norm_u(pattern + 3 * i);
         __syncwarp(gmask);
-        const double mean = ddiv(group_numpy_sum(gmask, l8, nd, [&](int i) { return scratch[i]; }), fnd);
-        const double var = group_numpy_sum(gmask, l8, nd, [&](int i) { const double d = dadd(scratch[i], -mean); return dmul(d, d); });
+        const double mean = ddiv(group_numpy_sum<ND_T>(gmask, l8, nd, [&](int i) { return scratch[i]; }), fnd);
+        const double var = group_numpy_sum<ND_T>(gmask, l8, nd, [&](int i) { const double d = dadd(scratch[i], -mean); return dmul(d, d); });
         const double sd = sqrt(ddiv(var, fnd));
         const bool success = sim >= p.success_threshold;
         const double reward = array_reward(p, success, sim, energy, dadd(sim, -prev), sd);
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
             st_v[STG_STAT_EPLEN] = (success || trunc) ? (double)step : 0.0;
         }
         // observation rows [p_x p_y p_z t_x t_y t_z] as f32, in place over the target rows
+#pragma unroll
         for (int d = l8; d < nd; d += kGroupLanes) {
             const double t0 = target[3 * d], t1 = target[3 * d + 1], t2 = target[3 * d + 2];
             target[3 * d] = pack2f((float)pattern[3 * d], (float)pattern[3 * d + 1]);
@@ -362,15 +367,15 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
             }
         }
     }
-    // statistics: the four group leaders are reduced in the warp, one atomic per statistic and warp (K5 input)
-    if (a.d_stats) {
+    // statistics (K5 input): fire-and-forget atomics from the four group leaders into this CTA's copy of the vector
+    // (include/stg.h, STG_STAT_REPLICAS). A shuffle reduction across the groups put 32 SHFL on the dependent chain of this
+    // latency-bound kernel (11 % of the stall samples); un-replicated, the 114,688 atomics of a 16,384-array launch land on one
+    // L2 line and the step takes 91 us instead of 43 us.
+    if (a.d_stats && valid && l8 == 0) {
+        double* st = a.d_stats + (blockIdx.x % STG_STAT_REPLICAS) * STG_NSTATS;
 #pragma unroll
-        for (int q = 0; q < STG_NSTATS; ++q) {
-            double v = st_v[q];
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (lane == 0 && v != 0.0) atomicAdd(a.d_stats + q, v);
-        }
+        for (int q = 0; q < STG_NSTATS; ++q)
+            if (st_v[q] != 0.0) atomicAdd(st + q, st_v[q]);
     }
     const unsigned reset_bits = __ballot_sync(0xffffffffu, reset && l8 == 0);      // bit 8*ar: array ar of this warp was reset
     __syncwarp();

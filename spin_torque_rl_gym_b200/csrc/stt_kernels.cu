@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_MINBLOCKS_DET : STG_M
 #pragma unroll
         for (int q = 0; q < STG_NSTATS; ++q) {
             const double s = warp_sum(v[q]);
-            if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(a.out.stats + q, s);
+            if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(a.out.stats + (blockIdx.x % STG_STAT_REPLICAS) * STG_NSTATS + q, s);
         }
     }
 }
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : STG_
 #pragma unroll
         for (int q = 0; q < STG_NSTATS; ++q) {
             const double sum = warp_sum(v[q]);
-            if ((threadIdx.x & 31) == 0 && sum != 0.0) atomicAdd(a.out.stats + q, sum);
+            if ((threadIdx.x & 31) == 0 && sum != 0.0) atomicAdd(a.out.stats + (blockIdx.x % STG_STAT_REPLICAS) * STG_NSTATS + q, sum);
         }
     }
 }

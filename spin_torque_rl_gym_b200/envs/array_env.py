@@ -147,7 +147,8 @@ class SpinTorqueArrayVectorEnv:
             self._truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
             self._step_energy = torch.zeros(N, dtype=f64, device=dev)
             self._similarity = torch.zeros(N, dtype=f64, device=dev)
-            self._stats = torch.zeros(_lib.NSTATS, dtype=f64, device=dev)
+            self._stats = torch.zeros(_lib.STAT_REPLICAS, _lib.NSTATS, dtype=f64, device=dev)
+            self._stats_folded = torch.zeros(_lib.NSTATS, dtype=f64, device=dev)
             self._adim = 2 if action_mode == "global" else 3
             self._action_dev = torch.zeros(N, self._adim, dtype=torch.float32, device=dev)
         self._needs_reset = True
@@ -249,11 +250,28 @@ class SpinTorqueArrayVectorEnv:
         """[N, rows, cols, 3] float64 (a view of the device state)."""
         return self._pattern.view(self.num_envs, self.n_rows, self.n_cols, 3)
 
+    def _fold_stats(self):
+        """Column sums of the replicated statistics buffer (include/stg.h, STG_STAT_REPLICAS) into one [NSTATS] vector."""
+        torch = self._torch
+        with _lib.device_guard(torch, self.device):
+            _lib.check(self._lib.stg_stats_fold_f64(self._stats.data_ptr(), self._stats_folded.data_ptr(), 0,
+                                                    torch.cuda.current_stream(self.device).cuda_stream), "stg_stats_fold_f64")
+        return self._stats_folded
+
     def episode_stats(self, reset: bool = False) -> Dict[str, float]:
-        vals = self._stats.cpu().tolist()
+        """Accumulated episode statistics of this rank (dict of python floats; one D2H of 64 bytes)."""
+        vals = self._fold_stats().cpu().tolist()
         if reset:
             self._stats.zero_()
         return dict(zip(_lib.STAT_NAMES, vals))
+
+    def stats_tensor(self):
+        """[NSTATS] float64 CUDA tensor of the statistics accumulated so far: the input of the one all-reduce per rollout.
+        It is a folded copy (overwritten by the next call); use reset_stats() to start a new accumulation."""
+        return self._fold_stats()
+
+    def reset_stats(self) -> None:
+        self._stats.zero_()
 
     def close(self):
         pass

@@ -175,7 +175,8 @@ class SpinTorqueVectorEnv:
             self._step_energy = torch.zeros(N, dtype=f64, device=dev)
             self._n_sub = torch.zeros(N, dtype=i32, device=dev)
             self._status = torch.zeros(N, dtype=i32, device=dev)
-            self._stats = torch.zeros(_lib.NSTATS, dtype=f64, device=dev)
+            self._stats = torch.zeros(_lib.STAT_REPLICAS, _lib.NSTATS, dtype=f64, device=dev)
+            self._stats_folded = torch.zeros(_lib.NSTATS, dtype=f64, device=dev)
             self._action_dev = torch.zeros(N, 2, dtype=torch.float32, device=dev)
             self._perm = torch.zeros(N, dtype=i32, device=dev)
             self._sort_work = torch.zeros(_lib.SORT_WORK_INTS, dtype=i32, device=dev)
@@ -376,26 +377,41 @@ class SpinTorqueVectorEnv:
     def target(self):
         return self._target.t().contiguous()
 
+    def _fold_stats(self):
+        """Column sums of the replicated statistics buffer (include/stg.h, STG_STAT_REPLICAS) into one [NSTATS] vector."""
+        torch = self._torch
+        with _lib.device_guard(torch, self.device):
+            _lib.check(self._lib.stg_stats_fold_f64(self._stats.data_ptr(), self._stats_folded.data_ptr(), 0,
+                                                    torch.cuda.current_stream(self.device).cuda_stream), "stg_stats_fold_f64")
+        return self._stats_folded
+
     def episode_stats(self, reset: bool = False) -> Dict[str, float]:
         """Accumulated episode statistics of this rank (dict of python floats; one D2H of 64 bytes)."""
-        vals = self._stats.cpu().tolist()
+        vals = self._fold_stats().cpu().tolist()
         if reset:
             self._stats.zero_()
         return dict(zip(_lib.STAT_NAMES, vals))
 
     def stats_tensor(self):
-        return self._stats
+        """[NSTATS] float64 CUDA tensor of the statistics accumulated so far: the input of the one all-reduce per rollout.
+        It is a folded copy (overwritten by the next call); use reset_stats() to start a new accumulation."""
+        return self._fold_stats()
+
+    def reset_stats(self) -> None:
+        self._stats.zero_()
 
     def state_dict(self) -> Dict[str, Any]:
         return {"m": self._m.clone(), "target": self._target.clone(), "total_energy": self._total_energy.clone(),
                 "last_action": self._last_action.clone(), "step_count": self._step_count.clone(),
-                "episode": self._episode.clone(), "rng_seed": self.rng_seed, "stats": self._stats.clone()}
+                "episode": self._episode.clone(), "rng_seed": self.rng_seed, "stats": self._fold_stats().clone()}
 
     def load_state_dict(self, sd: Dict[str, Any]) -> None:
         for k, t in (("m", self._m), ("target", self._target), ("total_energy", self._total_energy),
                      ("last_action", self._last_action), ("step_count", self._step_count),
-                     ("episode", self._episode), ("stats", self._stats)):
+                     ("episode", self._episode)):
             t.copy_(sd[k])
+        self._stats.zero_()
+        self._stats[0].copy_(sd["stats"])               # the folded vector goes into the first copy
         self.rng_seed = int(sd["rng_seed"])
         self._needs_reset = False
 

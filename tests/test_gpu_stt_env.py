@@ -529,3 +529,42 @@ def test_standalone_stats_reduce_matches_fused_epilogue(cuda_device):
         reduce_step_stats(acc, reward=stored["reward"], n_sub=stored["n_sub"][:2])
     with pytest.raises(ValueError):
         reduce_step_stats(torch.zeros(_lib.NSTATS, dtype=torch.float64), reward=stored["reward"])      # CPU vector
+
+
+def test_replicated_statistics_fold_and_state_dict(cuda_device):
+    """include/stg.h STG_STAT_REPLICAS: the step kernels spread their atomics over 256 copies of the statistics vector
+    (one L2 line would serialise every warp of a launch); stg_stats_fold_f64 gives the column sums."""
+    import ctypes as C
+    torch = _torch()
+    from spin_torque_rl_gym_b200 import _lib
+    lib = _lib.load()
+    rep = torch.rand(_lib.STAT_REPLICAS, _lib.NSTATS, dtype=torch.float64, device=cuda_device) * 1e3
+    out = torch.full((_lib.NSTATS,), 7.0, dtype=torch.float64, device=cuda_device)
+    stream = torch.cuda.current_stream(cuda_device).cuda_stream
+    _lib.check(lib.stg_stats_fold_f64(rep.data_ptr(), out.data_ptr(), 0, stream), "fold")
+    want = rep.sum(0)
+    assert torch.allclose(out, want, rtol=1e-13, atol=0)
+    _lib.check(lib.stg_stats_fold_f64(rep.data_ptr(), out.data_ptr(), 1, stream), "fold")
+    assert torch.allclose(out, 2 * want, rtol=1e-13, atol=0)
+    assert lib.stg_stats_fold_f64(None, out.data_ptr(), 0, stream) == -1          # STG_E_NULL
+    # the env really uses more than one copy, reports their sum, and carries it through a state dict
+    n = 65536
+    env = _make(n, "f32", cuda_device, max_steps=3, include_thermal_fluctuations=False, autoreset=True, rng_seed=2,
+                max_current=1.1e-6)
+    env.reset(seed=2)
+    act = torch.zeros(n, 2, dtype=torch.float32, device=cuda_device)
+    act[:, 0] = 6e-7
+    act[:, 1] = 5e-11
+    for _ in range(4):
+        env.step(act)
+    assert int((env._stats[:, 0] != 0).sum()) == _lib.STAT_REPLICAS               # every copy received env-steps
+    st = env.episode_stats()
+    assert st["steps"] == 4 * n and st["truncated"] + st["terminated"] >= n
+    sd = env.state_dict()
+    other = _make(n, "f32", cuda_device, max_steps=3, include_thermal_fluctuations=False, autoreset=True, rng_seed=2,
+                  max_current=1.1e-6)
+    other.reset(seed=2)
+    other.load_state_dict(sd)
+    assert other.episode_stats() == st
+    other.reset_stats()
+    assert other.episode_stats()["steps"] == 0 and torch.equal(other.stats_tensor(), torch.zeros_like(other.stats_tensor()))

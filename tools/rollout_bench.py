@@ -42,7 +42,7 @@ col = stg.RolloutCollector(env, n_steps=a.n_steps)
 warm = stg.RolloutCollector(env, n_steps=2, store_observations=False)
 warm.collect(policy)                       # warm-up: lazy NCCL communicator setup, first-launch overheads
 env.reset(seed=7)
-env.stats_tensor().zero_()
+env.reset_stats()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
