@@ -403,11 +403,15 @@ typedef struct StgDeviceParams {
 } StgDeviceParams;
 
 /* device.compute_effective_field(m, H_app[, V]) for n rows (devices/stt_mram.py:56-76, sot_mram.py:78-112,
- * vcma_mram.py:86-120). d_happ: NULL (zero), 1 row (broadcast) or n rows; d_voltage: VCMA only, NULL = 0 V. */
+ * vcma_mram.py:86-120). d_happ: NULL (zero), 1 row (broadcast) or n rows; d_voltage: VCMA only, NULL = 0 V.
+ * d_zero_rows: NULL, or one int32 the kernel ADDS the number of STT rows with |m| < 1e-12 to: the reference raises
+ * "Magnetization vector cannot be zero" for those (devices/base_device.py:112-114); the caller reads 4 bytes instead of
+ * scanning its input. */
 int stg_device_field_f64(const StgDeviceParams* p, const double* d_m, const double* d_happ, int32_t happ_rows,
-                         const double* d_voltage, double* d_out, int64_t n, void* stream);
-/* device.compute_resistance(m) (devices/stt_mram.py:78-94, sot_mram.py:196-228, vcma_mram.py:236-257). */
-int stg_device_resistance_f64(const StgDeviceParams* p, const double* d_m, double* d_out, int64_t n, void* stream);
+                         const double* d_voltage, double* d_out, int64_t n, int32_t* d_zero_rows, void* stream);
+/* device.compute_resistance(m) (devices/stt_mram.py:78-94, sot_mram.py:196-228, vcma_mram.py:236-257); d_zero_rows as above. */
+int stg_device_resistance_f64(const StgDeviceParams* p, const double* d_m, double* d_out, int64_t n, int32_t* d_zero_rows,
+                              void* stream);
 /* SOTMRAMDevice.compute_spin_torque(J, m, direction) (devices/sot_mram.py:163-194); current_direction: 3 host doubles. */
 int stg_device_sot_torque_f64(const StgDeviceParams* p, const double* d_current, int32_t current_rows, const double* d_m,
                               const double* current_direction, double* d_tau_dl, double* d_tau_fl, int64_t n, void* stream);

@@ -154,8 +154,9 @@ SYMBOLS = {
     "stg_array_step_f64": (C.c_int, [C.POINTER(StgArrayStepArgs), C.c_void_p]),
     "stg_array_reset": (C.c_int, [C.POINTER(StgArrayStepArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
     "stg_device_field_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
-                                       C.c_void_p, C.c_int64, C.c_void_p]),
-    "stg_device_resistance_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "stg_device_resistance_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                            C.c_void_p]),
     "stg_device_sot_torque_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_int32, C.c_void_p,
                                             C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "stg_vcma_anisotropy_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

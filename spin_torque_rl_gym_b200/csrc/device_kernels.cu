@@ -21,7 +21,7 @@ __device__ __forceinline__ double vcma_keff(const StgDeviceParams& p, double v) 
 
 __global__ void __launch_bounds__(256) device_field_kernel(const __grid_constant__ StgDeviceParams p, const double* m,
                                                            const double* happ, int happ_rows, const double* volt,
-                                                           double* out, int64_t n) {
+                                                           double* out, int64_t n, int* zero_rows) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double mx = m[3 * i], my = m[3 * i + 1], mz = m[3 * i + 2];
@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) device_field_kernel(const __grid_constant
     double ku = p.uniaxial_anisotropy;
     if (p.kind == STG_DEV_STT) {   // validate_magnetization normalises first (devices/stt_mram.py:62)
         const double nrm = sqrt(mx * mx + my * my + mz * mz);
+        if (zero_rows && nrm < 1e-12) atomicAdd(zero_rows, 1);      // devices/base_device.py:112-114 raises for these
         mx /= nrm; my /= nrm; mz /= nrm;
     } else if (p.kind == STG_DEV_VCMA) {
         ku = vcma_keff(p, volt ? volt[i] : 0.0);
@@ -46,9 +47,13 @@ __global__ void __launch_bounds__(256) device_field_kernel(const __grid_constant
 }
 
 __global__ void __launch_bounds__(256) device_resistance_kernel(const __grid_constant__ StgDeviceParams p, const double* m,
-                                                                double* out, int64_t n) {
+                                                                double* out, int64_t n, int* zero_rows) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (zero_rows && p.kind == STG_DEV_STT) {
+        const double x = m[3 * i], y = m[3 * i + 1], z = m[3 * i + 2];
+        if (sqrt(x * x + y * y + z * z) < 1e-12) atomicAdd(zero_rows, 1);
+    }
     double f[FI_COUNT];
     f[FI_KIND] = (double)p.kind;
     f[FI_RP] = p.resistance_parallel; f[FI_RAP] = p.resistance_antiparallel;
@@ -190,21 +195,23 @@ static inline unsigned grid_for(int64_t n) { return (unsigned)((n + 255) / 256);
 using namespace stg;
 
 extern "C" int stg_device_field_f64(const StgDeviceParams* p, const double* d_m, const double* d_happ, int32_t happ_rows,
-                                    const double* d_voltage, double* d_out, int64_t n, void* stream) {
+                                    const double* d_voltage, double* d_out, int64_t n, int32_t* d_zero_rows, void* stream) {
     if (!p || !d_m || !d_out) return STG_E_NULL;
     if (n < 0 || (d_happ && happ_rows != 1 && happ_rows != n)) return STG_E_SIZE;
     if (p->kind < STG_DEV_STT || p->kind > STG_DEV_VCMA) return STG_E_ENUM;
     if (n == 0) return STG_OK;
-    device_field_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*p, d_m, d_happ, happ_rows, d_voltage, d_out, n);
+    device_field_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*p, d_m, d_happ, happ_rows, d_voltage, d_out, n,
+                                                                       d_zero_rows);
     return (int)cudaGetLastError();
 }
 
-extern "C" int stg_device_resistance_f64(const StgDeviceParams* p, const double* d_m, double* d_out, int64_t n, void* stream) {
+extern "C" int stg_device_resistance_f64(const StgDeviceParams* p, const double* d_m, double* d_out, int64_t n,
+                                         int32_t* d_zero_rows, void* stream) {
     if (!p || !d_m || !d_out) return STG_E_NULL;
     if (n < 0) return STG_E_SIZE;
     if (p->kind < STG_DEV_STT || p->kind > STG_DEV_VCMA) return STG_E_ENUM;
     if (n == 0) return STG_OK;
-    device_resistance_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*p, d_m, d_out, n);
+    device_resistance_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(*p, d_m, d_out, n, d_zero_rows);
     return (int)cudaGetLastError();
 }
 

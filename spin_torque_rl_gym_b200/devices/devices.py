@@ -107,11 +107,26 @@ class BaseSpintronicDevice:
         torch = _lib.require_cuda()
         return torch.cuda.current_stream(self._device).cuda_stream
 
-    def compute_effective_field(self, magnetization, applied_field, applied_voltage=None):
+    def _zero_counter(self):
+        """Device int32 the kernels add the number of zero-norm STT rows to (devices/base_device.py:112-114 raises for them)."""
+        torch = _lib.require_cuda()
+        z = getattr(self, "_zero_rows", None)
+        if z is None:
+            z = self._zero_rows = torch.zeros(1, dtype=torch.int32, device=self._device)
+        else:
+            z.zero_()
+        return z
+
+    def _raise_if_zero_rows(self, z) -> None:
+        if z is not None and int(z.item()) > 0:             # one 4-byte D2H instead of three passes over the input
+            raise ValueError("Magnetization vector cannot be zero")
+
+    def compute_effective_field(self, magnetization, applied_field, applied_voltage=None, check_zero: bool = True):
+        """`check_zero=False` skips reading back the zero-row counter, which keeps a batched call fully asynchronous; the
+        output rows of zero vectors are then unspecified (the reference raises for them)."""
         torch = _lib.require_cuda()
         m, was_numpy, single = self._rows(magnetization)
-        if self.KIND == _lib.DEV_STT and bool((m.norm(dim=1) < 1e-12).any()):
-            raise ValueError("Magnetization vector cannot be zero")
+        z = self._zero_counter() if (check_zero and self.KIND == _lib.DEV_STT) else None
         h, _ = _to_dev(applied_field, self._device)
         h = h.reshape(-1, 3).contiguous()
         if h.shape[0] not in (1, m.shape[0]):
@@ -127,19 +142,21 @@ class BaseSpintronicDevice:
         p = self._struct()
         with torch.cuda.device(self._device):
             _lib.check(self._lib.stg_device_field_f64(C.byref(p), m.data_ptr(), h.data_ptr(), h.shape[0], _lib.ptr(v),
-                                                      out.data_ptr(), m.shape[0], self._stream()), "stg_device_field_f64")
+                                                      out.data_ptr(), m.shape[0], _lib.ptr(z), self._stream()),
+                       "stg_device_field_f64")
+        self._raise_if_zero_rows(z)
         return _back(out, was_numpy, single)
 
-    def compute_resistance(self, magnetization):
+    def compute_resistance(self, magnetization, check_zero: bool = True):
         torch = _lib.require_cuda()
         m, was_numpy, single = self._rows(magnetization)
-        if self.KIND == _lib.DEV_STT and bool((m.norm(dim=1) < 1e-12).any()):
-            raise ValueError("Magnetization vector cannot be zero")
+        z = self._zero_counter() if (check_zero and self.KIND == _lib.DEV_STT) else None
         out = torch.empty(m.shape[0], dtype=torch.float64, device=self._device)
         p = self._struct()
         with torch.cuda.device(self._device):
             _lib.check(self._lib.stg_device_resistance_f64(C.byref(p), m.data_ptr(), out.data_ptr(), m.shape[0],
-                                                           self._stream()), "stg_device_resistance_f64")
+                                                           _lib.ptr(z), self._stream()), "stg_device_resistance_f64")
+        self._raise_if_zero_rows(z)
         if single:
             return float(out[0])
         return out.cpu().numpy() if was_numpy else out

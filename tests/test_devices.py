@@ -108,3 +108,34 @@ def test_thermal_field_statistics(cuda_device):
     assert abs(float(cur.std()) / s - 1) < 0.03
     rho = float(((cur * prev).mean() / (cur.std() * prev.std())))
     assert abs(rho - np.exp(-0.5)) < 0.03
+
+
+@pytest.mark.gpu
+def test_zero_magnetisation_raises_like_the_reference(cuda_device):
+    """devices/base_device.py:112-114: a zero vector is a ValueError for the STT device (validate_magnetization normalises).
+    The check runs inside the kernel (a 4-byte row counter), also for one bad row inside a large batch."""
+    import torch
+    from spin_torque_rl_gym_b200.devices import create_device
+    from spin_torque_rl_gym_b200.params import default_device_parameters
+    stt = create_device("stt_mram", default_device_parameters("stt_mram"), device=cuda_device)
+    for bad in (np.zeros(3), np.array([0.0, 1e-13, 0.0])):
+        with pytest.raises(ValueError, match="cannot be zero"):
+            stt.compute_resistance(bad)
+        with pytest.raises(ValueError, match="cannot be zero"):
+            stt.compute_effective_field(bad, np.zeros(3))
+    m = torch.randn(100003, 3, dtype=torch.float64, device=cuda_device)
+    good_r = stt.compute_resistance(m)
+    good_h = stt.compute_effective_field(m, np.zeros(3))
+    assert torch.isfinite(good_r).all() and torch.isfinite(good_h).all()
+    m[77777] = 0.0
+    with pytest.raises(ValueError, match="cannot be zero"):
+        stt.compute_resistance(m)
+    with pytest.raises(ValueError, match="cannot be zero"):
+        stt.compute_effective_field(m, np.zeros(3))
+    r = stt.compute_resistance(m, check_zero=False)                 # asynchronous use: no read-back, no exception;
+    assert torch.equal(r[:77777], good_r[:77777]) and torch.equal(r[77778:], good_r[77778:])   # the bad row is unspecified
+    m[77777] = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64)
+    assert torch.equal(stt.compute_resistance(m)[:77777], good_r[:77777])          # the counter was reset
+    p = default_device_parameters("sot_mram")
+    sot = create_device("sot_mram", p, device=cuda_device)
+    assert np.isfinite(sot.compute_resistance(np.zeros(3)))         # SOT/VCMA do not normalise and do not raise

@@ -48,7 +48,7 @@ def collect(dev=None):
     def rk():
         res["r"] = solver.solve_batch(m0, t_end, [sot, vcma], current=cur, voltage=volt, param_index=pidx,
                                       device_type=["sot_mram", "vcma_mram"])
-    ms = timed(rk, reps=3, warm=1)
+    ms = timed(rk, reps=5, warm=3)      # three warm-ups: the first calls after large frees pay allocator misses
     attempts = float((res["r"]["n_accepted"] + res["r"]["n_rejected"]).sum())
     out["rk45_mix_262144"] = {"ms_per_solve": ms, "attempted_steps_per_s": attempts / (ms * 1e-3),
                               "rhs_evals_per_s": float(res["r"]["n_rhs"].sum()) / (ms * 1e-3),
@@ -81,6 +81,44 @@ def collect(dev=None):
         ms = timed(lambda: env.step(act), reps=5, warm=2)
         sub = float(env._n_sub.sum())
         out[f"ragged_T_uniform_{'sorted' if sort else 'unsorted'}"] = {"ms_per_step": ms, "substeps_per_s": sub / (ms * 1e-3)}
+    # ---- K4 elementwise FP64 ops and the standalone K5 reduction: HBM-bound, algorithmic bytes / device time ------------------
+    from spin_torque_rl_gym_b200 import _lib
+    from spin_torque_rl_gym_b200.devices import create_device
+    from spin_torque_rl_gym_b200.parallel import reduce_step_stats
+    from spin_torque_rl_gym_b200.physics import EnergyLandscape, VectorizedMagneticsOperations as VMO
+    R = 1 << 24                                              # 16.8M rows: 403 MB per [R,3] f64 operand, far beyond the 126 MB L2
+    a3 = torch.randn(R, 3, dtype=torch.float64, device=dev)
+    b3 = torch.randn(R, 3, dtype=torch.float64, device=dev)
+    k4 = {}
+    for name, fn, nbytes in (
+            ("vec3_cross", lambda: VMO.batch_cross_product(a3, b3), 72),          # 2 x 24 read + 24 written per row
+            ("vec3_dot", lambda: VMO.batch_dot_product(a3, b3), 56),
+            ("vec3_normalize", lambda: VMO.batch_normalize(a3), 48),
+            ("stt_effective_field", None, 48),
+            ("stt_resistance", None, 32),
+            ("energy_and_gradient", None, 56)):
+        if name == "stt_effective_field":
+            dv = create_device("stt_mram", P.default_device_parameters("stt_mram"), device=dev)
+            fn = lambda: dv.compute_effective_field(a3, np.zeros(3))                # noqa: E731
+        elif name == "stt_resistance":
+            fn = lambda: dv.compute_resistance(a3)                                   # noqa: E731
+        elif name == "energy_and_gradient":
+            land = EnergyLandscape(P.default_device_parameters("stt_mram"), device=dev)
+            fn = lambda: (land.compute_energy(a3), land.compute_energy_gradient(a3))  # noqa: E731  (24+8) + (24+24) B per row
+            nbytes = 80
+        ms = timed(fn, reps=5, warm=2)
+        k4[name] = {"ms": ms, "hbm_gbs_algorithmic": R * nbytes / (ms * 1e-3) / 1e9}
+    out["k4_elementwise_16M_rows"] = k4
+    T = 1 << 26                                              # 67M stored step results: 8+8+1+1+4+4+4 = 30 B each
+    bufs = dict(reward=torch.randn(T, dtype=torch.float64, device=dev), step_energy=torch.rand(T, dtype=torch.float64, device=dev),
+                terminated=(torch.rand(T, device=dev) < 0.1), truncated=(torch.rand(T, device=dev) < 0.1),
+                n_sub=torch.randint(10, 5000, (T,), dtype=torch.int32, device=dev),
+                status=torch.zeros(T, dtype=torch.int32, device=dev),
+                step_count=torch.randint(1, 100, (T,), dtype=torch.int32, device=dev))
+    bufs["terminated"], bufs["truncated"] = bufs["terminated"].to(torch.uint8), bufs["truncated"].to(torch.uint8)
+    vec = torch.zeros(_lib.NSTATS, dtype=torch.float64, device=dev)
+    ms = timed(lambda: reduce_step_stats(vec, **bufs), reps=5, warm=2)
+    out["k5_stats_reduce_67M"] = {"ms": ms, "hbm_gbs_algorithmic": T * 30 / (ms * 1e-3) / 1e9}
     return out
 
 
