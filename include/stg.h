@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 3
+#define STG_ABI_VERSION 4
 
 /* error codes */
 #define STG_OK 0

@@ -174,7 +174,8 @@ SYMBOLS = {
     "stg_probe_fma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
-ABI_VERSION = 3          # include/stg.h STG_ABI_VERSION (2: sampled current / field grids; 3: replicated statistics buffer)
+ABI_VERSION = 4          # include/stg.h STG_ABI_VERSION (2: sampled current / field grids; 3: replicated statistics buffer;
+                         # 4: zero-row counters of stg_device_field_f64 / stg_device_resistance_f64)
 _LIB: Optional[C.CDLL] = None
 
 
