@@ -9,7 +9,10 @@
 namespace stg {
 
 #ifndef STG_RK45_MINBLOCKS
-#define STG_RK45_MINBLOCKS 1
+// Occupancy sweep on the configs[2] mix (262,144 trajectories x 114 attempts, B200): min blocks 1 (184 registers, 8 warps/SM)
+// 3.99 ms; 5: 3.34; 6: 3.41; 7: 3.23; 8 (128 registers + 72 B spill, 16 warps/SM): 3.04; 10: 3.17; 12: 3.47; 16: 4.02 ms.
+// The kernel waits on dependent FP64 chains (ncu: `wait` 2.1 stalls per issue at 1.9 warps per scheduler), so warps beat registers.
+#define STG_RK45_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(64, STG_RK45_MINBLOCKS) llgs_rk45_kernel(const __grid_constant__ StgRk45Args a) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
