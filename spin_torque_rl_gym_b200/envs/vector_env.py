@@ -415,5 +415,44 @@ class SpinTorqueVectorEnv:
         self.rng_seed = int(sd["rng_seed"])
         self._needs_reset = False
 
+    def capture_step(self, actions):
+        """Capture one `step(actions)` in a CUDA graph and return a `GraphedStep`; `replay()` re-issues the captured launches
+        (counting sort + step kernel) for ~one driver call instead of the Python/ctypes launch path (19 us per step). Measured
+        (profiles/README.md): device time is unchanged at 1,024 envs - a step is >= ~100 dependent substeps, which already hides
+        the launch path - and 10 % lower at 16,384 envs; the gain is a free host thread. `actions` must be the device tensor [N,2] f32 that step() would use without staging: the caller
+        overwrites it in place before every replay, and the returned (obs, reward, terminated, truncated, info) are the env's
+        persistent output tensors. Thermal noise stays fresh across replays because the Philox counters are built from the
+        step / episode counters in device memory. Captured by value: rng_seed, flags and buffer addresses - capture again
+        after reset(seed=...)."""
+        torch = self._torch
+        if not (isinstance(actions, torch.Tensor) and actions.device == self.device and actions.dtype == torch.float32
+                and actions.is_contiguous() and tuple(actions.shape) == (self.num_envs, 2)):
+            raise ValueError("capture_step needs a contiguous float32 CUDA tensor [num_envs, 2] on the env's device")
+        if self._needs_reset:
+            raise RuntimeError("Environment must be reset before calling step")
+        launches0 = self.gpu_launches
+        saved = self.state_dict()
+        self.step(actions)                          # outside the capture: CUDA loads kernels lazily on their first launch
+        self.load_state_dict(saved)
+        graph = torch.cuda.CUDAGraph()
+        with _lib.device_guard(torch, self.device):
+            with torch.cuda.graph(graph):
+                out = self.step(actions)
+        per_replay = (self.gpu_launches - launches0) // 2    # warm-up + capture issued the same launches
+        self.gpu_launches = launches0               # capture records the launches, it does not execute them
+        return GraphedStep(self, graph, out, per_replay)
+
     def close(self):
         pass
+
+
+class GraphedStep:
+    """A captured `SpinTorqueVectorEnv.step` (see `capture_step`)."""
+
+    def __init__(self, env, graph, outputs, launches_per_replay: int):
+        self.env, self.graph, self.outputs, self.launches_per_replay = env, graph, outputs, launches_per_replay
+
+    def replay(self):
+        self.graph.replay()
+        self.env.gpu_launches += self.launches_per_replay
+        return self.outputs

@@ -568,3 +568,41 @@ def test_replicated_statistics_fold_and_state_dict(cuda_device):
     assert other.episode_stats() == st
     other.reset_stats()
     assert other.episode_stats()["steps"] == 0 and torch.equal(other.stats_tensor(), torch.zeros_like(other.stats_tensor()))
+
+
+@pytest.mark.parametrize("thermal", [False, True])
+def test_cuda_graph_replay_equals_eager_steps(thermal, cuda_device):
+    """capture_step(): a CUDA-graph replay of step() (counting sort + step kernel) gives the same bits as eager steps,
+    draws fresh Philox noise on every replay, and keeps the statistics and launch counters right."""
+    torch = _torch()
+    n = 8192                                               # >= 4096: the captured step includes the counting sort
+    kw = dict(max_steps=4, include_thermal_fluctuations=thermal, autoreset=True, rng_seed=9, max_current=1.1e-6)
+    eager, graphed = _make(n, "f32", cuda_device, **kw), _make(n, "f32", cuda_device, **kw)
+    eager.reset(seed=9)
+    graphed.reset(seed=9)
+    rng = np.random.default_rng(9)
+    acts = [np.stack([rng.uniform(-1.1e-6, 1.1e-6, n), rng.uniform(1e-12, 3e-10, n)], 1).astype(np.float32) for _ in range(6)]
+    static = torch.from_numpy(acts[0]).to(cuda_device)
+    g = graphed.capture_step(static)
+    assert g.launches_per_replay == 4 and graphed.gpu_launches == 1        # reset only: capture executed nothing
+    m_before = graphed.magnetization.clone()
+    assert torch.equal(m_before, eager.magnetization)
+    prev_obs = None
+    for a in acts:
+        o0, r0, te0, tr0, i0 = eager.step(torch.from_numpy(a).to(cuda_device))
+        static.copy_(torch.from_numpy(a))
+        o1, r1, te1, tr1, i1 = g.replay()
+        assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(te0, te1) and torch.equal(tr0, tr1)
+        assert torch.equal(i0["n_sub"], i1["n_sub"]) and torch.equal(i0["final_observation"], i1["final_observation"])
+        assert torch.equal(eager.magnetization, graphed.magnetization)
+        if prev_obs is not None:
+            assert not torch.equal(prev_obs, o1)
+        prev_obs = o1.clone()
+    se, sg = eager.episode_stats(), graphed.episode_stats()
+    for k in ("steps", "substeps", "terminated", "truncated", "guard", "episode_length"):
+        assert se[k] == sg[k], k
+    for k in ("energy", "reward"):                          # FP64 atomics: same terms, unordered sum
+        assert se[k] == pytest.approx(sg[k], rel=1e-12), k
+    assert se["steps"] == 6 * n and graphed.gpu_launches == 1 + 6 * 4
+    with pytest.raises(ValueError):
+        graphed.capture_step(acts[0])                       # a NumPy array would need staging copies

@@ -119,6 +119,20 @@ def collect(dev=None):
     vec = torch.zeros(_lib.NSTATS, dtype=torch.float64, device=dev)
     ms = timed(lambda: reduce_step_stats(vec, **bufs), reps=5, warm=2)
     out["k5_stats_reduce_67M"] = {"ms": ms, "hbm_gbs_algorithmic": T * 30 / (ms * 1e-3) / 1e9}
+    # ---- launch-bound regime: 1,024 envs, 100-substep pulses; eager step() vs CUDA-graph replay (capture_step) ------------------
+    small = {}
+    for nenv in (1024, 16384):
+        env = stg.SpinTorqueVectorEnv(num_envs=nenv, device=dev, max_current=1.1e-6, include_thermal_fluctuations=True, rng_seed=4)
+        env.reset(seed=4)
+        a_s = torch.zeros(nenv, 2, dtype=torch.float32, device=dev)
+        a_s[:, 0] = 5e-7
+        a_s[:, 1] = 1e-10
+        eager_ms = timed(lambda: env.step(a_s), reps=300, warm=20)
+        g = env.capture_step(a_s)
+        graph_ms = timed(g.replay, reps=300, warm=20)
+        small[f"{nenv}_envs"] = {"eager_us_per_step": eager_ms * 1e3, "graph_us_per_step": graph_ms * 1e3,
+                                 "launches_per_step": g.launches_per_replay}
+    out["small_batch_100_substeps"] = small
     return out
 
 
