@@ -318,9 +318,10 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
     if (axis_z) {
         if (sizeof(R) == 4 && noise == 0 && !(a.flags & (STG_F_EULER | STG_F_NO_PAIR))) {
             // two envs per thread, Blackwell packed FP32x2 arithmetic (bit-identical to the one-env-per-thread kernels).
-            // Measured (profiles/README.md): +8 % without thermal noise; with the Philox stream the packed variant needs 203
-            // registers and is 5 % slower than one env per thread (+4 % when capped to 168 registers), so it is not
-            // dispatched there.
+            // Measured (profiles/README.md): +8 % without thermal noise. With the Philox stream the packed variant was swept
+            // twice: 201 registers 15.4 ms, 168: 14.1 ms, 155: 14.6 ms, 128 + 88 B spill: 13.97 ms per 1M-env step against
+            // 14.17 ms for one env per thread (the integer Philox rounds do not pack, only the FP32 half of the substep does),
+            // so it is not dispatched there.
             const unsigned grid = (unsigned)((a.n_envs + 2 * kBlock - 1) / (2 * kBlock));
             stt_env_step_pair_kernel<0><<<grid, kBlock, 0, s>>>(a);
             return cudaGetLastError();
