@@ -133,6 +133,15 @@ __global__ void __launch_bounds__(kArrayBlock, kArrayMinBlocks) array_step_kerne
 // All results are bit-identical to the one-warp kernel and to the host sequence in array_core.cuh.
 constexpr int kGroupLanes = 8;
 constexpr int kGroupsPerWarp = 4;
+// Shared-memory stride of one array in doubles: pattern 3nd, target 3nd, scratch / coupling row nd, rounded so that the stride
+// is 8 (mod 16) doubles = 64 (mod 128) bytes. With a stride that is a multiple of 128 bytes (8x8: 3,584 B) the four groups of
+// a warp map to the same 16 banks and every group-parallel 64-bit access is a 4-way conflict (ncu: 2.9e6 conflicts per
+// launch, short-scoreboard + MIO-throttle stalls 7 per issue); alternating the groups between the two halves of the banks
+// leaves the two wavefronts a 32-lane 64-bit access needs anyway.
+__host__ __device__ inline int array8_stride(int nd) {
+    const int per = 7 * nd + (nd & 1);
+    return per + ((8 - per % 16) + 16) % 16;
+}
 constexpr int kArray8MinBlocks = 15;     // 14.3 KB of shared memory per CTA at 8x8: 15 CTAs resident, 4096 CTAs < 2 waves
 
 template <int ND_T, typename F>
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
     extern __shared__ __align__(16) double smem[];
     const StgArrayParams& p = a.params;
     const int nd = ND_T ? ND_T : p.n_rows * p.n_cols;
-    const int per = 7 * nd + (nd & 1);               // doubles per array: pattern 3nd, target 3nd, scratch / coupling row nd
+    const int per = array8_stride(nd);
     const int lane = threadIdx.x, g = lane >> 3, l8 = lane & 7;
     const unsigned gmask = 0xFFu << (8 * g);
     const int64_t arr0 = (int64_t)blockIdx.x * kGroupsPerWarp;
@@ -473,7 +482,8 @@ extern "C" int stg_array_step_f64(const StgArrayStepArgs* args, void* stream) {
     const auto aligned = [](const void* q, uintptr_t n) { return (reinterpret_cast<uintptr_t>(q) & (n - 1)) == 0; };
     if (nd >= 8 && nd <= 128 && !(a.flags & STG_F_ARRAY_ONE_WARP) && aligned(a.d_obs, 8) &&
         (!a.d_final_obs || aligned(a.d_final_obs, 8))) {
-        const size_t smem8 = sizeof(double) * (7 * (size_t)nd + (nd & 1)) * stg::kGroupsPerWarp;   // <= 28 KB
+        const size_t smem8 = sizeof(double) * ((size_t)stg::array8_stride(nd) * stg::kGroupsPerWarp - 8);   // <= 28.2 KB; the
+        // last group needs no trailing pad (8x8: 14,528 B + 1 KB reserved, 15 CTAs = 233,280 of the 233,472 B per SM)
         const unsigned grid = (unsigned)((a.n_arrays + stg::kGroupsPerWarp - 1) / stg::kGroupsPerWarp);
         const bool vec = nd % 2 == 0 && aligned(a.d_pattern, 16) && aligned(a.d_target, 16) && aligned(a.d_obs, 16) &&
                          (!a.d_final_obs || aligned(a.d_final_obs, 16));
