@@ -319,17 +319,21 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
     for (int q = 0; q < STG_NSTATS; ++q) st_v[q] = 0.0;
     if (valid) {
         const double fnd = (double)nd;
+        // x / nd. For a power-of-two device count known at compile time the quotient equals x * 2^-k bit for bit (an exact
+        // scaling; no result here is anywhere near the subnormal range), which takes four software FP64 divisions off the chain.
+        constexpr bool kPow2 = ND_T > 0 && (ND_T & (ND_T - 1)) == 0;
+        auto over_nd = [&](double x) { return kPow2 ? dmul(x, 1.0 / (double)(ND_T > 0 ? ND_T : 1)) : ddiv(x, fnd); };
         auto dots = [&](int i) { return dot_u(pattern + 3 * i, target + 3 * i); };
-        const double prev = ddiv(group_numpy_sum<ND_T>(gmask, l8, nd, dots), fnd);
+        const double prev = over_nd(group_numpy_sum<ND_T>(gmask, l8, nd, dots));
         const ArrayAction act = array_parse_action(p, act_raw);
         const double energy = group_apply_action<ND_T>(p, a.d_coupling, pattern, scratch, act, gmask, l8);
-        const double sim = ddiv(group_numpy_sum<ND_T>(gmask, l8, nd, dots), fnd);
+        const double sim = over_nd(group_numpy_sum<ND_T>(gmask, l8, nd, dots));
 #pragma unroll
         for (int i = l8; i < nd; i += kGroupLanes) scratch[i] = norm_u(pattern + 3 * i);
         __syncwarp(gmask);
-        const double mean = ddiv(group_numpy_sum<ND_T>(gmask, l8, nd, [&](int i) { return scratch[i]; }), fnd);
+        const double mean = over_nd(group_numpy_sum<ND_T>(gmask, l8, nd, [&](int i) { return scratch[i]; }));
         const double var = group_numpy_sum<ND_T>(gmask, l8, nd, [&](int i) { const double d = dadd(scratch[i], -mean); return dmul(d, d); });
-        const double sd = sqrt(ddiv(var, fnd));
+        const double sd = sqrt(over_nd(var));
         const bool success = sim >= p.success_threshold;
         const double reward = array_reward(p, success, sim, energy, dadd(sim, -prev), sd);
         const int step = step_prev + 1;
