@@ -142,7 +142,8 @@ __host__ __device__ inline int array8_stride(int nd) {
     const int per = 7 * nd + (nd & 1);
     return per + ((8 - per % 16) + 16) % 16;
 }
-constexpr int kArray8MinBlocks = 15;     // 14.3 KB of shared memory per CTA at 8x8: 15 CTAs resident, 4096 CTAs < 2 waves
+constexpr int kArray8MinBlocks = 14;     // 14.2 KB of shared memory per CTA at 8x8: ncu reports 14 resident CTAs per SM
+                                         // (shared-memory limit), so 4,096 CTAs are 1.98 waves
 
 template <int ND_T, typename F>
 __device__ __forceinline__ double group_numpy_sum(unsigned gmask, int l8, int n_rt, F v) {      // 8 <= n <= 128
@@ -487,7 +488,7 @@ extern "C" int stg_array_step_f64(const StgArrayStepArgs* args, void* stream) {
     if (nd >= 8 && nd <= 128 && !(a.flags & STG_F_ARRAY_ONE_WARP) && aligned(a.d_obs, 8) &&
         (!a.d_final_obs || aligned(a.d_final_obs, 8))) {
         const size_t smem8 = sizeof(double) * ((size_t)stg::array8_stride(nd) * stg::kGroupsPerWarp - 8);   // <= 28.2 KB; the
-        // last group needs no trailing pad (8x8: 14,528 B + 1 KB reserved, 15 CTAs = 233,280 of the 233,472 B per SM)
+        // last group needs no trailing pad (8x8: 14,528 B + 1 KB reserved per CTA; 14 CTAs fit the 233,472 B of an SM)
         const unsigned grid = (unsigned)((a.n_arrays + stg::kGroupsPerWarp - 1) / stg::kGroupsPerWarp);
         const bool vec = nd % 2 == 0 && aligned(a.d_pattern, 16) && aligned(a.d_target, 16) && aligned(a.d_obs, 16) &&
                          (!a.d_final_obs || aligned(a.d_final_obs, 16));
