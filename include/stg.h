@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 4
+#define STG_ABI_VERSION 5
 
 /* error codes */
 #define STG_OK 0
@@ -314,6 +314,8 @@ typedef struct StgRk45Args {
     int64_t n_envs;
     int32_t n_sets;
     uint32_t flags;
+    const int32_t* d_perm;           /* NULL or [n]: thread s integrates trajectory d_perm[s]; every array above stays indexed by
+                                      * the trajectory, as does the Philox id (sort by (parameter set, t_end) for homogeneous warps) */
 } StgRk45Args;
 
 int stg_llgs_rk45_f64(const StgRk45Args* args, void* stream);

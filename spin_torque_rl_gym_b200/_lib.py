@@ -107,7 +107,8 @@ class StgRk45Args(C.Structure):
                 ("d_n_rhs", C.c_void_p), ("d_status", C.c_void_p), ("d_t_reached", C.c_void_p), ("d_traj", C.c_void_p),
                 ("traj_stride", C.c_int64), ("d_noise", C.c_void_p), ("noise_stride", C.c_int64), ("rtol", C.c_double),
                 ("atol", C.c_double), ("max_step", C.c_double), ("max_attempts", C.c_int64), ("seed", C.c_uint64),
-                ("env_offset", C.c_uint64), ("n_envs", C.c_int64), ("n_sets", C.c_int32), ("flags", C.c_uint32)]
+                ("env_offset", C.c_uint64), ("n_envs", C.c_int64), ("n_sets", C.c_int32), ("flags", C.c_uint32),
+                ("d_perm", C.c_void_p)]
 
 
 ARRAY_MODES = {"individual": 0, "row": 1, "column": 2, "global": 3}
@@ -174,8 +175,8 @@ SYMBOLS = {
     "stg_probe_fma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
-ABI_VERSION = 4          # include/stg.h STG_ABI_VERSION (2: sampled current / field grids; 3: replicated statistics buffer;
-                         # 4: zero-row counters of stg_device_field_f64 / stg_device_resistance_f64)
+ABI_VERSION = 5          # include/stg.h STG_ABI_VERSION (2: sampled current / field grids; 3: replicated statistics buffer;
+                         # 4: zero-row counters of stg_device_field_f64 / stg_device_resistance_f64; 5: StgRk45Args.d_perm)
 _LIB: Optional[C.CDLL] = None
 
 

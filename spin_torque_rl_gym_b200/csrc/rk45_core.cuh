@@ -154,10 +154,34 @@ STG_HD double pow_m02(double en) { return exp(-0.2 * log(en)); }
 STG_HD V3 vabs_max(V3 a, V3 b) { return {fmax(fabs(a.x), fabs(b.x)), fmax(fabs(a.y), fabs(b.y)), fmax(fabs(a.z), fabs(b.z))}; }
 
 // One trajectory of LLGSSolver.solve. Returns through the StgRk45Args output arrays of env e.
-STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
-    using T = Rk45Tableau;
-    const StgLlgParams& q = a.d_table[a.d_param_index ? a.d_param_index[e] : 0];
+// One trajectory's integration state. rk45_init / rk45_attempt / rk45_finish are the three phases of SciPy's solve_ivp loop
+// for one trajectory; rk45_body chains them (host build, one-trajectory-per-thread kernel), the refill kernel interleaves them
+// across trajectories so that a lane whose trajectory has finished starts the next one instead of idling.
+struct Rk45State {
     LlgRhs f;
+    V3 y, fk;
+    double t, tb, h_abs, min_step;
+    double* traj;
+    int64_t e, attempts;
+    int n_acc, n_rej, status, overflow;
+    bool new_step, rejected;
+    STG_HD bool running() const { return t != tb && status == 0; }
+};
+
+STG_HD void rk45_record(const StgRk45Args& a, Rk45State& S, int row, double tt, V3 yy) {
+    if (!S.traj) return;
+    if (row >= a.traj_stride) { S.overflow = 2; return; }   // keeps integrating; only the recording stops
+    const double n = sqrt(dot3(yy, yy));
+    const V3 m = {yy.x / n, yy.y / n, yy.z / n};            // :152-153
+    double en, tq;
+    S.f.diagnostics(tt, m, en, tq);
+    double* r = S.traj + 6 * (int64_t)row;
+    r[0] = tt; r[1] = m.x; r[2] = m.y; r[3] = m.z; r[4] = en; r[5] = tq;
+}
+
+STG_HD void rk45_init(const StgRk45Args& a, int64_t e, Rk45State& S) {
+    const StgLlgParams& q = a.d_table[a.d_param_index ? a.d_param_index[e] : 0];
+    LlgRhs& f = S.f;
     f.p = &q;
     f.load();
     f.J = a.d_current ? a.d_current[e] : 0.0;
@@ -178,105 +202,116 @@ STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
     f.noise_cap = a.noise_stride;
     f.n_eval = 0;
 
-    const double t0 = 0.0, tb = a.d_t_end[e];
+    const double t0 = 0.0;
+    S.e = e;
+    S.tb = a.d_t_end[e];
     const double rtol = a.rtol, atol = a.atol, max_step = a.max_step;
     V3 y = {a.d_m0[3 * e], a.d_m0[3 * e + 1], a.d_m0[3 * e + 2]};
     {   // m_initial / ||m_initial|| (physics/llgs_solver.py:75)
         const double n0 = sqrt(dot3(y, y));
         y = {y.x / n0, y.y / n0, y.z / n0};
     }
-    double t = t0;
-    int n_acc = 0, n_rej = 0, status = 0, overflow = 0;
-    double* traj = a.d_traj ? a.d_traj + (int64_t)e * a.traj_stride * 6 : nullptr;
-    auto record = [&](int row, double tt, V3 yy) {
-        if (!traj) return;
-        if (row >= a.traj_stride) { overflow = 2; return; }   // keeps integrating; only the recording stops
-        const double n = sqrt(dot3(yy, yy));
-        const V3 m = {yy.x / n, yy.y / n, yy.z / n};            // :152-153
-        double en, tq;
-        f.diagnostics(tt, m, en, tq);
-        double* r = traj + 6 * (int64_t)row;
-        r[0] = tt; r[1] = m.x; r[2] = m.y; r[3] = m.z; r[4] = en; r[5] = tq;
-    };
-    record(0, t, y);
-
-    if (tb > t0) {
-        V3 fk = f(t, y);                                        // rk.py:94
+    S.y = y;
+    S.t = t0;
+    S.n_acc = 0; S.n_rej = 0; S.status = 0; S.overflow = 0;
+    S.attempts = 0;
+    S.new_step = true; S.rejected = false;
+    S.min_step = 0.0;
+    S.h_abs = 0.0;
+    S.fk = V3{0.0, 0.0, 0.0};
+    S.traj = a.d_traj ? a.d_traj + (int64_t)e * a.traj_stride * 6 : nullptr;
+    rk45_record(a, S, 0, S.t, y);
+    if (S.tb > t0) {
+        const V3 fk = f(S.t, y);                                // rk.py:94
         // select_initial_step (common.py:68-133), order = 4
-        double h_abs;
-        {
-            const double interval = fabs(tb - t0);
-            const V3 sc = {atol + fabs(y.x) * rtol, atol + fabs(y.y) * rtol, atol + fabs(y.z) * rtol};
-            const double d0 = rms3({y.x / sc.x, y.y / sc.y, y.z / sc.z});
-            const double d1 = rms3({fk.x / sc.x, fk.y / sc.y, fk.z / sc.z});
-            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-            h0 = fmin(h0, interval);
-            const V3 y1 = y + h0 * fk;
-            const V3 f1 = f(t0 + h0, y1);
-            const double d2 = rms3({(f1.x - fk.x) / sc.x, (f1.y - fk.y) / sc.y, (f1.z - fk.z) / sc.z}) / h0;
-            double h1;
-            if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
-            else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
-            h_abs = fmin(fmin(100.0 * h0, h1), fmin(interval, max_step));
-        }
-        // solve_ivp main loop: step until t == t_bound (ivp.py), RungeKutta._step_impl (rk.py:111-167).
-        // SciPy nests "while not step_accepted" inside the stepping loop; here ONE flat loop performs one attempt per iteration
-        // for every lane that is still integrating, so the lanes of a warp stay converged on the six RHS evaluations whether
-        // their previous attempt was accepted or rejected (nested loops make the whole warp pay for every lane's rejection).
-        const int64_t max_attempts = a.max_attempts > 0 ? a.max_attempts : 1000000;
-        int64_t attempts = 0;
-        bool new_step = true, rejected = false;
-        double min_step = 0.0;
-        while (t != tb && status == 0) {
-            if (new_step) {                                   // head of _step_impl
-                min_step = 10.0 * ulp_above(t);
-                if (h_abs > max_step) h_abs = max_step;
-                else if (h_abs < min_step) h_abs = min_step;
-                rejected = false;
-                new_step = false;
-            }
-            if (h_abs < min_step) { status |= 1; break; }     // TOO_SMALL_STEP
-            if (++attempts > max_attempts) { status |= 4; break; }
-            double h = h_abs;
-            double t_new = t + h;
-            if (t_new - tb > 0.0) t_new = tb;
-            h = t_new - t;
-            h_abs = fabs(h);
-            // rk_step (rk.py:14-72)
-            const V3 k1 = fk;
-            const V3 k2 = f(t + T::c2 * h, y + h * (T::a21 * k1));
-            const V3 k3 = f(t + T::c3 * h, y + h * (T::a31 * k1 + T::a32 * k2));
-            const V3 k4 = f(t + T::c4 * h, y + h * (T::a41 * k1 + T::a42 * k2 + T::a43 * k3));
-            const V3 k5 = f(t + T::c5 * h, y + h * (T::a51 * k1 + T::a52 * k2 + T::a53 * k3 + T::a54 * k4));
-            const V3 k6 = f(t + h, y + h * (T::a61 * k1 + T::a62 * k2 + T::a63 * k3 + T::a64 * k4 + T::a65 * k5));
-            const V3 y_new = y + h * (T::b1 * k1 + T::b3 * k3 + T::b4 * k4 + T::b5 * k5 + T::b6 * k6);
-            const V3 f_new = f(t + h, y_new);
-            const V3 err = h * (T::e1 * k1 + T::e3 * k3 + T::e4 * k4 + T::e5 * k5 + T::e6 * k6 + T::e7 * f_new);
-            const V3 mx = vabs_max(y, y_new);
-            const double en = rms3({err.x / (atol + mx.x * rtol), err.y / (atol + mx.y * rtol), err.z / (atol + mx.z * rtol)});
-            if (en < 1.0) {
-                double factor = (en == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow_m02(en));
-                if (rejected) factor = fmin(1.0, factor);
-                h_abs *= factor;
-                t = t_new; y = y_new; fk = f_new;
-                ++n_acc;
-                new_step = true;
-                record(n_acc, t, y);
-            } else if (en >= 1.0) {
-                h_abs *= fmax(0.2, 0.9 * pow_m02(en));
-                rejected = true;
-                ++n_rej;
-            } else {               // NaN error norm: SciPy would never terminate; flag and stop
-                status |= 8;
-            }
-        }
+        const double interval = fabs(S.tb - t0);
+        const V3 sc = {atol + fabs(y.x) * rtol, atol + fabs(y.y) * rtol, atol + fabs(y.z) * rtol};
+        const double d0 = rms3({y.x / sc.x, y.y / sc.y, y.z / sc.z});
+        const double d1 = rms3({fk.x / sc.x, fk.y / sc.y, fk.z / sc.z});
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = fmin(h0, interval);
+        const V3 y1 = y + h0 * fk;
+        const V3 f1 = f(t0 + h0, y1);
+        const double d2 = rms3({(f1.x - fk.x) / sc.x, (f1.y - fk.y) / sc.y, (f1.z - fk.z) / sc.z}) / h0;
+        double h1;
+        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+        else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+        S.h_abs = fmin(fmin(100.0 * h0, h1), fmin(interval, max_step));
+        S.fk = fk;
+    } else {
+        S.tb = S.t;                                             // t_end <= 0: nothing to integrate (running() is false)
     }
-    a.d_y_out[3 * e] = y.x; a.d_y_out[3 * e + 1] = y.y; a.d_y_out[3 * e + 2] = y.z;
-    if (a.d_n_accepted) a.d_n_accepted[e] = n_acc;
-    if (a.d_n_rejected) a.d_n_rejected[e] = n_rej;
-    if (a.d_n_rhs) a.d_n_rhs[e] = f.n_eval;
-    if (a.d_status) a.d_status[e] = status | overflow;
-    if (a.d_t_reached) a.d_t_reached[e] = t;
+}
+
+// ONE attempted step of a running trajectory: solve_ivp main loop (ivp.py), RungeKutta._step_impl (rk.py:111-167).
+// SciPy nests "while not step_accepted" inside the stepping loop; here one flat loop performs one attempt per iteration for
+// every lane that is still integrating, so the lanes of a warp stay converged on the six RHS evaluations whether their previous
+// attempt was accepted or rejected (nested loops make the whole warp pay for every lane's rejection).
+STG_HD void rk45_attempt(const StgRk45Args& a, Rk45State& S) {
+    using T = Rk45Tableau;
+    const double rtol = a.rtol, atol = a.atol, max_step = a.max_step;
+    const int64_t max_attempts = a.max_attempts > 0 ? a.max_attempts : 1000000;
+    LlgRhs& f = S.f;
+    if (S.new_step) {                                   // head of _step_impl
+        S.min_step = 10.0 * ulp_above(S.t);
+        if (S.h_abs > max_step) S.h_abs = max_step;
+        else if (S.h_abs < S.min_step) S.h_abs = S.min_step;
+        S.rejected = false;
+        S.new_step = false;
+    }
+    if (S.h_abs < S.min_step) { S.status |= 1; return; }     // TOO_SMALL_STEP
+    if (++S.attempts > max_attempts) { S.status |= 4; return; }
+    const double t = S.t;
+    const V3 y = S.y;
+    double h = S.h_abs;
+    double t_new = t + h;
+    if (t_new - S.tb > 0.0) t_new = S.tb;
+    h = t_new - t;
+    S.h_abs = fabs(h);
+    // rk_step (rk.py:14-72)
+    const V3 k1 = S.fk;
+    const V3 k2 = f(t + T::c2 * h, y + h * (T::a21 * k1));
+    const V3 k3 = f(t + T::c3 * h, y + h * (T::a31 * k1 + T::a32 * k2));
+    const V3 k4 = f(t + T::c4 * h, y + h * (T::a41 * k1 + T::a42 * k2 + T::a43 * k3));
+    const V3 k5 = f(t + T::c5 * h, y + h * (T::a51 * k1 + T::a52 * k2 + T::a53 * k3 + T::a54 * k4));
+    const V3 k6 = f(t + h, y + h * (T::a61 * k1 + T::a62 * k2 + T::a63 * k3 + T::a64 * k4 + T::a65 * k5));
+    const V3 y_new = y + h * (T::b1 * k1 + T::b3 * k3 + T::b4 * k4 + T::b5 * k5 + T::b6 * k6);
+    const V3 f_new = f(t + h, y_new);
+    const V3 err = h * (T::e1 * k1 + T::e3 * k3 + T::e4 * k4 + T::e5 * k5 + T::e6 * k6 + T::e7 * f_new);
+    const V3 mx = vabs_max(y, y_new);
+    const double en = rms3({err.x / (atol + mx.x * rtol), err.y / (atol + mx.y * rtol), err.z / (atol + mx.z * rtol)});
+    if (en < 1.0) {
+        double factor = (en == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow_m02(en));
+        if (S.rejected) factor = fmin(1.0, factor);
+        S.h_abs *= factor;
+        S.t = t_new; S.y = y_new; S.fk = f_new;
+        ++S.n_acc;
+        S.new_step = true;
+        rk45_record(a, S, S.n_acc, S.t, S.y);
+    } else if (en >= 1.0) {
+        S.h_abs *= fmax(0.2, 0.9 * pow_m02(en));
+        S.rejected = true;
+        ++S.n_rej;
+    } else {               // NaN error norm: SciPy would never terminate; flag and stop
+        S.status |= 8;
+    }
+}
+
+STG_HD void rk45_finish(const StgRk45Args& a, const Rk45State& S) {
+    const int64_t e = S.e;
+    a.d_y_out[3 * e] = S.y.x; a.d_y_out[3 * e + 1] = S.y.y; a.d_y_out[3 * e + 2] = S.y.z;
+    if (a.d_n_accepted) a.d_n_accepted[e] = S.n_acc;
+    if (a.d_n_rejected) a.d_n_rejected[e] = S.n_rej;
+    if (a.d_n_rhs) a.d_n_rhs[e] = S.f.n_eval;
+    if (a.d_status) a.d_status[e] = S.status | S.overflow;
+    if (a.d_t_reached) a.d_t_reached[e] = S.t;
+}
+
+STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
+    Rk45State S;
+    rk45_init(a, e, S);
+    while (S.running()) rk45_attempt(a, S);
+    rk45_finish(a, S);
 }
 
 }  // namespace stg

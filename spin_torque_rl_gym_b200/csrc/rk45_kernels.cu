@@ -1,5 +1,8 @@
-// rk45_kernels.cu — K2 launch + C-ABI entry (see rk45_core.cuh). One trajectory per thread; lanes whose trajectory has
-// finished idle until the warp's slowest lane is done (step counts differ by a few percent within a device class).
+// rk45_kernels.cu — K2 launch + C-ABI entry (see rk45_core.cuh). One trajectory per thread; lanes whose trajectory has finished
+// idle until the warp's slowest lane is done, so the caller passes a permutation that sorts the batch by (parameter set, t_end)
+// and warps hold trajectories of similar length. A resident grid whose lanes pick up the next trajectory when theirs ends was
+// measured instead (262,144 trajectories): 8 % slower on a uniform batch, 10 % faster on t_end ~ U(0.05, 1) - with ~3.5
+// trajectories per resident thread the tail of every CTA costs a quarter of its lifetime - and dropped in favour of the sort.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -15,8 +18,11 @@ namespace stg {
 #define STG_RK45_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(64, STG_RK45_MINBLOCKS) llgs_rk45_kernel(const __grid_constant__ StgRk45Args a) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < a.n_envs) rk45_body(a, e);
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.n_envs) return;
+    // d_perm (optional): thread `slot` integrates trajectory perm[slot]. Inputs, outputs and the Philox id stay indexed by the
+    // trajectory, so a permutation that sorts by (parameter set, t_end) makes the lanes of a warp homogeneous without moving data.
+    rk45_body(a, a.d_perm ? (int64_t)a.d_perm[slot] : slot);
 }
 
 }  // namespace stg
@@ -31,7 +37,7 @@ extern "C" int stg_llgs_rk45_f64(const StgRk45Args* args, void* stream) {
     if ((a.flags & STG_F_THERMAL_INJECT) && (!a.d_noise || a.noise_stride <= 0)) return STG_E_NULL;
     if (a.d_traj && a.traj_stride <= 0) return STG_E_SIZE;
     if (a.n_envs == 0) return STG_OK;
-    const unsigned grid = (unsigned)((a.n_envs + 63) / 64);
-    stg::llgs_rk45_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(a);
+    const int64_t ctas = (a.n_envs + 63) / 64;
+    stg::llgs_rk45_kernel<<<(unsigned)ctas, 64, 0, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }

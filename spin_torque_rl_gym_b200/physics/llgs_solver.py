@@ -39,7 +39,10 @@ def _pulse_from_callable(fn: Callable[[float], float], t_end: float) -> Tuple[fl
 
 class LLGSSolver:
     def __init__(self, method: str = "RK45", rtol: float = 1e-6, atol: float = 1e-9, max_step: float = 1e-12,
-                 gamma: float = 2.21e5, device: Any = "cuda", device_type: str = "stt_mram"):
+                 gamma: float = 2.21e5, device: Any = "cuda", device_type: str = "stt_mram", sort_trajectories: bool = True):
+        """`sort_trajectories`: batches of >= 64 trajectories are launched through a permutation sorted by (parameter set,
+        t_end descending) so the lanes of a warp integrate trajectories of similar length (StgRk45Args.d_perm; results are
+        identical, inputs and outputs are not moved)."""
         if method != "RK45":
             raise ValueError("only method='RK45' (SciPy's default Dormand-Prince pair) is implemented on the GPU")
         torch = _lib.require_cuda()
@@ -49,6 +52,7 @@ class LLGSSolver:
         self.device_type = device_type
         self._device = torch.device(device)
         self._lib = _lib.load()
+        self.sort_trajectories = bool(sort_trajectories)
 
     # -----------------------------------------------------------------------------------------------------------------
     def solve_batch(self, m_initial, t_end, device_params: Union[Dict[str, Any], Sequence[Dict[str, Any]]], current=0.0,
@@ -79,27 +83,22 @@ class LLGSSolver:
                    for t, p in zip(types, plist)]
         table = torch.from_numpy(_params.llg_table(structs)).to(dev)
         pidx = None
-        order = None
         if param_index is not None:
             pidx = torch.as_tensor(param_index, dtype=torch.int32).to(dev).contiguous()
-            philox = thermal_noise and noise is None      # Philox counters use the trajectory index: keep the caller's order
-            if len(structs) > 1 and n >= 64 and not philox:
-                # group trajectories of the same parameter set into the same warps (interleaved device classes leave most
-                # lanes of a warp idle); inputs are gathered through `order`, outputs scattered back below
-                order = torch.argsort(pidx, stable=True)
-                pidx = pidx[order].contiguous()
-                m0 = m0[order].contiguous()
         elif len(structs) != 1:
             raise ValueError("several parameter sets need a param_index")
-        if order is not None:
-            _arr = arr
-
-            def arr(x, shape, fill=None):                      # noqa: F811 - per-trajectory inputs follow the grouping
-                t = _arr(x, shape, fill)
-                return t if t is None else t[order].contiguous()
         a = _lib.StgRk45Args()
         t_end_t = arr(t_end, (n,))
         keep = [table, pidx, m0, t_end_t]
+        if self.sort_trajectories and n >= 64:
+            # lanes whose trajectory has ended idle until the slowest lane of the warp is done: launch in an order that puts
+            # trajectories of the same parameter set and similar length into the same warp (longest first)
+            perm = torch.argsort(t_end_t, descending=True, stable=True)
+            if pidx is not None and len(structs) > 1:
+                perm = perm[torch.argsort(pidx[perm], stable=True)]
+            perm = perm.to(torch.int32).contiguous()
+            keep.append(perm)
+            a.d_perm = perm.data_ptr()
         a.d_table, a.d_param_index, a.d_m0, a.d_t_end = table.data_ptr(), _lib.ptr(pidx), m0.data_ptr(), t_end_t.data_ptr()
         for name, val, shape in (("d_current", current, (n,)), ("d_t_pulse", t_pulse, (n,)),
                                  ("d_happ", applied_field, (n, 3)), ("d_voltage", voltage, (n,))):
@@ -137,10 +136,6 @@ class LLGSSolver:
         with torch.cuda.device(dev):
             _lib.check(self._lib.stg_llgs_rk45_f64(C.byref(a), torch.cuda.current_stream(dev).cuda_stream),
                        "stg_llgs_rk45_f64")
-        if order is not None:
-            inv = torch.empty_like(order)
-            inv[order] = torch.arange(n, device=dev)
-            out = {k: v[inv].contiguous() for k, v in out.items()}
         out["m"] = out["y"] / out["y"].norm(dim=1, keepdim=True)
         out["success"] = out["status"] == 0
         self._keep = keep

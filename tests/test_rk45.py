@@ -190,3 +190,41 @@ def test_cuda_sot_vcma_mix_batch(cuda_device):
     assert torch.equal(big["t_reached"], torch.as_tensor(np.tile(t_end, reps)).to(cuda_device))
     # the raw end state is not renormalised (sol.y[:, -1]); the SOT field-like torque is not tangential, so |y| drifts (up to ~20 % here)
     assert float((big["y"].norm(dim=1) - 1).abs().max()) < 0.5 and bool(torch.isfinite(big["y"]).all())
+
+
+@pytest.mark.gpu
+def test_cuda_rk45_sorted_launch_identical_to_caller_order(cuda_device):
+    """Large ragged batches are launched through a permutation sorted by (parameter set, t_end) so warps hold trajectories of
+    similar length (StgRk45Args.d_perm). Which thread integrates a trajectory must not matter: every output equals the
+    caller-order launch bit for bit, also with Philox noise (counters come from the trajectory id) and recorded rows."""
+    import torch
+    from spin_torque_rl_gym_b200.physics import LLGSSolver
+    n = 256
+    sot, vcma, m0, pidx, cur, volt, happ, t_end = _mix_setup(n, seed=21)
+    N = 262144
+    reps = N // n
+    rng = np.random.default_rng(21)
+    kw = dict(current=np.tile(cur, reps) * rng.uniform(0.5, 1.5, N), applied_field=np.tile(happ, (reps, 1)),
+              voltage=np.tile(volt, reps) * rng.uniform(0.5, 1.0, N), param_index=np.tile(pidx, reps),
+              device_type=["sot_mram", "vcma_mram"])
+    M0 = rng.normal(size=(N, 3))
+    T = np.tile(t_end, reps) * rng.uniform(0.3, 1.0, N)    # ragged trajectory lengths
+    a = LLGSSolver(device=cuda_device).solve_batch(M0, T, [sot, vcma], **kw)
+    b = LLGSSolver(device=cuda_device, sort_trajectories=False).solve_batch(M0, T, [sot, vcma], **kw)
+    for k in ("y", "n_accepted", "n_rejected", "n_rhs", "status", "t_reached"):
+        assert torch.equal(a[k], b[k]), k
+    spread = a["n_accepted"].float()
+    assert float(spread.max()) > 1.5 * float(spread.min()) and bool(a["success"].all())       # the batch really is ragged
+    # thermal noise from the in-kernel stream + recorded rows, 90,112 short trajectories
+    N2 = 90112
+    sel = slice(0, N2)
+    kw2 = {k: (v[sel] if isinstance(v, np.ndarray) else v) for k, v in kw.items()}
+    T2 = T[sel] * 0.15
+    c = LLGSSolver(device=cuda_device).solve_batch(M0[sel], T2, [sot, vcma], thermal_noise=True, temperature=300.0, seed=5,
+                                                   return_trajectory=True, **kw2)
+    d = LLGSSolver(device=cuda_device, sort_trajectories=False).solve_batch(M0[sel], T2, [sot, vcma], thermal_noise=True,
+                                                                            temperature=300.0, seed=5, return_trajectory=True,
+                                                                            **kw2)
+    for k in ("y", "n_accepted", "n_rejected", "n_rhs", "status", "traj"):
+        assert torch.equal(c[k], d[k]), k
+    assert not torch.equal(c["y"], LLGSSolver(device=cuda_device).solve_batch(M0[sel], T2, [sot, vcma], **kw2)["y"])

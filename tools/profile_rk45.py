@@ -22,7 +22,9 @@ z = torch.zeros(n, dtype=torch.float64, device=dev)
 cur = torch.where(pidx == 0, torch.from_numpy(rng.uniform(-3e11, 3e11, n)).to(dev), z)
 volt = torch.where(pidx == 1, torch.from_numpy(rng.uniform(-2.5, 2.5, n)).to(dev), z)
 t_end = torch.full((n,), t, dtype=torch.float64, device=dev)
-solver = LLGSSolver(device=dev)
+if os.environ.get("RK_RAGGED", "0") == "1":          # ragged trajectory lengths: t_end ~ U(0.05, 1) * t
+    t_end = t_end * torch.from_numpy(rng.uniform(0.05, 1.0, n)).to(dev)
+solver = LLGSSolver(device=dev, sort_trajectories=os.environ.get("RK_SORT", "1") == "1")
 for _ in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -31,4 +33,6 @@ for _ in range(3):
     e1.record()
     torch.cuda.synchronize()
 att = float((r["n_accepted"] + r["n_rejected"]).sum())
-print(f"rk45 n={n}: {e0.elapsed_time(e1):.3f} ms, {att / n:.1f} attempts/env, {att / e0.elapsed_time(e1) / 1e6:.3f} G attempts/s")
+amax, amin = int((r["n_accepted"] + r["n_rejected"]).max()), int((r["n_accepted"] + r["n_rejected"]).min())
+print(f"sort={solver.sort_trajectories} ragged={os.environ.get('RK_RAGGED', '0')} attempts min/max {amin}/{amax}; "
+      f"rk45 n={n}: {e0.elapsed_time(e1):.3f} ms, {att / n:.1f} attempts/env, {att / e0.elapsed_time(e1) / 1e6:.3f} G attempts/s")
