@@ -7,6 +7,11 @@
 
 namespace stg {
 
+#ifndef STG_SUBSTEP_UNROLL
+#define STG_SUBSTEP_UNROLL 2      // measured in stt_kernels.cu (STG_MINBLOCKS_NOISE_F32)
+#endif
+constexpr int kSubstepUnroll = STG_SUBSTEP_UNROLL;   // unroll factor of the RK4 substep loop of the FP32 fast path (tuning)
+
 constexpr int kObs = 12;
 #ifndef STG_RESYNC_MASK
 #define STG_RESYNC_MASK 15   // exact FP64 renormalisation of the master every 16 substeps (fast path)
@@ -91,6 +96,7 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
             }
         };
         int i = 0;
+#pragma unroll kSubstepUnroll
         for (; i < i_safe; ++i) one(i, false);
         for (; i < n; ++i) one(i, true);
         guard_normalise<float>(s.st, guard);

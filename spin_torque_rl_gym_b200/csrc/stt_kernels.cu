@@ -26,7 +26,14 @@ namespace stg {
 #define STG_MINBLOCKS_DET 12    // no-noise variants: 80 registers, 24 warps/SM measured best (profiles/)
 #endif
 #ifndef STG_MINBLOCKS_NOISE
-#define STG_MINBLOCKS_NOISE 1   // thermal variants: let ptxas keep the 12 Gaussians + Philox state in registers
+#define STG_MINBLOCKS_NOISE 1   // FP64-stage thermal variants: let ptxas keep the 12 Gaussians + Philox state in registers
+#endif
+#ifndef STG_MINBLOCKS_NOISE_F32
+// FP32 thermal variants: the substep loop is unrolled by two (STG_SUBSTEP_UNROLL, stt_env_core.cuh) so that the Philox rounds of
+// substep i+1 can be scheduled under the dependent stage chain of substep i; unrolled, ptxas would take 146 registers (14
+// warps/SM), so the kernel is held at 128 (16 warps/SM, no spill). 1M envs x 999 substeps: 14.17 ms plain, 13.94 ms unrolled at
+// 146 registers, 13.72 ms unrolled at 128, 14.11 ms unrolled by four.
+#define STG_MINBLOCKS_NOISE_F32 8
 #endif
 constexpr int kBlock = STG_BLOCK;   // 64: 65,536 envs -> 1024 CTAs = 6.9 per SM, balanced to 1.2 % on 148 SMs
 
@@ -48,7 +55,8 @@ __device__ __forceinline__ void store_row(float* dst, const float* o) {
 }
 
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>
-__global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_MINBLOCKS_DET : STG_MINBLOCKS_NOISE) stt_env_step_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_MINBLOCKS_DET : (sizeof(R) == 4 ? STG_MINBLOCKS_NOISE_F32 : STG_MINBLOCKS_NOISE))
+stt_env_step_kernel(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) float s_obs[kBlock * kObs];
     const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool active = slot < a.n_envs;
