@@ -447,6 +447,11 @@ int stg_stats_reduce_f64(const double* d_reward, const double* d_step_energy, co
 /* Column sums of the replicated statistics buffer of the step kernels: d_out[q] (+)= sum_r d_replicas[r][q], q < STG_NSTATS
  * (accumulate != 0 adds to d_out, 0 overwrites). d_out is what one all-reduce(SUM) per rollout exchanges between ranks. */
 int stg_stats_fold_f64(const double* d_replicas, double* d_out, int32_t accumulate, void* stream);
+/* Device-side address of a pinned, mapped host allocation. Every OUTPUT array of the step / reset entry points (obs,
+ * final_obs, reward, terminated, truncated, ...) is write-only for the kernels, so it may live in pinned host memory: the
+ * kernels then deliver results over PCIe while they run (posted writes, overlapped), instead of a serialised device-to-host
+ * copy after the launch. The caller synchronises the stream before reading. */
+int stg_host_device_pointer(void* host_ptr, void** device_ptr);
 
 /* VectorizedMagneticsOperations (utils/vectorized_operations.py:288-393), n rows of 3 doubles, NumPy's operation order:
  *   CROSS           out[n][3] = a x b                              (batch_cross_product :292-303)

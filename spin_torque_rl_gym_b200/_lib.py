@@ -168,6 +168,7 @@ SYMBOLS = {
     "stg_stats_reduce_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int64, C.c_void_p, C.c_void_p]),
     "stg_stats_fold_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "stg_host_device_pointer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "stg_vec3_op_f64": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_void_p]),
     "stg_phase_diagram_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p,
@@ -249,5 +250,14 @@ def device_guard(torch, device):
 
 
 def ptr(t) -> Optional[int]:
-    """Device pointer of a torch tensor (None -> NULL)."""
-    return None if t is None else t.data_ptr()
+    """Device pointer of a torch tensor (None -> NULL). A pinned CPU tensor yields the device-side address of its mapped
+    host memory (kernels may write their outputs there directly)."""
+    if t is None:
+        return None
+    if t.device.type == "cpu":
+        if not t.is_pinned():
+            raise StgError("a CPU tensor handed to a kernel must be pinned")
+        out = C.c_void_p()
+        check(load().stg_host_device_pointer(t.data_ptr(), C.byref(out)), "stg_host_device_pointer")
+        return out.value
+    return t.data_ptr()

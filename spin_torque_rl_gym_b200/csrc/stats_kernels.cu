@@ -89,3 +89,10 @@ extern "C" int stg_stats_fold_f64(const double* d_replicas, double* d_out, int32
     stg::stats_fold_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_replicas, d_out, accumulate);
     return (int)cudaGetLastError();
 }
+
+// Device-side address of a pinned (page-locked, mapped) host allocation: what a kernel must be given to write its outputs
+// straight into host memory (under unified addressing it equals the host pointer, but that is the runtime's call to make).
+extern "C" int stg_host_device_pointer(void* host_ptr, void** device_ptr) {
+    if (!host_ptr || !device_ptr) return STG_E_NULL;
+    return (int)cudaHostGetDevicePointer(device_ptr, host_ptr, 0);
+}

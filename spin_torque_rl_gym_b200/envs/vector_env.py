@@ -59,6 +59,7 @@ class SpinTorqueVectorEnv:
         sort_by_substeps: Union[str, bool] = "auto",
         collect_stats: bool = True,
         pair_kernel: bool = True,
+        host_outputs: bool = False,
     ):
         torch = _lib.require_cuda()
         self._torch = torch
@@ -100,6 +101,10 @@ class SpinTorqueVectorEnv:
         self.env_offset = int(env_offset)
         self.collect_stats = bool(collect_stats)
         self.pair_kernel = bool(pair_kernel)       # FP32 / e=z / RK4: two envs per thread on packed FFMA2 (same results)
+        # host_outputs: obs / final_obs / reward / terminated / truncated live in PINNED HOST memory and the kernels write
+        # them there directly (posted PCIe writes while the kernel runs) - for consumers on the CPU (SB3, NumPy policies).
+        # step() then returns CPU tensors and synchronises the stream before returning. Default: CUDA tensors, no sync.
+        self.host_outputs = bool(host_outputs)
         if rng_seed is None:
             rng_seed = 0 if seed is None else int(seed)
         self.rng_seed = int(rng_seed) & 0xFFFFFFFFFFFFFFFF
@@ -167,11 +172,15 @@ class SpinTorqueVectorEnv:
             self._last_action = torch.zeros(2, N, dtype=f64, device=dev)
             self._step_count = torch.zeros(N, dtype=i32, device=dev)
             self._episode = torch.zeros(N, dtype=i32, device=dev)
-            self._obs = torch.zeros(N, _lib.OBS_DIM, dtype=torch.float32, device=dev)
-            self._final_obs = torch.zeros(N, _lib.OBS_DIM, dtype=torch.float32, device=dev)
-            self._reward = torch.zeros(N, dtype=f64, device=dev)
-            self._terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
-            self._truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
+            def out_buf(shape, dtype):
+                if self.host_outputs:
+                    return torch.zeros(shape, dtype=dtype).pin_memory()
+                return torch.zeros(shape, dtype=dtype, device=dev)
+            self._obs = out_buf((N, _lib.OBS_DIM), torch.float32)
+            self._final_obs = out_buf((N, _lib.OBS_DIM), torch.float32)
+            self._reward = out_buf((N,), f64)
+            self._terminated = out_buf((N,), torch.uint8)
+            self._truncated = out_buf((N,), torch.uint8)
             self._step_energy = torch.zeros(N, dtype=f64, device=dev)
             self._n_sub = torch.zeros(N, dtype=i32, device=dev)
             self._status = torch.zeros(N, dtype=i32, device=dev)
@@ -219,14 +228,14 @@ class SpinTorqueVectorEnv:
         a.d_param_index = _lib.ptr(self._param_index)
         a.state = self._state_struct()
         o = a.out
-        o.obs = self._obs.data_ptr()
-        o.reward = self._reward.data_ptr()
-        o.terminated = self._terminated.data_ptr()
-        o.truncated = self._truncated.data_ptr()
+        o.obs = _lib.ptr(self._obs)
+        o.reward = _lib.ptr(self._reward)
+        o.terminated = _lib.ptr(self._terminated)
+        o.truncated = _lib.ptr(self._truncated)
         o.step_energy = self._step_energy.data_ptr()
         o.n_sub = self._n_sub.data_ptr()
         o.status = self._status.data_ptr()
-        o.final_obs = self._final_obs.data_ptr() if self.autoreset else None
+        o.final_obs = _lib.ptr(self._final_obs) if self.autoreset else None
         o.stats = self._stats.data_ptr() if self.collect_stats else None
         a.d_target_table = self._target_table.data_ptr()
         a.n_targets = self._target_table.shape[0]
@@ -280,7 +289,7 @@ class SpinTorqueVectorEnv:
             a.d_target0 = t0.data_ptr()
         a.d_target_table = self._target_table.data_ptr()
         a.n_targets = self._target_table.shape[0]
-        a.d_obs = self._obs.data_ptr()
+        a.d_obs = _lib.ptr(self._obs)
         a.seed = self.rng_seed
         a.env_offset = self.env_offset
         a.n_envs = N
@@ -290,6 +299,7 @@ class SpinTorqueVectorEnv:
         self.gpu_launches += 1
         self._needs_reset = False
         self._keep = keep
+        self._sync_host_outputs()
         return self._obs, {}
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -365,7 +375,14 @@ class SpinTorqueVectorEnv:
         }
         if self.autoreset:
             info["final_observation"] = self._final_obs
+        self._sync_host_outputs()
         return self._obs, self._reward, self._terminated_b, self._truncated_b, info
+
+    def _sync_host_outputs(self) -> None:
+        """host_outputs: the kernel wrote obs / reward / flags into pinned host memory; they may be read once the stream has
+        drained (not during CUDA-graph capture, where the caller synchronises after replay)."""
+        if self.host_outputs and not self._torch.cuda.is_current_stream_capturing():
+            self._torch.cuda.current_stream(self.device).synchronize()
 
     # ------------------------------------------------------------------------------------------------------------------
     @property
