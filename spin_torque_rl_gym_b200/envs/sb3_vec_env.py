@@ -50,13 +50,15 @@ class SB3VecEnvAdapter(_VecEnvBase):
     def step_wait(self):
         obs, rew, term, trunc, info = self.env.step(self._actions)
         obs_np = obs.cpu().numpy()
+        if obs.device.type == "cpu":          # host_outputs env: the tensor IS the pinned buffer the next step overwrites
+            obs_np = obs_np.copy()
         term_np, trunc_np = term.cpu().numpy(), trunc.cpu().numpy()
         dones = term_np | trunc_np
         infos: List[Dict[str, Any]] = [{} for _ in range(self.num_envs)]
         if dones.any():
             fin = info["final_observation"].cpu().numpy()
             for i in np.nonzero(dones)[0]:
-                infos[i]["terminal_observation"] = fin[i]
+                infos[i]["terminal_observation"] = fin[i].copy()
                 infos[i]["TimeLimit.truncated"] = bool(trunc_np[i] and not term_np[i])
                 infos[i]["is_success"] = bool(term_np[i])
         return obs_np, rew.cpu().numpy().astype(np.float32), dones, infos
