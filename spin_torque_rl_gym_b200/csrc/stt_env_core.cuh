@@ -8,7 +8,7 @@
 namespace stg {
 
 #ifndef STG_SUBSTEP_UNROLL
-#define STG_SUBSTEP_UNROLL 2      // measured in stt_kernels.cu (STG_MINBLOCKS_NOISE_F32)
+#define STG_SUBSTEP_UNROLL 4      // measured in stt_kernels.cu (STG_MINBLOCKS_NOISE_F32)
 #endif
 constexpr int kSubstepUnroll = STG_SUBSTEP_UNROLL;
 #ifndef STG_REF_SUBSTEP_UNROLL

@@ -29,10 +29,11 @@ namespace stg {
 #define STG_MINBLOCKS_NOISE 1   // FP64-stage thermal variants: let ptxas keep the 12 Gaussians + Philox state in registers
 #endif
 #ifndef STG_MINBLOCKS_NOISE_F32
-// FP32 thermal variants: the substep loop is unrolled by two (STG_SUBSTEP_UNROLL, stt_env_core.cuh) so that the Philox rounds of
-// substep i+1 can be scheduled under the dependent stage chain of substep i; unrolled, ptxas would take 146 registers (14
-// warps/SM), so the kernel is held at 128 (16 warps/SM, no spill). 1M envs x 999 substeps: 14.17 ms plain, 13.94 ms unrolled at
-// 146 registers, 13.72 ms unrolled at 128, 14.11 ms unrolled by four.
+// FP32 thermal variants: the substep loop is unrolled by four (STG_SUBSTEP_UNROLL, stt_env_core.cuh) so that the Philox rounds of
+// the following substeps can be scheduled under the dependent stage chain of the current one; unrolled, ptxas would take ~146
+// registers (14 warps/SM), so the kernel is held at 128 (16 warps/SM, no spill). 1M envs x 999 substeps: 14.17 ms plain; unroll 2:
+// 13.94 ms at 146 registers, 13.71 ms at 128; unroll 3 at 128: 13.87; unroll 4: 14.11 ms at 148 registers, 13.56 ms at 128;
+// unroll 8 at 128: 15.9 ms (instruction cache).
 #define STG_MINBLOCKS_NOISE_F32 8
 #endif
 constexpr int kBlock = STG_BLOCK;   // 64: 65,536 envs -> 1024 CTAs = 6.9 per SM, balanced to 1.2 % on 148 SMs
