@@ -389,8 +389,8 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size from the ncu --set full capture
                 # (profiles/r01_ncu_stt_env_step_f32_thermal1.csv): 76.2 MB + 146.8 MB; algorithmic 150 B x 1M envs = 157 MB
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 1,048,576 envs from the ncu --set full capture of
-                # the shipped kernel (profiles/r01_ncu_stt_env_step_f32_thermal1.csv: 76.4 + 141.3 MB; algorithmic 157 MB)
-                "traffic": 217.8e6 if n_local == N_ENVS_PER_GPU and thermal and args.dtype == "f32" else None,
+                # the shipped kernel (profiles/r01_ncu_stt_env_step_f32_thermal1.csv: 76.1 + 141.8 MB; algorithmic 157 MB)
+                "traffic": 217.9e6 if n_local == N_ENVS_PER_GPU and thermal and args.dtype == "f32" else None,
                 "hbm": {"achieved_gbs": n_local * BYTES_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src},
             },
