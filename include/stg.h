@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 5
+#define STG_ABI_VERSION 6
 
 /* error codes */
 #define STG_OK 0
@@ -113,10 +113,15 @@ typedef struct StgSttStepOut {
     double* step_energy; /* [n]     energy_consumed (:474-480)                                         */
     int32_t* n_sub;      /* [n]     substeps integrated (physics/simple_solver.py:137-139)              */
     int32_t* status;     /* [n]     0 ok; bit0 non-finite/zero-norm guard fired (m kept); bit1 solver
-                                    validation failed (solver_valid==0)                               */
+                                    validation failed (solver_valid==0); bit2 (STG_STATUS_REDONE_F64)
+                                    stg_stt_step_f32 repeated this env with FP64 stages (see d_redo)   */
     float* final_obs;    /* [n][12] with STG_F_AUTORESET: observation before the reset (terminal_observation) */
     double* stats;       /* [STG_STAT_REPLICAS][STG_NSTATS] accumulated with atomics (K5 input), see below */
 } StgSttStepOut;
+
+#define STG_STATUS_GUARD 1
+#define STG_STATUS_INVALID_PARAMS 2
+#define STG_STATUS_REDONE_F64 4
 
 /* stats vector layout (all doubles, SUM-reducible across ranks) */
 #define STG_STAT_STEPS 0        /* env-steps executed                */
@@ -144,7 +149,15 @@ typedef struct StgSttStepOut {
  *                  more than noise_stride substeps reuses the last row (no out-of-bounds read)
  *   d_perm         STG_F_SORTED: [n] int32 env indices processed by consecutive threads (stg_stt_sort_by_substeps)
  *   d_target_table STG_F_AUTORESET: [n_targets][3] f64 target_states (envs/spin_torque_env.py:117-120)
- *   seed, env_offset: Philox key / global env id of local env 0 (rank sharding keeps streams independent of #GPUs) */
+ *   seed, env_offset: Philox key / global env id of local env 0 (rank sharding keeps streams independent of #GPUs)
+ *   d_redo         stg_stt_step_f32, STG_F_AXIS_Z, RK4, without STG_F_THERMAL_PHILOX: int32 workspace of STG_REDO_HEADER + n
+ *                  entries (contents irrelevant on entry). The FP32 stages track a conditioning bound per trajectory
+ *                  (csrc/llgs_core.cuh: CondTrack); an env whose bound exceeds the FP32 contract (1e-4 on m, energy, reward:
+ *                  trajectories held near an unstable polar angle for thousands of substeps, ~0.2 % of uniformly random
+ *                  (state, pulse <= 5 ns) samples) is not stepped by the FP32 kernel but appended to this list, and a second,
+ *                  compacted launch in the same call steps the listed envs with FP64 stages (status bit 2). Results do not
+ *                  depend on the order of the list. Required (STG_E_NULL) for those launches; ignored otherwise. */
+#define STG_REDO_HEADER 4
 typedef struct StgSttStepArgs {
     const StgSttFolded* d_table;
     const int32_t* d_param_index;
@@ -162,6 +175,7 @@ typedef struct StgSttStepArgs {
     int32_t n_targets;
     uint32_t flags;
     uint32_t reserved;
+    int32_t* d_redo;
 } StgSttStepArgs;
 
 /* Argument block of a batched reset (envs/spin_torque_env.py:250-308) of the envs with d_mask[i]!=0 (all if NULL).

@@ -26,6 +26,8 @@ STAT_REPLICAS = 256      # include/stg.h STG_STAT_REPLICAS: the step kernels spr
 STAT_NAMES = ("steps", "substeps", "terminated", "truncated", "energy", "reward", "guard", "episode_length")
 FOLDED_DOUBLES = 40
 SORT_WORK_INTS = 8192 + 8
+REDO_HEADER = 4          # include/stg.h STG_REDO_HEADER
+STATUS_GUARD, STATUS_INVALID_PARAMS, STATUS_REDONE_F64 = 1, 2, 4
 OBS_DIM = 12
 
 
@@ -62,7 +64,7 @@ class StgSttStepArgs(C.Structure):
                 ("d_action", C.c_void_p), ("out", StgSttStepOut), ("d_noise", C.c_void_p),
                 ("noise_stride", C.c_int64), ("d_perm", C.c_void_p), ("d_target_table", C.c_void_p),
                 ("seed", C.c_uint64), ("env_offset", C.c_uint64), ("n_envs", C.c_int64), ("n_sets", C.c_int32),
-                ("n_targets", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("n_targets", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint32), ("d_redo", C.c_void_p)]
 
 
 class StgSttResetArgs(C.Structure):
@@ -176,8 +178,9 @@ SYMBOLS = {
     "stg_probe_fma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
-ABI_VERSION = 5          # include/stg.h STG_ABI_VERSION (2: sampled current / field grids; 3: replicated statistics buffer;
-                         # 4: zero-row counters of stg_device_field_f64 / stg_device_resistance_f64; 5: StgRk45Args.d_perm)
+ABI_VERSION = 6          # include/stg.h STG_ABI_VERSION (2: sampled current / field grids; 3: replicated statistics buffer;
+                         # 4: zero-row counters of stg_device_field_f64 / stg_device_resistance_f64; 5: StgRk45Args.d_perm;
+                         # 6: StgSttStepArgs.d_redo, status bit 2)
 _LIB: Optional[C.CDLL] = None
 
 

@@ -611,6 +611,56 @@ STG_HD void fast_apply(FastState& s, float ix, float iy, float iz, float cx, flo
         fast_resync(s);
     }
 }
+// ---- conditioning of an FP32-stage trajectory (deterministic / injected-noise runs of the fast path) ---------------------
+// The FP32 stages leave a relative rounding error of ~2^-24 in the polar rate of every substep. For e = z^ the polar angle obeys
+// an autonomous equation,  d(theta)/dn = sin(theta) W(z),  z = cos(theta),  W = 6 (ac z + a)  (ac = alpha c; the constants carry
+// the RK4 factor 1/6), so an error in theta is multiplied per substep by exp(lambda),
+//     lambda = d/d(theta) [sin(theta) W] = z W - 6 ac (1 - z^2),
+// and every unit of z error turns the azimuth by |6 c| per substep. A trajectory held where W ~ 0 on the unstable side
+// (lambda > 0: the current balances the anisotropy) for thousands of substeps amplifies the 1e-10 per substep beyond the 1e-4
+// contract of the FP32 mode (the reference, physics/simple_solver.py:278-295, is FP64). The tracker integrates that bound
+// forward, once per resynchronisation block of the master (nb = 16 substeps), with s = sin(theta):
+//     A   <- A e^{nb lambda} + nb eps s max(1, e^{nb lambda})     (polar-angle error bound after the block)
+//     Phi <- Phi + nb |6 c| s A                                     (azimuth error bound)
+//     estimate of |delta m| = A + s_end Phi
+// eps = 2^-24 (|6 ac| + |6 a| + 0.01 |6 c|): rounding of the polar rates plus the share of the precession term's rounding that
+// leaks into the polar angle (dominant at low damping). The caller repeats an env with FP64 stages when the estimate exceeds
+// STG_COND_TOL. Calibrated on the host build of these bodies against the FP64 oracle over random (state, pulse <= 5 ns) samples
+// and four parameter sets (tests/test_hostsim_parity.py::test_fp32_conditioning_flag): the worst error of an env that is NOT
+// flagged stays below ~1 x STG_COND_TOL, i.e. a margin of ~20x to 1e-4; 0.3 - 1.5 % of such samples are flagged.
+struct CondTrack {
+    float A, Phi;
+};
+#ifndef STG_COND_TOL
+#define STG_COND_TOL 5.0e-6f
+#endif
+STG_HD float fast_ex2(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return exp2f(x);
+#endif
+}
+// c, ac, a: the per-substep constants of the stages (already divided by 6); z: current m_z; s: current transverse magnitude
+// sin(theta); nb: substeps in the block
+STG_HD void cond_block(CondTrack& t, float c, float ac, float a, float z, float s, float nb) {
+    const float ac6 = 6.0f * ac, a6 = 6.0f * a;
+    s = fminf(s, 1.0f);
+    const float lam = fmaf(z, fmaf(ac6, z, a6), -ac6 * s * s);
+    const float g = fast_ex2(fminf(nb * lam * 1.4426950408889634f, 80.0f));
+    const float eps = 5.9604645e-8f * (fabsf(ac6) + fabsf(a6) + 0.06f * fabsf(c));
+    t.A = fmaf(t.A, g, nb * eps * s * fmaxf(1.0f, g));
+    t.Phi = fmaf(nb * fabsf(6.0f * c) * s, t.A, t.Phi);
+}
+STG_HD float transverse_of(float fx, float fy, float inv_s) {      // sin(theta) from the (block-scaled) FP32 working copy
+    return fast_sqrt(fmaf(fx, fx, fy * fy)) * inv_s;
+}
+STG_HD bool cond_exceeded(const CondTrack& t, float s_end) {
+    return !(fmaf(fminf(s_end, 1.0f), t.Phi, t.A) <= STG_COND_TOL);        // NaN counts as exceeded
+}
+
 template <typename P>
 STG_HD void pack_consts(const StepConsts<float>& a, const StepConsts<float>& b, PackConsts<P>& c);
 template <>

@@ -42,12 +42,15 @@ STG_HD void parse_action(float a0, float a1, double max_current, double max_dura
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>
 STG_HD void integrate(const double* f, double J, double& mx, double& my, double& mz, int n, double dt, double t_pulse,
                       double t_end, const Philox& ph, uint64_t gid, uint32_t step_id, const double* noise_row, double* traj,
-                      int& guard, int64_t noise_rows = 0x7fffffff, int64_t traj_rows = 0x7fffffff) {
+                      int& guard, int64_t noise_rows = 0x7fffffff, int64_t traj_rows = 0x7fffffff, int* illcond = nullptr) {
+    // illcond (FP32 fast path without the Philox stream only): set to 1 when the conditioning bound of the trajectory exceeds
+    // kCondTol (llgs_core.cuh: CondTrack) - the caller then repeats the env with FP64 stages
     // injected noise: substeps beyond the caller's tensor reuse its last row instead of reading out of bounds
     auto nrow_of = [&](int i) { return (int64_t)(i < noise_rows ? i : noise_rows - 1); };
     constexpr bool TH = NOISE != 0;
     constexpr bool FAST = sizeof(R) == 4 && AXIS_Z && !EULER;          // substep_fast (llgs_core.cuh)
     constexpr bool SCALED = sizeof(R) == 4 && AXIS_Z && !TH;            // block-scaled transverse pair
+    constexpr bool TRACK = FAST && NOISE != 1;                          // with the Philox stream parity is statistical
     constexpr int NS = EULER ? 3 : 12;
     // substeps whose stage times are certainly inside the pulse run with the constant a; the few around the pulse edge
     // evaluate current_func(t) exactly in FP64 (the k4 stage of the LAST substep sees t_i+dt > T for ~16 % of f32 durations)
@@ -70,6 +73,7 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
         s.st = ScaledState{mx, my, mz, 1.0, 1.0, 1.0f};
         if (SCALED) rescale(s.st);
         fast_resync(s);
+        CondTrack ct{0.0f, 0.0f};
         // one substep + the periodic exact renormalisation; `edge` substeps evaluate the pulse gate per stage
         auto one = [&](int i, bool edge) {
             float aH1 = c.a_hi, aL1 = c.a_lo, aH2 = c.a_hi, aL2 = c.a_lo, aH4 = c.a_hi, aL4 = c.a_lo;
@@ -90,6 +94,9 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
                                         ix, iy, iz, cx, cy, cz, d);
             fast_apply(s, ix, iy, iz, cx, cy, cz, d, guard);
             if ((i & STG_RESYNC_MASK) == STG_RESYNC_MASK || traj) {
+                if (TRACK)
+                    cond_block(ct, pc.c_hi, pc.ac_hi, aH1, s.fz, transverse_of(s.fx, s.fy, (float)s.st.inv_s),
+                               traj ? 1.0f : (float)(STG_RESYNC_MASK + 1));
                 guard_normalise<float>(s.st, guard);      // exact FP64 renormalisation of the master
                 if (SCALED) rescale(s.st);
                 fast_resync(s);
@@ -103,6 +110,12 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
 #pragma unroll kSubstepUnroll
         for (; i < i_safe; ++i) one(i, false);
         for (; i < n; ++i) one(i, true);
+        if (TRACK && illcond) {
+            const float s_end = transverse_of(s.fx, s.fy, (float)s.st.inv_s);
+            if (!traj && (n & STG_RESYNC_MASK))
+                cond_block(ct, pc.c_hi, pc.ac_hi, t_pulse >= t_end ? c.a_hi : 0.0f, s.fz, s_end, (float)(n & STG_RESYNC_MASK));
+            *illcond = cond_exceeded(ct, s_end) ? 1 : 0;
+        }
         guard_normalise<float>(s.st, guard);
         mx = s.st.sx * s.st.inv_s; my = s.st.sy * s.st.inv_s; mz = s.st.z;
     } else {
@@ -187,8 +200,10 @@ STG_HD void pair_renorm(ScaledState& st, F2& fx, F2& fy, F2& fz, F2& q, F2& nq, 
 
 template <int NOISE>
 STG_HD void integrate_pair(const PairEnv& A, const PairEnv& B, uint32_t seed_lo, double* mA, double* mB, int& guardA,
-                           int& guardB) {
+                           int& guardB, int& illA, int& illB) {
     constexpr bool TH = NOISE != 0;
+    constexpr bool TRACK = NOISE != 1;
+    CondTrack ctA{0.0f, 0.0f}, ctB{0.0f, 0.0f};
     constexpr bool SCALED = !TH;
     StepConsts<float> ca, cb;
     make_consts<float>(A.f, A.dt, A.J, 1.0 / 6.0, ca);
@@ -231,6 +246,12 @@ STG_HD void integrate_pair(const PairEnv& A, const PairEnv& B, uint32_t seed_lo,
         if (runA) pair_apply<0>(sa, fx, fy, fz, q, nq, ix, iy, iz, cx, cy, cz, d, guardA);
         if (runB) pair_apply<1>(sb, fx, fy, fz, q, nq, ix, iy, iz, cx, cy, cz, d, guardB);
         if ((i & STG_RESYNC_MASK) == STG_RESYNC_MASK) {
+            if (TRACK) {
+                if (runA) cond_block(ctA, pc.c_hi.x, pc.ac_hi.x, aH.x, fz.x, transverse_of(fx.x, fy.x, (float)sa.inv_s),
+                                     (float)(STG_RESYNC_MASK + 1));
+                if (runB) cond_block(ctB, pc.c_hi.y, pc.ac_hi.y, aH.y, fz.y, transverse_of(fx.y, fy.y, (float)sb.inv_s),
+                                     (float)(STG_RESYNC_MASK + 1));
+            }
             if (runA) pair_renorm<0, SCALED>(sa, fx, fy, fz, q, nq, guardA);
             if (runB) pair_renorm<1, SCALED>(sb, fx, fy, fz, q, nq, guardB);
         }
@@ -238,6 +259,15 @@ STG_HD void integrate_pair(const PairEnv& A, const PairEnv& B, uint32_t seed_lo,
     int i = 0;
     for (; i < edge_from; ++i) one(i, false);
     for (; i < n_max; ++i) one(i, true);
+    illA = illB = 0;
+    if (TRACK) {
+        const float sA = transverse_of((float)sa.sx, (float)sa.sy, (float)sa.inv_s);
+        const float sB = transverse_of((float)sb.sx, (float)sb.sy, (float)sb.inv_s);
+        if (A.n & STG_RESYNC_MASK) cond_block(ctA, ca.c_hi, ca.ac_hi, ca.a_hi, (float)sa.z, sA, (float)(A.n & STG_RESYNC_MASK));
+        if (B.n & STG_RESYNC_MASK) cond_block(ctB, cb.c_hi, cb.ac_hi, cb.a_hi, (float)sb.z, sB, (float)(B.n & STG_RESYNC_MASK));
+        illA = cond_exceeded(ctA, sA) ? 1 : 0;
+        illB = cond_exceeded(ctB, sB) ? 1 : 0;
+    }
     guard_normalise<float>(sa, guardA);
     guard_normalise<float>(sb, guardB);
     mA[0] = sa.sx * sa.inv_s; mA[1] = sa.sy * sa.inv_s; mA[2] = sa.z;
@@ -307,6 +337,7 @@ struct EnvStepCtx {
     double w[3];        // working magnetisation handed to / returned by the integrator
     StepPlan plan;
     int step, guard;
+    int illcond;        // FP32 stages only: the conditioning bound of the trajectory exceeded kCondTol (llgs_core.cuh)
     bool valid;
 };
 
@@ -323,19 +354,20 @@ STG_HD void env_step_prologue(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c)
     c.plan = substep_plan(c.T, c.f[FI_MAXSTEP_DT]);
     c.w[0] = c.mx; c.w[1] = c.my; c.w[2] = c.mz;
     c.guard = 0;
+    c.illcond = 0;
     c.valid = c.f[FI_VALID] != 0.0 && (!AXIS_Z || c.f[FI_AXISZ] != 0.0);
     if (c.valid) guard_normalise<R>(c.w[0], c.w[1], c.w[2], c.guard);         // SimpleLLGSSolver.solve :119
 }
 
 // Second half: env-level renormalisation, energy, reward, flags, observation, auto-reset, state / output stores.
-STG_HD void env_step_epilogue(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c, EnvStepResult& r) {
+STG_HD void env_step_epilogue(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c, EnvStepResult& r, int status_bits = 0) {
     const int64_t n = a.n_envs;
     const bool autoreset = (a.flags & STG_F_AUTORESET) != 0;
     const double* f = c.f;
     const double mx = c.mx, my = c.my, mz = c.mz;
     double tx = c.tx, ty = c.ty, tz = c.tz;
     double nx = mx, ny = my, nz = mz;
-    int status = 0;
+    int status = status_bits;
     if (c.valid) {
         // env-level renormalisation of the last trajectory row (envs/spin_torque_env.py:464)
         const double inv = 1.0 / sqrt(c.w[0] * c.w[0] + c.w[1] * c.w[1] + c.w[2] * c.w[2]);
@@ -411,24 +443,31 @@ STG_HD void env_step_integrate(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c
     const uint32_t step_id = (uint32_t)c.step;
     if (c.f[FI_HTH] > 0.0 || NOISE == 0)
         integrate<R, AXIS_Z, NOISE, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ph, gid, step_id,
-                                           nrow, nullptr, c.guard, NOISE == 2 ? a.noise_stride : 0x7fffffff);
+                                           nrow, nullptr, c.guard, NOISE == 2 ? a.noise_stride : 0x7fffffff, 0x7fffffff,
+                                           &c.illcond);
     else
         integrate<R, AXIS_Z, 0, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ph, gid, step_id,
-                                       nullptr, nullptr, c.guard);
+                                       nullptr, nullptr, c.guard, 0x7fffffff, 0x7fffffff, &c.illcond);
 }
 
 // One env (index e of a.n_envs): reads and updates the FP64 state planes, returns the outputs in `r`.
+// Returns false - with NOTHING written, state and outputs untouched - when the FP32 stages cannot guarantee the 1e-4 contract
+// for this trajectory (CondTrack): the caller repeats the env through the <double> instantiation (the kernels collect such
+// envs in StgSttStepArgs.d_redo and run them in a second, compacted launch; status bit 2 marks them).
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>
-STG_HD void env_step_body(const StgSttStepArgs& a, int64_t e, EnvStepResult& r) {
+STG_HD bool env_step_body(const StgSttStepArgs& a, int64_t e, EnvStepResult& r, int status_bits = 0) {
     EnvStepCtx c;
     env_step_prologue<R, AXIS_Z>(a, e, c);
     if (c.valid) env_step_integrate<R, AXIS_Z, NOISE, EULER>(a, e, c);
-    env_step_epilogue(a, e, c, r);
+    if (sizeof(R) == 4 && c.illcond) return false;
+    env_step_epilogue(a, e, c, r, status_bits);
+    return true;
 }
 
-// Two envs (eA, eB) through the packed FP32x2 integrator (R = float, e = z^, RK4, NOISE 0 or 1).
+// Two envs (eA, eB) through the packed FP32x2 integrator (R = float, e = z^, RK4, NOISE 0 or 1). Returns a mask of the envs
+// that were NOT stepped because their FP32 trajectory is ill-conditioned (bit 0: eA, bit 1: eB; see env_step_body).
 template <int NOISE>
-STG_HD void env_step_pair_body(const StgSttStepArgs& a, int64_t eA, int64_t eB, EnvStepResult& rA, EnvStepResult& rB) {
+STG_HD int env_step_pair_body(const StgSttStepArgs& a, int64_t eA, int64_t eB, EnvStepResult& rA, EnvStepResult& rB) {
     EnvStepCtx ca, cb;
     env_step_prologue<float, true>(a, eA, ca);
     env_step_prologue<float, true>(a, eB, cb);
@@ -438,13 +477,14 @@ STG_HD void env_step_pair_body(const StgSttStepArgs& a, int64_t eA, int64_t eB, 
                   (uint32_t)ca.step, a.env_offset + (uint64_t)eA};
         PairEnv B{cb.f, cb.J, cb.plan.dt, cb.T, cb.plan.n, (uint32_t)(a.seed >> 32) ^ (uint32_t)a.state.episode[eB],
                   (uint32_t)cb.step, a.env_offset + (uint64_t)eB};
-        integrate_pair<NOISE>(A, B, (uint32_t)a.seed, ca.w, cb.w, ca.guard, cb.guard);
+        integrate_pair<NOISE>(A, B, (uint32_t)a.seed, ca.w, cb.w, ca.guard, cb.guard, ca.illcond, cb.illcond);
     } else {
         if (ca.valid) env_step_integrate<float, true, NOISE, false>(a, eA, ca);
         if (cb.valid) env_step_integrate<float, true, NOISE, false>(a, eB, cb);
     }
-    env_step_epilogue(a, eA, ca, rA);
-    env_step_epilogue(a, eB, cb, rB);
+    if (!ca.illcond) env_step_epilogue(a, eA, ca, rA);
+    if (!cb.illcond) env_step_epilogue(a, eB, cb, rB);
+    return (ca.illcond ? 1 : 0) | (cb.illcond ? 2 : 0);
 }
 
 // SpinTorqueEnv.reset for one env (envs/spin_torque_env.py:250-308)
@@ -502,13 +542,29 @@ STG_HD void solve_body(const StgSttSolveArgs& a, int64_t e) {
         Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
         const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
         double* traj = a.d_traj ? a.d_traj + (int64_t)e * a.traj_stride * 3 : nullptr;
+        // the solver API repeats an ill-conditioned FP32 trajectory with FP64 stages on the spot (CondTrack, llgs_core.cuh)
+        const double sx = mx, sy = my, sz = mz;
+        const int guard0 = guard;
+        int ill = 0;
         if (f[FI_HTH] > 0.0 || NOISE == 0)
             integrate<R, AXIS_Z, NOISE, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph,
                                                a.env_offset + (uint64_t)e, 0u, nrow, traj, guard,
-                                               NOISE == 2 ? a.noise_stride : 0x7fffffff, traj ? a.traj_stride : 0x7fffffff);
+                                               NOISE == 2 ? a.noise_stride : 0x7fffffff, traj ? a.traj_stride : 0x7fffffff, &ill);
         else
             integrate<R, AXIS_Z, 0, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph, a.env_offset + (uint64_t)e,
-                                           0u, nullptr, traj, guard, 0x7fffffff, traj ? a.traj_stride : 0x7fffffff);
+                                           0u, nullptr, traj, guard, 0x7fffffff, traj ? a.traj_stride : 0x7fffffff, &ill);
+        if (sizeof(R) == 4 && ill) {
+            mx = sx; my = sy; mz = sz; guard = guard0;
+            if (f[FI_HTH] > 0.0 || NOISE == 0)
+                integrate<double, AXIS_Z, NOISE, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph,
+                                                        a.env_offset + (uint64_t)e, 0u, nrow, traj, guard,
+                                                        NOISE == 2 ? a.noise_stride : 0x7fffffff,
+                                                        traj ? a.traj_stride : 0x7fffffff);
+            else
+                integrate<double, AXIS_Z, 0, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph,
+                                                    a.env_offset + (uint64_t)e, 0u, nullptr, traj, guard, 0x7fffffff,
+                                                    traj ? a.traj_stride : 0x7fffffff);
+        }
     }
     a.d_m_out[3 * e] = mx; a.d_m_out[3 * e + 1] = my; a.d_m_out[3 * e + 2] = mz;
     if (a.d_n_sub) a.d_n_sub[e] = nsub;

@@ -48,6 +48,16 @@ using StepArgs = StgSttStepArgs;
 using ResetArgs = StgSttResetArgs;
 using SolveArgs = StgSttSolveArgs;
 
+// An env the FP32 stages declined (env_step_body returned false, nothing written): append it to the list of the second pass.
+// Its rows of this launch's cooperative observation stores are zeros and are overwritten by that pass.
+__device__ __forceinline__ void redo_push(const StgSttStepArgs& a, int64_t e, EnvStepResult& r) {
+    const int pos = atomicAdd(a.d_redo, 1);
+    a.d_redo[STG_REDO_HEADER + pos] = (int32_t)e;
+#pragma unroll
+    for (int q = 0; q < kObs; ++q) { r.obs[q] = 0.0f; r.final_obs[q] = 0.0f; }
+    r.did_reset = false;
+}
+
 __device__ __forceinline__ void store_row(float* dst, const float* o) {
     float4* d = reinterpret_cast<float4*>(dst);
     d[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -67,7 +77,11 @@ stt_env_step_kernel(const __grid_constant__ StepArgs a) {
 
     EnvStepResult r;
     r.did_reset = false;
-    if (active) env_step_body<R, AXIS_Z, NOISE, EULER>(a, e, r);
+    bool stepped = active;
+    if (active) {
+        stepped = env_step_body<R, AXIS_Z, NOISE, EULER>(a, e, r);
+        if (!stepped) redo_push(a, e, r);      // FP32 stages only: repeated with FP64 stages by stt_env_redo_kernel
+    }
 
     // ---- observation rows ------------------------------------------------------------------------------------------------
     if (!sorted) {
@@ -112,7 +126,7 @@ stt_env_step_kernel(const __grid_constant__ StepArgs a) {
         double v[STG_NSTATS];
 #pragma unroll
         for (int q = 0; q < STG_NSTATS; ++q) v[q] = 0.0;
-        if (active) {
+        if (stepped) {
             const bool ended = r.terminated || r.truncated;
             v[STG_STAT_STEPS] = 1.0;
             v[STG_STAT_SUBSTEPS] = r.valid ? (double)r.n_sub : 0.0;
@@ -165,8 +179,11 @@ __global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : STG_
 
     EnvStepResult rA, rB;
     rA.did_reset = rB.did_reset = false;
-    if (actB) env_step_pair_body<NOISE>(a, eA, eB, rA, rB);
-    else if (actA) env_step_body<float, true, NOISE, false>(a, eA, rA);
+    int redo = 0;
+    if (actB) redo = env_step_pair_body<NOISE>(a, eA, eB, rA, rB);
+    else if (actA) redo = env_step_body<float, true, NOISE, false>(a, eA, rA) ? 0 : 1;
+    if (redo & 1) redo_push(a, eA, rA);
+    if (redo & 2) redo_push(a, eB, rB);
 
     if (!sorted) {
         const int64_t rows = (a.n_envs - base) < 2 * kBlock ? (a.n_envs - base) : 2 * kBlock;
@@ -218,12 +235,44 @@ __global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : STG_
         double v[STG_NSTATS];
 #pragma unroll
         for (int q = 0; q < STG_NSTATS; ++q) v[q] = 0.0;
-        if (actA) accumulate_stats(v, rA);
-        if (actB) accumulate_stats(v, rB);
+        if (actA && !(redo & 1)) accumulate_stats(v, rA);
+        if (actB && !(redo & 2)) accumulate_stats(v, rB);
 #pragma unroll
         for (int q = 0; q < STG_NSTATS; ++q) {
             const double sum = warp_sum(v[q]);
             if ((threadIdx.x & 31) == 0 && sum != 0.0) atomicAdd(a.out.stats + (blockIdx.x % STG_STAT_REPLICAS) * STG_NSTATS + q, sum);
+        }
+    }
+}
+
+// ---- second pass of stg_stt_step_f32: the envs the FP32 stages declined, compacted, with FP64 stages ---------------------
+// Grid-stride over the list d_redo[STG_REDO_HEADER ..] (count in d_redo[0], written by the first pass on the same stream).
+// Typically empty or a fraction of a per cent of the batch, so rows are stored per thread and statistics added per thread.
+template <int NOISE>
+__global__ void __launch_bounds__(kBlock) stt_env_redo_kernel(const __grid_constant__ StepArgs a) {
+    const int64_t count = a.d_redo[0] < a.n_envs ? (int64_t)a.d_redo[0] : a.n_envs;
+    const bool want_fin = (a.flags & STG_F_AUTORESET) != 0 && a.out.final_obs != nullptr;
+    for (int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x; slot < count; slot += (int64_t)gridDim.x * kBlock) {
+        const int64_t e = a.d_redo[STG_REDO_HEADER + slot];
+        EnvStepResult r;
+        r.did_reset = false;
+        env_step_body<double, true, NOISE, false>(a, e, r, STG_STATUS_REDONE_F64);
+        store_row(a.out.obs + e * kObs, r.obs);
+        if (want_fin) {
+            if (!r.did_reset) {
+#pragma unroll
+                for (int q = 0; q < kObs; ++q) r.final_obs[q] = 0.0f;
+            }
+            store_row(a.out.final_obs + e * kObs, r.final_obs);
+        }
+        if (a.out.stats) {
+            double v[STG_NSTATS];
+#pragma unroll
+            for (int q = 0; q < STG_NSTATS; ++q) v[q] = 0.0;
+            accumulate_stats(v, r);
+#pragma unroll
+            for (int q = 0; q < STG_NSTATS; ++q)
+                if (v[q] != 0.0) atomicAdd(a.out.stats + (blockIdx.x % STG_STAT_REPLICAS) * STG_NSTATS + q, v[q]);
         }
     }
 }
@@ -312,29 +361,52 @@ __global__ void __launch_bounds__(kBlock) stt_solve_grid_kernel(const __grid_con
 template <typename R, bool AXIS_Z, int NOISE>
 static cudaError_t launch_step2(const StepArgs& a, cudaStream_t s) {
     const unsigned grid = (unsigned)((a.n_envs + kBlock - 1) / kBlock);
-    if (a.flags & STG_F_EULER)
-        stt_env_step_kernel<R, AXIS_Z, NOISE, true><<<grid, kBlock, 0, s>>>(a);
-    else
-        stt_env_step_kernel<R, AXIS_Z, NOISE, false><<<grid, kBlock, 0, s>>>(a);
+    if constexpr (sizeof(R) == 8) {      // Euler always runs FP64 stages (launch_step)
+        if (a.flags & STG_F_EULER) {
+            stt_env_step_kernel<R, AXIS_Z, NOISE, true><<<grid, kBlock, 0, s>>>(a);
+            return cudaGetLastError();
+        }
+    }
+    stt_env_step_kernel<R, AXIS_Z, NOISE, false><<<grid, kBlock, 0, s>>>(a);
+    return cudaGetLastError();
+}
+// FP32 stages without the Philox stream: zero the redo counter, run the FP32 kernel, then the compacted FP64 pass
+static bool step_uses_redo(const StepArgs& a, bool f32, bool axis_z) {
+    return f32 && axis_z && !(a.flags & (STG_F_EULER | STG_F_THERMAL_PHILOX));
+}
+template <int NOISE>
+static cudaError_t launch_redo(const StepArgs& a, cudaStream_t s) {
+    const int64_t blocks = (a.n_envs + kBlock - 1) / kBlock;
+    const unsigned grid = (unsigned)(blocks < 4 * 148 ? blocks : 4 * 148);
+    stt_env_redo_kernel<NOISE><<<grid, kBlock, 0, s>>>(a);
     return cudaGetLastError();
 }
 // FP32 stage arithmetic exists for the axis-aligned geometry only (compensated constants + block scaling, llgs_core.cuh).
 // A tilted easy axis / applied field always runs FP64 stages, also through the _f32 entry points: rounding the axis
 // components to 24 bits is a systematic rate error the 1e-4 contract does not survive over thousands of substeps.
+// The explicit Euler map amplifies rounding errors chaotically (0.35 rad per substep, renormalised): FP32 stages do not hold the
+// 1e-4 contract there either, so Euler runs FP64 stages through both entry points as well.
 template <typename R>
 static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
     const int noise = (a.flags & STG_F_THERMAL_INJECT) ? 2 : ((a.flags & STG_F_THERMAL_PHILOX) ? 1 : 0);
-    if (axis_z) {
-        if (sizeof(R) == 4 && noise == 0 && !(a.flags & (STG_F_EULER | STG_F_NO_PAIR))) {
+    if (sizeof(R) == 4 && (a.flags & STG_F_EULER)) return launch_step<double>(a, axis_z, s);
+    if (step_uses_redo(a, sizeof(R) == 4, axis_z)) {
+        cudaError_t err = cudaMemsetAsync(a.d_redo, 0, sizeof(int32_t) * STG_REDO_HEADER, s);
+        if (err != cudaSuccess) return err;
+        if (noise == 0 && !(a.flags & STG_F_NO_PAIR)) {
             // two envs per thread, Blackwell packed FP32x2 arithmetic (bit-identical to the one-env-per-thread kernels).
-            // Measured (profiles/README.md): +8 % without thermal noise. With the Philox stream the packed variant was swept
-            // twice: 201 registers 15.4 ms, 168: 14.1 ms, 155: 14.6 ms, 128 + 88 B spill: 13.97 ms per 1M-env step against
-            // 14.17 ms for one env per thread (the integer Philox rounds do not pack, only the FP32 half of the substep does),
-            // so it is not dispatched there.
+            // Measured (profiles/README.md): +12 % without thermal noise. With the Philox stream the packed variant needs
+            // 201 registers and loses (the integer Philox rounds do not pack), so it is not dispatched there.
             const unsigned grid = (unsigned)((a.n_envs + 2 * kBlock - 1) / (2 * kBlock));
             stt_env_step_pair_kernel<0><<<grid, kBlock, 0, s>>>(a);
-            return cudaGetLastError();
+            err = cudaGetLastError();
+        } else {
+            err = noise == 0 ? launch_step2<float, true, 0>(a, s) : launch_step2<float, true, 2>(a, s);
         }
+        if (err != cudaSuccess) return err;
+        return noise == 0 ? launch_redo<0>(a, s) : launch_redo<2>(a, s);
+    }
+    if (axis_z) {
         if (noise == 0) return launch_step2<R, true, 0>(a, s);
         if (noise == 1) return launch_step2<R, true, 1>(a, s);
         return launch_step2<R, true, 2>(a, s);
@@ -478,6 +550,10 @@ static int stt_step_impl(const StgSttStepArgs* args, void* stream) {
     if (!args) return STG_E_NULL;
     int rc = check_step_args(*args);
     if (rc != STG_OK) return rc;
+    if (step_uses_redo(*args, sizeof(R) == 4, (args->flags & STG_F_AXIS_Z) != 0)) {
+        if (!args->d_redo) return STG_E_NULL;
+        if (args->n_envs > 2147483647LL - STG_REDO_HEADER) return STG_E_SIZE;
+    }
     if (args->n_envs == 0) return STG_OK;
     return (int)launch_step<R>(*args, (args->flags & STG_F_AXIS_Z) != 0, (cudaStream_t)stream);
 }

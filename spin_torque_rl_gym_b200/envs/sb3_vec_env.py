@@ -27,6 +27,8 @@ class SB3VecEnvAdapter(_VecEnvBase):
         if not env.autoreset:
             raise ValueError("the SB3 adapter needs an env constructed with autoreset=True")
         self.env = env
+        if _VecEnvBase is not object:          # the real SB3 base class: let it set num_envs / spaces / render bookkeeping
+            super().__init__(env.num_envs, env.single_observation_space, env.single_action_space)
         self.num_envs = env.num_envs
         self.observation_space = env.single_observation_space
         self.action_space = env.single_action_space
@@ -38,7 +40,9 @@ class SB3VecEnvAdapter(_VecEnvBase):
     def reset(self) -> np.ndarray:
         obs, _ = self.env.reset(seed=self._seed)
         self._seed = None
-        return obs.cpu().numpy()
+        obs_np = obs.cpu().numpy()
+        # host_outputs env: the tensor IS the pinned buffer the next step overwrites, and SB3 keeps reset()'s array as _last_obs
+        return obs_np.copy() if obs.device.type == "cpu" else obs_np
 
     def seed(self, seed: Optional[int] = None) -> List[Optional[int]]:
         self._seed = seed

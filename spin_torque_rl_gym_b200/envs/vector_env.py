@@ -10,6 +10,7 @@ There is no CPU fallback: constructing the env without CUDA or without libstg.so
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Dict, List, Optional, Sequence, Union
 
 import numpy as np
@@ -106,7 +107,8 @@ class SpinTorqueVectorEnv:
         # step() then returns CPU tensors and synchronises the stream before returning. Default: CUDA tensors, no sync.
         self.host_outputs = bool(host_outputs)
         if rng_seed is None:
-            rng_seed = 0 if seed is None else int(seed)
+            # no seed at all: fresh entropy like gymnasium / the reference (np_random(None)); state_dict() records the value
+            rng_seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
         self.rng_seed = int(rng_seed) & 0xFFFFFFFFFFFFFFFF
 
         # ---- device parameter sets ---------------------------------------------------------------------------------
@@ -189,7 +191,13 @@ class SpinTorqueVectorEnv:
             self._action_dev = torch.zeros(N, 2, dtype=torch.float32, device=dev)
             self._perm = torch.zeros(N, dtype=i32, device=dev)
             self._sort_work = torch.zeros(_lib.SORT_WORK_INTS, dtype=i32, device=dev)
-            self._action_pinned = torch.zeros(N, 2, dtype=torch.float32).pin_memory()
+            # second-pass list of stg_stt_step_f32 (include/stg.h, d_redo): envs the FP32 stages decline are repeated with FP64 stages
+            self._redo = torch.zeros(_lib.REDO_HEADER + N, dtype=i32, device=dev)
+            # NumPy / list actions are staged through two pinned buffers used in turn: the host may only overwrite a buffer after
+            # the asynchronous H2D copy that read it has completed (event recorded behind each copy, waited on before reuse)
+            self._action_pinned = [torch.zeros(N, 2, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._action_copied = [None, None]
+            self._action_slot = 0
 
         self._sort_mode = sort_by_substeps
         self._needs_reset = True
@@ -237,6 +245,7 @@ class SpinTorqueVectorEnv:
         o.status = self._status.data_ptr()
         o.final_obs = _lib.ptr(self._final_obs) if self.autoreset else None
         o.stats = self._stats.data_ptr() if self.collect_stats else None
+        a.d_redo = self._redo.data_ptr()
         a.d_target_table = self._target_table.data_ptr()
         a.n_targets = self._target_table.shape[0]
         a.env_offset = self.env_offset
@@ -267,6 +276,9 @@ class SpinTorqueVectorEnv:
         torch = self._torch
         options = options or {}
         if seed is not None:
+            if mask is not None:
+                # one Philox key serves every env: re-keying under a mask would move the running envs onto another noise stream
+                raise ValueError("reset(seed=..., mask=...) is not supported: reseed with a full reset")
             self.rng_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
             self._episode.zero_()
         N = self.num_envs
@@ -312,14 +324,24 @@ class SpinTorqueVectorEnv:
                 return actions
             if actions.device.type == "cpu" and actions.dtype == torch.float32 and actions.is_pinned() \
                     and tuple(actions.shape) == (N, 2):
-                self._action_dev.copy_(actions, non_blocking=True)       # pinned host tensor: one async H2D, no staging copy
+                # pinned host tensor: one async H2D, no staging copy. The CALLER owns that buffer: it must not be overwritten
+                # before the copy has run (synchronise the stream, or hand over a different buffer for the next step).
+                self._action_dev.copy_(actions, non_blocking=True)
                 return self._action_dev
             act = actions.to(device=self.device, dtype=torch.float32).reshape(N, 2)
             self._action_dev.copy_(act)
             return self._action_dev
         arr = np.asarray(actions, dtype=np.float32).reshape(N, 2)
-        self._action_pinned.numpy()[...] = arr
-        self._action_dev.copy_(self._action_pinned, non_blocking=True)
+        k = self._action_slot
+        self._action_slot = 1 - k
+        if self._action_copied[k] is not None:
+            self._action_copied[k].synchronize()        # the copy issued two steps ago out of this buffer has finished
+        self._action_pinned[k].numpy()[...] = arr
+        self._action_dev.copy_(self._action_pinned[k], non_blocking=True)
+        if not torch.cuda.is_current_stream_capturing():
+            ev = self._action_copied[k] or torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._action_copied[k] = ev
         return self._action_dev
 
     def step(self, actions, noise=None):
@@ -368,7 +390,10 @@ class SpinTorqueVectorEnv:
             a.seed = self.rng_seed
             a.flags = flags
             _lib.check(self._step_fn(C.byref(a), stream), "stg_stt_step")
-        self.gpu_launches += 1
+        # FP32 stages without the Philox stream are followed by the compacted FP64 pass over the declined envs (d_redo)
+        two_pass = (self.dtype == torch.float32 and self._axis_z and self.integrator == "rk4"
+                    and not (flags & _lib.F_THERMAL_PHILOX))
+        self.gpu_launches += 2 if two_pass else 1
         info = {
             "step_energy": self._step_energy, "n_sub": self._n_sub, "status": self._status,
             "total_energy": self._total_energy, "step_count": self._step_count,

@@ -34,3 +34,9 @@ def noise_for_step(seed, action, max_current, max_duration=5e-9, stages=4):
 
 def rel_err(a, ref, floor=1e-300):
     return float((np.abs(a - ref) / np.maximum(np.abs(ref), floor)).max())
+
+
+def transverse_rel_err(m, ref):
+    """|delta(m_x, m_y)| / |(m_x, m_y)_ref|: the transverse pair compared as a vector relative to its own magnitude (magnitude
+    ratio and azimuth together), meaningful down to 1e-300 where the absolute error is zero for every practical purpose."""
+    return float(np.hypot(m[0] - ref[0], m[1] - ref[1]) / max(np.hypot(ref[0], ref[1]), 1e-300))

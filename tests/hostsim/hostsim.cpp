@@ -15,18 +15,31 @@
 
 using namespace stg;
 
+static void store_rows(const StgSttStepArgs& a, int64_t e, const EnvStepResult& r) {
+    for (int q = 0; q < kObs; ++q) a.out.obs[e * kObs + q] = r.obs[q];
+    if ((a.flags & STG_F_AUTORESET) && a.out.final_obs)
+        for (int q = 0; q < kObs; ++q) a.out.final_obs[e * kObs + q] = r.did_reset ? r.final_obs[q] : 0.0f;
+}
+// second pass of the FP32 entry point (stt_env_redo_kernel on the device): envs whose FP32 trajectory is ill-conditioned are
+// repeated with FP64 stages, status bit 2 set
+template <bool AXIS_Z, int NOISE>
+static void redo_f64(const StgSttStepArgs& a, int64_t e) {
+    EnvStepResult r;
+    env_step_body<double, AXIS_Z, NOISE, false>(a, e, r, STG_STATUS_REDONE_F64);
+    store_rows(a, e, r);
+}
 template <typename R, bool AXIS_Z, int NOISE>
 static void step_all(const StgSttStepArgs& a) {
     for (int64_t s = 0; s < a.n_envs; ++s) {
         const int64_t e = (a.flags & STG_F_SORTED) ? a.d_perm[s] : s;
         EnvStepResult r;
+        bool done;
         if (a.flags & STG_F_EULER)
-            env_step_body<R, AXIS_Z, NOISE, true>(a, e, r);
+            done = env_step_body<R, AXIS_Z, NOISE, true>(a, e, r);
         else
-            env_step_body<R, AXIS_Z, NOISE, false>(a, e, r);
-        for (int q = 0; q < kObs; ++q) a.out.obs[e * kObs + q] = r.obs[q];
-        if ((a.flags & STG_F_AUTORESET) && a.out.final_obs)
-            for (int q = 0; q < kObs; ++q) a.out.final_obs[e * kObs + q] = r.did_reset ? r.final_obs[q] : 0.0f;
+            done = env_step_body<R, AXIS_Z, NOISE, false>(a, e, r);
+        if (done) store_rows(a, e, r);
+        else redo_f64<AXIS_Z, NOISE>(a, e);
     }
 }
 template <typename R, bool AXIS_Z>
@@ -50,22 +63,20 @@ static void step_pairs(const StgSttStepArgs& a) {
     for (int64_t s = 0; s < a.n_envs; s += 2) {
         const int64_t eA = (a.flags & STG_F_SORTED) ? a.d_perm[s] : s;
         EnvStepResult rA, rB;
+        int redo = 0;
         if (s + 1 < a.n_envs) {
             const int64_t eB = (a.flags & STG_F_SORTED) ? a.d_perm[s + 1] : s + 1;
-            env_step_pair_body<NOISE>(a, eA, eB, rA, rB);
-            for (int q = 0; q < kObs; ++q) a.out.obs[eB * kObs + q] = rB.obs[q];
-            if ((a.flags & STG_F_AUTORESET) && a.out.final_obs)
-                for (int q = 0; q < kObs; ++q) a.out.final_obs[eB * kObs + q] = rB.did_reset ? rB.final_obs[q] : 0.0f;
+            redo = env_step_pair_body<NOISE>(a, eA, eB, rA, rB);
+            if (redo & 2) redo_f64<true, NOISE>(a, eB); else store_rows(a, eB, rB);
         } else {
-            env_step_body<float, true, NOISE, false>(a, eA, rA);
+            redo = env_step_body<float, true, NOISE, false>(a, eA, rA) ? 0 : 1;
         }
-        for (int q = 0; q < kObs; ++q) a.out.obs[eA * kObs + q] = rA.obs[q];
-        if ((a.flags & STG_F_AUTORESET) && a.out.final_obs)
-            for (int q = 0; q < kObs; ++q) a.out.final_obs[eA * kObs + q] = rA.did_reset ? rA.final_obs[q] : 0.0f;
+        if (redo & 1) redo_f64<true, NOISE>(a, eA); else store_rows(a, eA, rA);
     }
 }
 
 extern "C" int hostsim_stt_step(const StgSttStepArgs* a, int f64) {
+    if (a->flags & STG_F_EULER) f64 = 1;      // as launch_step<> dispatches: Euler always runs FP64 stages
     FtzScope ftz(!f64);
     if (!f64 && (a->flags & STG_F_AXIS_Z) && !(a->flags & (STG_F_THERMAL_INJECT | STG_F_EULER | STG_F_NO_PAIR))) {
         // the device dispatches the packed variant for the no-noise case only (faster there); the host build also runs the

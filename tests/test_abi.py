@@ -30,7 +30,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True).stdout
     for name in declared:
         assert re.search(rf"\bT {name}\b", out), name
-    assert lib.stg_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.stg_abi_version() == _lib.ABI_VERSION == 6
 
 
 def test_struct_layouts_match_the_c_header(tmp_path):

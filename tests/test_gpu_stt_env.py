@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.helpers import GOLDEN, load_case, noise_for_step, rel_err, stt_params_for
+from tests.helpers import GOLDEN, load_case, noise_for_step, rel_err, stt_params_for, transverse_rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = {"f64": 1e-6, "f32": 1e-4}
@@ -69,8 +69,10 @@ def test_c1_single_env_100_pulses(prec, cuda_device):
             break
         o, r, te, tr, info = env.step(a[None].copy())
         m = env.magnetization.cpu().numpy()[0]
-        assert rel_err(m, c["m"][k + 1]) < (1e-6 if prec == "f64" else 5e-2), k
-        assert np.abs(m - c["m"][k + 1]).max() < tol
+        assert np.abs(m - c["m"][k + 1]).max() < tol                                  # the contract
+        # beyond the contract: the transverse pair (1e-73 ... 1e-256 here) agrees as a vector relative to its own magnitude;
+        # free-running, the per-step relative errors accumulate in the exponent of the decay / regrowth
+        assert transverse_rel_err(m, c["m"][k + 1]) < (1e-6 if prec == "f64" else 2e-3), k
         assert abs(float(r[0]) - c["reward"][k]) < tol * max(1.0, abs(c["reward"][k]))
         assert bool(te[0]) == c["terminated"][k]
     assert k >= 8
@@ -82,8 +84,12 @@ def test_c1_single_env_100_pulses(prec, cuda_device):
         env._step_count.fill_(k)
         o, r, te, tr, info = env.step(a[None].copy())
         m = env.magnetization.cpu().numpy()[0]
-        if t_in > 1e-200:
-            assert rel_err(m, c["m"][k + 1]) < (1e-6 if prec == "f64" else 5e-3), k
+        if t_in > 1e-200 and np.hypot(*c["m"][k + 1][:2]) > 1e-300:
+            # beyond the contract: one step from the golden's state keeps the exponentially small transverse pair within the
+            # mode's tolerance relative to its own magnitude (FP32: block-scaled state)
+            assert transverse_rel_err(m, c["m"][k + 1]) < tol, k
+            if prec == "f64":
+                assert rel_err(m, c["m"][k + 1]) < 1e-6, k
         assert np.abs(m - c["m"][k + 1]).max() < tol, k
         assert np.abs(o.cpu().numpy()[0] - c["obs"][k + 1]).max() < tol
         assert abs(float(r[0]) - c["reward"][k]) < tol * max(1.0, abs(c["reward"][k]))
@@ -122,11 +128,13 @@ def _random_setup(n, seed, jm=1.1e-6, tmax=1.5e-9):
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("variant", ["default", "tilted", "euler"])
 def test_random_batch_vs_c_oracle(prec, variant, cuda_device):
-    """4096 envs with ragged substep counts (10..1500), edge-case actions, two consecutive steps."""
+    """4096 envs with ragged substep counts (10..5000: pulses up to max_duration), edge-case actions, two consecutive steps.
+    Every env must meet the mode's tolerance: FP32 stages repeat the few ill-conditioned trajectories with FP64 stages (status
+    bit 2, llgs_core.cuh CondTrack); Euler always runs FP64 stages."""
     from oracle.c_oracle import COracleEnv
     from oracle.stt_oracle import default_stt_params
     n, jm = 4096, 1.1e-6
-    m0, tgt, acts = _random_setup(n, 21)
+    m0, tgt, acts = _random_setup(n, 21, tmax=5e-9)
     p = default_stt_params()
     method = "rk4"
     if variant == "tilted":
@@ -140,24 +148,24 @@ def test_random_batch_vs_c_oracle(prec, variant, cuda_device):
                      nthreads=os.cpu_count() or 1)
     obs0, _ = env.reset(options={"initial_state": m0, "target_state": tgt})
     assert np.array_equal(obs0.cpu().numpy(), ora.reset(m0, tgt))
-    tol = TOL[prec] * (20 if (variant == "euler" and prec == "f32") else 1)
+    tol = TOL[prec]
     for a in acts:
         o, r, te, tr, info = env.step(a.copy())
         oo, orr, ote, otr = ora.step(a)
         assert np.array_equal(info["n_sub"].cpu().numpy(), ora.n_sub)
         err = np.abs(env.magnetization.cpu().numpy() - ora.m).max(1)
-        if prec == "f64":
-            assert err.max() < tol
+        assert err.max() < tol
+        redone = (info["status"].cpu().numpy() & 4) != 0
+        if prec == "f32" and variant == "default":
+            assert 0 < redone.mean() < 0.03 and err[redone].max() < 1e-9 and err[~redone].max() < 2e-5
         else:
-            # FP32 stages: 1e-4 for 99.9 % of random (state, pulse) samples; trajectories that linger on the unstable
-            # equator for >1000 substeps have condition numbers >1e4 and may reach a few 1e-4 (precision)
-            assert np.quantile(err, 0.999) < tol and err.max() < 10 * tol
-        ok = err < tol
-        assert np.abs(o.cpu().numpy() - oo)[ok].max() < tol
-        assert np.allclose(r.cpu().numpy()[ok], orr[ok], rtol=tol, atol=tol)
+            assert not redone.any()              # FP64 stages (also: tilted geometry and Euler through the f32 entry point)
+        # an env sitting within tol of the success threshold may legitimately flip its flag (and with it the +100 of its reward)
         mism = (te.cpu().numpy() != ote)
-        # an env sitting within tol of the success threshold may legitimately flip its flag
-        assert mism.sum() <= 2
+        align = (ora.m * tgt).sum(1)
+        assert np.all(np.abs(align[mism] - 0.9) < tol)
+        assert np.abs(o.cpu().numpy() - oo).max() < tol
+        assert np.allclose(r.cpu().numpy()[~mism], orr[~mism], rtol=tol, atol=tol)
         assert np.array_equal(tr.cpu().numpy(), otr)
         assert np.allclose(info["step_energy"].cpu().numpy(), ora.step_energy, rtol=tol, atol=0)
 
@@ -185,8 +193,51 @@ def test_injected_noise_batch_vs_c_oracle(prec, cuda_device):
     # at the equator m_z is O(1e-8): compare it relatively (never through 1-|m.z|)
     mz, mz_ref = m[:16, 2], ora.m[:16, 2]
     assert np.all(np.abs(mz_ref) < 1e-6)
-    assert np.abs(mz - mz_ref).max() < (1e-6 if prec == "f64" else 2e-3) * np.abs(mz_ref).max()
+    assert np.abs(mz - mz_ref).max() < TOL[prec] * np.abs(mz_ref).max()
     assert np.allclose(r.cpu().numpy(), orr, rtol=TOL[prec], atol=TOL[prec])
+
+
+@pytest.mark.parametrize("pair", [True, False])
+def test_fp32_second_pass_equals_fp64_mode(pair, cuda_device):
+    """stg_stt_step_f32 = FP32 kernel + compacted FP64 pass over the envs it declined (include/stg.h d_redo). The redone envs
+    must carry status bit 2 and the bits of a plain FP64-mode env; statistics, auto-reset rows, sorted launches and pinned host
+    outputs must see them exactly once."""
+    torch = _torch()
+    n, jm = 16384, 1.1e-6
+    m0, tgt, acts = _random_setup(n, 77, tmax=5e-9)
+    for a in acts:
+        a[: n // 4, 0] *= 0.1                     # slow regime: trajectories that linger where the polar rate vanishes
+    kw = dict(max_current=jm, include_thermal_fluctuations=False, autoreset=True, max_steps=2, rng_seed=5)
+    e32 = _make(n, "f32", cuda_device, pair_kernel=pair, sort_by_substeps=True, **kw)
+    e64 = _make(n, "f64", cuda_device, sort_by_substeps=False, **kw)
+    eh = _make(n, "f32", cuda_device, pair_kernel=pair, sort_by_substeps=False, host_outputs=True, **kw)
+    for e in (e32, e64, eh):
+        e.reset(options={"initial_state": m0, "target_state": tgt})
+    seen = 0
+    for a in acts:
+        o32, r32, te32, tr32, i32 = e32.step(a.copy())
+        o64, r64, te64, tr64, i64 = e64.step(a.copy())
+        oh, rh, teh, trh, ih = eh.step(a.copy())
+        redone = (i32["status"] & 4) != 0
+        seen += int(redone.sum())
+        assert not bool(((i64["status"] & 4) != 0).any())
+        assert torch.equal(o32[redone], o64[redone]) and torch.equal(r32[redone], r64[redone])
+        assert torch.equal(i32["final_observation"][redone], i64["final_observation"][redone])
+        assert torch.equal(e32.magnetization[redone], e64.magnetization[redone])
+        assert float((e32.magnetization - e64.magnetization).abs().max()) < 1e-4
+        # host-output env (unsorted launch): same bits as the sorted device-output env, redone rows included
+        assert torch.equal(oh, o32.cpu()) and torch.equal(teh, te32.cpu()) and torch.equal(ih["final_observation"], i32["final_observation"].cpu())
+        assert torch.equal(ih["status"], i32["status"])
+        # envs whose flags differ between the modes sit within tol of the success threshold; align them for the next step
+        mism = te32 != te64
+        align = (e64.magnetization * torch.as_tensor(tgt, device=cuda_device)).sum(1)
+        assert bool(((align[mism] - 0.9).abs() < 1e-4).all())
+        if bool(mism.any()):
+            e32.load_state_dict(e64.state_dict())
+            eh.load_state_dict(e64.state_dict())
+    assert 0 < seen < 0.05 * n * len(acts)
+    st32, st64 = e32.episode_stats(), e64.episode_stats()
+    assert st32["steps"] == st64["steps"] == n * len(acts) and st32["substeps"] == st64["substeps"]
 
 
 @pytest.mark.parametrize("prec", ["f32", "f64"])

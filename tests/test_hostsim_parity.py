@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.helpers import GOLDEN, load_case, noise_for_step, rel_err, stt_params_for
+from tests.helpers import GOLDEN, load_case, noise_for_step, rel_err, stt_params_for, transverse_rel_err
 from tests.hostsim.harness import HostSimEnv
 from oracle.c_oracle import COracleEnv
 
@@ -53,9 +53,12 @@ def test_c1_teacher_forced(f64, general):
         env.total_energy[0] = c["total_energy"][k - 1] if k else 0.0
         env.step_count[0] = k
         o, r, te, tr = env.step(a[None])
-        if t_in > 1e-200 and (f64 or not general):
-            # relative agreement even of the exponentially small transverse components (FP32: 2e-3 of 1e-257)
-            assert rel_err(env.m[:, 0], c["m"][k + 1]) < (1e-6 if f64 else 5e-3), k
+        if t_in > 1e-200 and np.hypot(*c["m"][k + 1][:2]) > 1e-300 and (f64 or not general):
+            # beyond the contract: the exponentially small transverse pair (down to 1e-257) agrees as a vector, relative to
+            # its own magnitude, within the mode's tolerance (FP32: block-scaled state, llgs_core.cuh ScaledState)
+            assert transverse_rel_err(env.m[:, 0], c["m"][k + 1]) < TOL[f64], k
+            if f64:
+                assert rel_err(env.m[:, 0], c["m"][k + 1]) < 1e-6, k
         assert np.abs(env.m[:, 0] - c["m"][k + 1]).max() < TOL[f64], k
         assert abs(r[0] - c["reward"][k]) < TOL[f64] * max(1.0, abs(c["reward"][k]))
         assert te[0] == c["terminated"][k] and tr[0] == c["truncated"][k]
@@ -71,8 +74,10 @@ def test_c1_free_running_prefix(f64):
         o, r, te, tr = env.step(a[None])
         if np.hypot(*c["m"][k + 1][:2]) < 1e-300:
             break
-        assert rel_err(env.m[:, 0], c["m"][k + 1]) < (1e-6 if f64 else 5e-2), k
-        assert np.abs(env.m[:, 0] - c["m"][k + 1]).max() < TOL[f64]
+        assert np.abs(env.m[:, 0] - c["m"][k + 1]).max() < TOL[f64]                 # the contract
+        # beyond the contract: free-running over nine steps the transverse pair decays to 1e-256 and regrows; the per-step
+        # relative errors (test_c1_teacher_forced) accumulate in the exponent, so the free-running bound is looser
+        assert transverse_rel_err(env.m[:, 0], c["m"][k + 1]) < (1e-6 if f64 else 2e-3), k
         assert abs(r[0] - c["reward"][k]) < TOL[f64] * max(1.0, abs(c["reward"][k]))
         assert te[0] == c["terminated"][k] and tr[0] == c["truncated"][k]
     assert k >= 8
@@ -92,23 +97,16 @@ def test_multi_episode_golden(f64):
     assert np.array_equal(te, g["terminated"]) and np.array_equal(tr, g["truncated"])
 
 
-def test_euler_teacher_forced_f32():
-    """The explicit-Euler map with 0.35 rad/substep amplifies rounding differences over an episode (FP64: 1e-11 after 16
-    steps); in FP32 the comparison is therefore per step from the golden's pre-step state."""
+@pytest.mark.parametrize("f64", [True, False])
+def test_euler_free_running(f64):
+    """The explicit-Euler map with 0.35 rad/substep amplifies rounding differences chaotically, so Euler runs FP64 stages
+    through both entry points (stt_kernels.cu: launch_step) and the whole free-running episode agrees to 1e-6."""
     c = load_case("stt_env.npz", "tilted_euler")
-    env = _env(c, False)
+    env = _env(c, f64)
     env.reset(c["m0"], c["target"])
-    worst = 0.0
     for k, a in enumerate(c["actions"]):
-        env.m[:, 0] = c["m"][k]
         env.step(a[None])
-        worst = max(worst, np.abs(env.m[:, 0] - c["m"][k + 1]).max())
-    assert worst < 5e-3
-    env64 = _env(c, True)
-    env64.reset(c["m0"], c["target"])
-    for k, a in enumerate(c["actions"]):
-        env64.step(a[None])
-        assert np.abs(env64.m[:, 0] - c["m"][k + 1]).max() < 1e-6
+        assert np.abs(env.m[:, 0] - c["m"][k + 1]).max() < 1e-6
 
 
 @pytest.mark.parametrize("f64", [True, False])
@@ -133,6 +131,34 @@ def test_random_batch_vs_c_oracle(f64):
         assert np.allclose(hr, orr, rtol=TOL[f64], atol=TOL[f64])
         assert np.array_equal(hte, ote) and np.array_equal(htr, otr)
         assert np.allclose(h.step_energy, o.step_energy, rtol=TOL[f64], atol=0)
+
+
+@pytest.mark.parametrize("pair", [False, True])
+def test_fp32_conditioning_flag(pair):
+    """FP32 stages + conditioning bound (llgs_core.cuh CondTrack): over uniformly random (state, current, pulse <= 5 ns) samples
+    EVERY env ends within the FP32 contract of the FP64 oracle - the few trajectories held near an unstable polar angle for
+    thousands of substeps are detected in flight and repeated with FP64 stages (status bit 2) - and the worst error of the envs
+    that stayed on FP32 stages keeps a wide margin to 1e-4."""
+    rng = np.random.default_rng(31 + pair)
+    n, jm = 8192, 1.1e-6
+    m0 = rng.normal(size=(n, 3))
+    tgt = np.where(rng.integers(2, size=(n, 1)) == 0, 1.0, -1.0) * np.array([[0, 0, 1.0]])
+    act = np.stack([rng.uniform(-jm, jm, n), rng.uniform(0, 5e-9, n)], 1).astype(np.float32)
+    act[: n // 4, 0] *= 0.1                      # a quarter of the batch in the slow regime where W ~ 0 is reachable
+    h = HostSimEnv(n, max_current=jm, include_thermal_fluctuations=False, f64=False, pair=pair)
+    o = COracleEnv(n, max_current=jm, include_thermal=False, nthreads=os.cpu_count() or 1)
+    h.reset(m0, tgt)
+    o.reset(m0, tgt)
+    ho, hr, hte, htr = h.step(act)
+    oo, orr, ote, otr = o.step(act)
+    err = np.abs(h.m.T - o.m).max(1)
+    redone = (h.status & 4) != 0
+    assert err.max() < 1e-4
+    assert err[~redone].max() < 2e-5 and err[redone].max() < 1e-9
+    assert 0 < redone.mean() < 0.03
+    assert np.abs(ho - oo).max() < 1e-4 and np.allclose(hr, orr, rtol=1e-4, atol=1e-4)
+    align = (o.m * tgt).sum(1)
+    assert np.all(np.abs(align[hte != ote] - 0.9) < 1e-4)          # a flag may only differ within tol of the threshold
 
 
 def test_substep_plan_matches_numpy_quirks():
