@@ -115,7 +115,9 @@ typedef struct StgSttStepOut {
     int32_t* status;     /* [n]     0 ok; bit0 non-finite/zero-norm guard fired (m kept); bit1 solver
                                     validation failed (solver_valid==0); bit2 (STG_STATUS_REDONE_F64)
                                     stg_stt_step_f32 repeated this env with FP64 stages (see d_redo)   */
-    float* final_obs;    /* [n][12] with STG_F_AUTORESET: observation before the reset (terminal_observation) */
+    float* final_obs;    /* [n][12] with STG_F_AUTORESET: observation before the reset (terminal_observation). Only the rows of
+                            envs whose episode ended in this step (terminated | truncated) are written; the others keep their
+                            previous contents */
     double* stats;       /* [STG_STAT_REPLICAS][STG_NSTATS] accumulated with atomics (K5 input), see below */
 } StgSttStepOut;
 

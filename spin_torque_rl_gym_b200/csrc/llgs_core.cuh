@@ -133,68 +133,76 @@ STG_HD void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
     box_muller_scaled(u0, u1, -1.3862943611198906f, n0, n1);
 }
 
-// radius uniform from the top 23 bits (no int->float conversion): a in (0, 1], tail of the normals out to 5.65 sigma
-STG_HD float bits_to_open_unit(uint32_t x) {
+// ---- thermal-field stream ------------------------------------------------------------------------------------------------
+// Philox4x32-10, key = the 64-bit seed (uniform over a launch: the key schedule lives in uniform registers), counter =
+// (global env id low word, episode, env step, block index | global env id bits 32..42 << 20): every (env, episode, step, block)
+// owns one counter value, independent of how the batch is partitioned over launches or GPUs (global ids < 2^43, checked by the
+// entry points). Only the last counter word changes inside a step, so the first Philox round and half of the second are
+// loop-invariant.
+//
+// Bit budget of the RK4 path: one 32-bit word per Box-Muller pair (16-bit radius uniform, tail to 4.85 sigma; 16-bit angle =
+// 65,536 directions), i.e. THREE Philox blocks per TWO substeps (12 words -> 12 pairs -> 24 normals = 2 substeps x 4 stages x 3
+// components, drawn in the reference's order: substep, stage, xyz). The Philox multiplies (IMAD.WIDE) are the most expensive
+// instructions of the thermal kernel; round 1 spent two blocks per substep (23-bit radius + 19-bit angle), see profiles/README.md.
+struct NoiseStream {
+    Philox ph;
+    uint32_t c0, c1, c2, c3;      // c3: (gid >> 32) << 20, the block index is added to it
+};
+STG_HD NoiseStream make_stream(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t step) {
+    NoiseStream s;
+    s.ph = Philox{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    s.c0 = (uint32_t)gid; s.c1 = episode; s.c2 = step; s.c3 = (uint32_t)(gid >> 32) << 20;
+    return s;
+}
+STG_HD float bits_as_float(uint32_t u) {
 #if defined(__CUDA_ARCH__)
-    return 2.0f - __uint_as_float(0x3f800000u | (x >> 9));
+    return __uint_as_float(u);
 #else
     union { uint32_t u; float f; } v;
-    v.u = 0x3f800000u | (x >> 9);
-    return 2.0f - v.f;
+    v.u = u;
+    return v.f;
 #endif
 }
-// Box-Muller pair from one 32-bit word `w` (23-bit radius uniform in its top bits, 9 angle bits in its low bits) plus 10 more
-// angle bits `extra` (19-bit angle = 524,288 directions)
-STG_HD void box_muller_packed(uint32_t w, uint32_t extra10, float neg2ln2_scale2, float& n0, float& n1) {
-    const float r = fast_sqrt(neg2ln2_scale2 * fast_lg2(bits_to_open_unit(w)));
-    const uint32_t ang_bits = ((w & 0x1ffu) << 23) | ((extra10 & 0x3ffu) << 13);   // 19 bits in the top of a word
+// Box-Muller pair from ONE 32-bit word: radius uniform U = (hi16 + 1/2) / 65536 in (0, 1), angle = 2 pi lo16 / 65536. Both are
+// formed by dropping the 16 bits into the mantissa of 1.0f (one PRMT / LOP3) and one exact FFMA, no int->float conversion.
+// `neg2ln2_scale2` = -2 ln(2) scale^2 folds the field strength into the radius.
+STG_HD void box_muller16(uint32_t w, float neg2ln2_scale2, float& n0, float& n1) {
+    const float vr = bits_as_float(0x3f800000u | (w >> 16));       // 1 + hi16 2^-23
+    const float va = bits_as_float(0x3f800000u | (w & 0xffffu));   // 1 + lo16 2^-23
+    const float U = fmaf(vr, 128.0f, -127.99999237060546875f);     // 128 vr - (128 - 2^-17) = (hi16 + 1/2) 2^-16, exact
+    const float ang = fmaf(va, 804.24771931898703f, -804.24771931898703f);   // 2 pi 128 (va - 1), one rounding
+    const float r = fast_sqrt(neg2ln2_scale2 * fast_lg2(U));
     float s, c;
-    fast_sincos(bits_to_angle(ang_bits), s, c);
+    fast_sincos(ang, s, c);
     n0 = r * c;
     n1 = r * s;
 }
-
-// 12 samples N(0, scale^2) for the 4 stages of RK4 substep `sub` of env-step `step` of env `gid`.
-// Bit budget: TWO Philox4x32-10 blocks (256 bits) per substep = 6 Box-Muller pairs x (23-bit radius + 19-bit angle). The
-// integer multiplies of Philox are the most expensive instructions of the thermal kernel (ncu: 39 % of its time with three
-// blocks per substep), so the third block that full 32-bit uniforms would need is not spent.
-STG_HD void philox_normals12(const Philox& ph, uint64_t gid, uint32_t step, uint32_t sub, float neg2ln2_scale2,
-                             float xi[12]) {
-    uint32_t a[4], b[4];
-    ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u, a);
-    ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u + 1u, b);
-    // words a0..a3, b0, b1 carry (radius, 9 angle bits); b2, b3 carry 6 x 10 further angle bits
-    box_muller_packed(a[0], b[2], neg2ln2_scale2, xi[0], xi[1]);
-    box_muller_packed(a[1], b[2] >> 10, neg2ln2_scale2, xi[2], xi[3]);
-    box_muller_packed(a[2], b[2] >> 20, neg2ln2_scale2, xi[4], xi[5]);
-    box_muller_packed(a[3], b[3], neg2ln2_scale2, xi[6], xi[7]);
-    box_muller_packed(b[0], b[3] >> 10, neg2ln2_scale2, xi[8], xi[9]);
-    box_muller_packed(b[1], b[3] >> 20, neg2ln2_scale2, xi[10], xi[11]);
+// 24 samples N(0, scale^2): the 4 x 3 stage fields of the RK4 substeps 2g (xi[0..11]) and 2g+1 (xi[12..23])
+STG_HD void philox_normals24(const NoiseStream& ns, uint32_t g, float neg2ln2_scale2, float xi[24]) {
+    uint32_t w[12];
+    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3 + 3u * g, w);
+    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3 + 3u * g + 1u, w + 4);
+    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3 + 3u * g + 2u, w + 8);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) box_muller16(w[k], neg2ln2_scale2, xi[2 * k], xi[2 * k + 1]);
 }
-// same stream, written straight into one half (H = 0: .x, 1: .y) of 12 packed pairs (two-envs-per-thread kernels)
-template <int H, typename P2>
-STG_HD void philox_normals12_half(const Philox& ph, uint64_t gid, uint32_t step, uint32_t sub, float neg2ln2_scale2,
-                                  P2* nz) {
+// the 12 samples of ONE substep (same values as its half of philox_normals24; used around the pulse edge and for odd counts)
+STG_HD void philox_normals12(const NoiseStream& ns, uint32_t sub, float neg2ln2_scale2, float xi[12]) {
+    const uint32_t g = sub >> 1;
+    const bool odd = (sub & 1u) != 0;
+    // substep 2g: words 0..5 = block 3g + first half of block 3g+1; substep 2g+1: second half of block 3g+1 + block 3g+2
     uint32_t a[4], b[4];
-    ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u, a);
-    ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u + 1u, b);
-    float n0, n1;
-#define STG_BM_PAIR(k, w, e)                                              \
-    box_muller_packed(w, e, neg2ln2_scale2, n0, n1);                       \
-    if (H == 0) { nz[2 * (k)].x = n0; nz[2 * (k) + 1].x = n1; }            \
-    else { nz[2 * (k)].y = n0; nz[2 * (k) + 1].y = n1; }
-    STG_BM_PAIR(0, a[0], b[2])
-    STG_BM_PAIR(1, a[1], b[2] >> 10)
-    STG_BM_PAIR(2, a[2], b[2] >> 20)
-    STG_BM_PAIR(3, a[3], b[3])
-    STG_BM_PAIR(4, b[0], b[3] >> 10)
-    STG_BM_PAIR(5, b[1], b[3] >> 20)
-#undef STG_BM_PAIR
+    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3 + 3u * g + 1u, b);
+    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3 + 3u * g + (odd ? 2u : 0u), a);
+    const uint32_t w[6] = {odd ? b[2] : a[0], odd ? b[3] : a[1], odd ? a[0] : a[2], odd ? a[1] : a[3],
+                           odd ? a[2] : b[0], odd ? a[3] : b[1]};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) box_muller16(w[k], neg2ln2_scale2, xi[2 * k], xi[2 * k + 1]);
 }
-STG_HD void philox_normals4(const Philox& ph, uint64_t gid, uint32_t step, uint32_t sub, uint32_t lane,
-                            float neg2ln2_scale2, float xi[4]) {
+// Euler: 3 samples per substep from its own block (full 32-bit uniforms; not a hot path)
+STG_HD void philox_normals3(const NoiseStream& ns, uint32_t sub, float neg2ln2_scale2, float xi[4]) {
     uint32_t o[4];
-    ph((uint32_t)gid, (uint32_t)(gid >> 32), step, sub * 4u + lane, o);
+    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3 + sub, o);
     box_muller_scaled(o[0], o[1], neg2ln2_scale2, xi[0], xi[1]);
     box_muller_scaled(o[2], o[3], neg2ln2_scale2, xi[2], xi[3]);
 }
@@ -588,6 +596,63 @@ STG_HD void rk4_fast(const PackConsts<P>& c, P fx, P fy, P fz, P nq, P q, P aH1,
     cz = K::fma(rho, uz, iz);
 }
 
+// ---- thermal fast path: one merged field per stage ------------------------------------------------------------------------
+// With a thermal field every stage needs the full cross products anyway, so the anisotropy / demagnetisation field c m_z z^ is
+// merged into the noise rotation vector, B = (bn_x, bn_y, c m_z + bn_z), and the two damping-like terms share one product:
+//     p = m x B,   t = alpha p + a (m x z^) = alpha p + a (m_y, -m_x, 0),   k = p + m x t
+// which is  m x B + alpha m x (m x B) + a m x (m x z^)  in 18 FMA-pipe instructions (32 for stage_zp + stage_noisep).
+// COMP: compensated (hi, lo) constants c and a, as the deterministic path carries them - the injected-noise mode, whose parity
+// with the FP64 reference is per trajectory (1e-4). With the in-kernel stream parity is statistical and the constants are plain
+// FP32 (a relative rate error of 3e-8).
+struct ThermalConsts {
+    float c_hi, c_lo, al;
+};
+template <bool COMP>
+STG_HD void stage_th(const ThermalConsts& c, float mx, float my, float mz, float aH, float aL, float bx, float by, float bz,
+                     float& kx, float& ky, float& kz) {
+    using K = Pk<float>;
+    const float Bz = COMP ? K::fma(c.c_hi, mz, K::fma(c.c_lo, mz, bz)) : K::fma(c.c_hi, mz, bz);
+    const float px = K::fma(my, Bz, K::mul(-mz, by));
+    const float py = K::fma(mz, bx, K::mul(-mx, Bz));
+    const float pz = K::fma(mx, by, K::mul(-my, bx));
+    float tx, ty;
+    if (COMP) {
+        tx = K::fma(c.al, px, K::fma(aH, my, K::mul(aL, my)));
+        ty = K::fma(c.al, py, K::fma(-aH, mx, K::mul(-aL, mx)));
+    } else {
+        tx = K::fma(aH, my, K::mul(c.al, px));
+        ty = K::fma(-aH, mx, K::mul(c.al, py));
+    }
+    const float tz = K::mul(c.al, pz);
+    kx = K::fma(my, tz, K::fma(-mz, ty, px));
+    ky = K::fma(mz, tx, K::fma(-mx, tz, py));
+    kz = K::fma(mx, ty, K::fma(-my, tx, pz));
+}
+// RK4 substep of the thermal fast path; same conventions as rk4_fast (constants carry 1/6; outputs increment, correction, d)
+template <bool COMP>
+STG_HD void rk4_thermal(const ThermalConsts& c, float fx, float fy, float fz, float aH1, float aL1, float aH2, float aL2,
+                        float aH4, float aL4, const float* nz, float& ix, float& iy, float& iz, float& cx, float& cy,
+                        float& cz, float& d) {
+    using K = Pk<float>;
+    float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
+    stage_th<COMP>(c, fx, fy, fz, aH1, aL1, nz[0], nz[1], nz[2], k1x, k1y, k1z);
+    stage_th<COMP>(c, K::fma(3.0f, k1x, fx), K::fma(3.0f, k1y, fy), K::fma(3.0f, k1z, fz), aH2, aL2, nz[3], nz[4], nz[5],
+                   k2x, k2y, k2z);
+    stage_th<COMP>(c, K::fma(3.0f, k2x, fx), K::fma(3.0f, k2y, fy), K::fma(3.0f, k2z, fz), aH2, aL2, nz[6], nz[7], nz[8],
+                   k3x, k3y, k3z);
+    stage_th<COMP>(c, K::fma(6.0f, k3x, fx), K::fma(6.0f, k3y, fy), K::fma(6.0f, k3z, fz), aH4, aL4, nz[9], nz[10], nz[11],
+                   k4x, k4y, k4z);
+    ix = K::add(K::fma(2.0f, K::add(k2x, k3x), k1x), k4x);
+    iy = K::add(K::fma(2.0f, K::add(k2y, k3y), k1y), k4y);
+    iz = K::add(K::fma(2.0f, K::add(k2z, k3z), k1z), k4z);
+    const float ux = K::add(fx, ix), uy = K::add(fy, iy), uz = K::add(fz, iz);
+    d = K::fma(iz, K::add(fz, uz), K::fma(ix, K::add(fx, ux), K::mul(iy, K::add(fy, uy))));
+    const float rho = K::mul(d, K::fma(d, K::fma(d, -0.3125f, 0.375f), -0.5f));
+    cx = K::fma(rho, ux, ix);
+    cy = K::fma(rho, uy, iy);
+    cz = K::fma(rho, uz, iz);
+}
+
 struct FastState {
     ScaledState st;
     float fx, fy, fz, q;
@@ -724,18 +789,23 @@ STG_HD bool pulse_on(int i, int stage_kind, double dt, double t_pulse) {
 }
 
 // ---- resistance (devices/stt_mram.py:78-94, devices/sot_mram.py:196-228, devices/vcma_mram.py:236-257) ---------------
+// Multiplications and additions are explicit (no FMA contraction): the same env must get the same bits from every kernel
+// that evaluates it (one- and two-envs-per-thread variants, the FP64 second pass), whatever the compiler fuses elsewhere.
+STG_HD double dot3(double ax, double ay, double az, double bx, double by, double bz) {
+    return dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz));
+}
 STG_HD double resistance(const double* f, double mx, double my, double mz) {
     int kind = (int)f[FI_KIND];
     double rp = f[FI_RP], rap = f[FI_RAP];
     if (kind == 0) {
-        double inv = 1.0 / sqrt(mx * mx + my * my + mz * mz);   // validate_magnetization renormalises (base_device.py:94-116)
-        double c = (mx * f[FI_REFX] + my * f[FI_REFY] + mz * f[FI_REFZ]) * inv;
-        double r = rp * (1.0 + f[FI_TMR] * (1.0 - c) / 2.0);
+        double inv = 1.0 / sqrt(dot3(mx, my, mz, mx, my, mz));   // validate_magnetization renormalises (base_device.py:94-116)
+        double c = dmul(dot3(mx, my, mz, f[FI_REFX], f[FI_REFY], f[FI_REFZ]), inv);
+        double r = dmul(rp, dadd(1.0, dmul(f[FI_TMR], dadd(1.0, -c)) / 2.0));
         double lo = rp * 0.5;
         return r > lo ? r : lo;
     }
-    double c = mx * f[FI_REFX] + my * f[FI_REFY] + mz * f[FI_REFZ];
-    double r = rp + (rap - rp) * (1.0 - c) / 2.0 + f[FI_RSERIES];
+    double c = dot3(mx, my, mz, f[FI_REFX], f[FI_REFY], f[FI_REFZ]);
+    double r = dadd(dadd(rp, dmul(rap - rp, dadd(1.0, -c)) / 2.0), f[FI_RSERIES]);
     return r > 1.0 ? r : 1.0;
 }
 

@@ -11,6 +11,10 @@ namespace stg {
 #define STG_SUBSTEP_UNROLL 4      // measured in stt_kernels.cu (STG_MINBLOCKS_NOISE_F32)
 #endif
 constexpr int kSubstepUnroll = STG_SUBSTEP_UNROLL;
+#ifndef STG_SUBSTEP_PAIR_UNROLL
+#define STG_SUBSTEP_PAIR_UNROLL 2     // thermal fast path: substep pairs per loop iteration (one Philox draw serves two substeps)
+#endif
+constexpr int kSubstepPairUnroll = STG_SUBSTEP_PAIR_UNROLL;
 #ifndef STG_REF_SUBSTEP_UNROLL
 #define STG_REF_SUBSTEP_UNROLL 2      // FP64 thermal 262,144-env step: 4.55 -> 4.45 ms; thermal off and tilted axis unchanged
 #endif
@@ -38,17 +42,17 @@ STG_HD void parse_action(float a0, float a1, double max_current, double max_dura
 }
 
 // Integrate n substeps of size dt from (mx,my,mz); pulse of density J on while t <= t_pulse (envs/spin_torque_env.py:442-443).
-// NOISE: 0 none, 1 Philox, 2 injected tensor [n][S][3]. traj: optional [n+1][3] FP64 rows.
+// NOISE: 0 none, 1 Philox stream `ns`, 2 injected tensor [n][S][3]. traj: optional [n+1][3] FP64 rows.
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>
 STG_HD void integrate(const double* f, double J, double& mx, double& my, double& mz, int n, double dt, double t_pulse,
-                      double t_end, const Philox& ph, uint64_t gid, uint32_t step_id, const double* noise_row, double* traj,
+                      double t_end, const NoiseStream& ns, const double* noise_row, double* traj,
                       int& guard, int64_t noise_rows = 0x7fffffff, int64_t traj_rows = 0x7fffffff, int* illcond = nullptr) {
     // illcond (FP32 fast path without the Philox stream only): set to 1 when the conditioning bound of the trajectory exceeds
     // kCondTol (llgs_core.cuh: CondTrack) - the caller then repeats the env with FP64 stages
     // injected noise: substeps beyond the caller's tensor reuse its last row instead of reading out of bounds
     auto nrow_of = [&](int i) { return (int64_t)(i < noise_rows ? i : noise_rows - 1); };
     constexpr bool TH = NOISE != 0;
-    constexpr bool FAST = sizeof(R) == 4 && AXIS_Z && !EULER;          // substep_fast (llgs_core.cuh)
+    constexpr bool FAST = sizeof(R) == 4 && AXIS_Z && !EULER;          // rk4_fast / rk4_thermal (llgs_core.cuh)
     constexpr bool SCALED = sizeof(R) == 4 && AXIS_Z && !TH;            // block-scaled transverse pair
     constexpr bool TRACK = FAST && NOISE != 1;                          // with the Philox stream parity is statistical
     constexpr int NS = EULER ? 3 : 12;
@@ -68,6 +72,7 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
         make_consts<float>(f, dt, J, 1.0 / 6.0, c);
         PackConsts<float> pc;
         pack_consts<float>(c, c, pc);
+        const ThermalConsts tc{c.c_hi, c.c_lo, c.al_hi};
         const float nscale = -1.3862943611198906f * c.cth * c.cth;      // -2 ln2 * (G h_th / 6)^2
         FastState s;
         s.st = ScaledState{mx, my, mz, 1.0, 1.0, 1.0f};
@@ -75,23 +80,19 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
         fast_resync(s);
         CondTrack ct{0.0f, 0.0f};
         // one substep + the periodic exact renormalisation; `edge` substeps evaluate the pulse gate per stage
-        auto one = [&](int i, bool edge) {
+        auto one = [&](int i, const float* nz, bool edge) {
             float aH1 = c.a_hi, aL1 = c.a_lo, aH2 = c.a_hi, aL2 = c.a_lo, aH4 = c.a_hi, aL4 = c.a_lo;
             if (edge) {
                 if (!pulse_on(i, 0, dt, t_pulse)) { aH1 = 0.0f; aL1 = 0.0f; }
                 if (!pulse_on(i, 1, dt, t_pulse)) { aH2 = 0.0f; aL2 = 0.0f; }
                 if (!pulse_on(i, 2, dt, t_pulse)) { aH4 = 0.0f; aL4 = 0.0f; }
             }
-            float nz[12];
-            if (NOISE == 1) {
-                philox_normals12(ph, gid, step_id, (uint32_t)i, nscale, nz);
-            } else if (NOISE == 2) {
-#pragma unroll
-                for (int q = 0; q < 12; ++q) nz[q] = c.cth * (float)noise_row[nrow_of(i) * 12 + q];
-            }
             float ix, iy, iz, cx, cy, cz, d;
-            rk4_fast<float, TH, SCALED>(pc, s.fx, s.fy, s.fz, -s.q, s.q, aH1, aL1, aH2, aL2, aH4, aL4, TH ? nz : nullptr,
-                                        ix, iy, iz, cx, cy, cz, d);
+            if constexpr (TH)
+                rk4_thermal<NOISE == 2>(tc, s.fx, s.fy, s.fz, aH1, aL1, aH2, aL2, aH4, aL4, nz, ix, iy, iz, cx, cy, cz, d);
+            else
+                rk4_fast<float, false, SCALED>(pc, s.fx, s.fy, s.fz, -s.q, s.q, aH1, aL1, aH2, aL2, aH4, aL4, nullptr,
+                                               ix, iy, iz, cx, cy, cz, d);
             fast_apply(s, ix, iy, iz, cx, cy, cz, d, guard);
             if ((i & STG_RESYNC_MASK) == STG_RESYNC_MASK || traj) {
                 if (TRACK)
@@ -107,9 +108,32 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
             }
         };
         int i = 0;
+        if constexpr (NOISE == 1) {
+            // the stream serves two substeps per draw (three Philox blocks -> 24 normals)
+#pragma unroll kSubstepPairUnroll
+            for (; i + 1 < i_safe; i += 2) {
+                float nz[24];
+                philox_normals24(ns, (uint32_t)i >> 1, nscale, nz);
+                one(i, nz, false);
+                one(i + 1, nz + 12, false);
+            }
+            for (; i < n; ++i) {
+                float nz[12];
+                philox_normals12(ns, (uint32_t)i, nscale, nz);
+                one(i, nz, i >= i_safe);
+            }
+        } else if constexpr (NOISE == 2) {
+            for (; i < n; ++i) {
+                float nz[12];
+#pragma unroll
+                for (int q = 0; q < 12; ++q) nz[q] = c.cth * (float)noise_row[nrow_of(i) * 12 + q];
+                one(i, nz, i >= i_safe);
+            }
+        } else {
 #pragma unroll kSubstepUnroll
-        for (; i < i_safe; ++i) one(i, false);
-        for (; i < n; ++i) one(i, true);
+            for (; i < i_safe; ++i) one(i, nullptr, false);
+            for (; i < n; ++i) one(i, nullptr, true);
+        }
         if (TRACK && illcond) {
             const float s_end = transverse_of(s.fx, s.fy, (float)s.st.inv_s);
             if (!traj && (n & STG_RESYNC_MASK))
@@ -124,42 +148,61 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
         const float nscale = -1.3862943611198906f * (float)c.cth * (float)c.cth;
         ScaledState st{mx, my, mz, 1.0, 1.0, 1.0f};
         if (SCALED) rescale(st);
-#pragma unroll kRefSubstepUnroll
-        for (int i = 0; i < n; ++i) {
+        // one reference-structure substep with the noise rotation components nz (already scaled by cth)
+        auto one = [&](int i, const R* nz) {
             R aH[3] = {c.a_hi, c.a_hi, c.a_hi}, aL[3] = {c.a_lo, c.a_lo, c.a_lo};
             if (i >= i_safe) {
 #pragma unroll
                 for (int g = 0; g < 3; ++g)
                     if (!pulse_on(i, g, dt, t_pulse)) { aH[g] = R(0); aL[g] = R(0); }
             }
-            R nz[NS];
-            if (NOISE == 1) {
-                if (EULER) {
-                    float z[4];
-                    philox_normals4(ph, gid, step_id, (uint32_t)i, 0u, nscale, z);
-                    nz[0] = (R)z[0]; nz[1] = (R)z[1]; nz[2] = (R)z[2];
-                } else {
-                    float z[12];
-                    philox_normals12(ph, gid, step_id, (uint32_t)i, nscale, z);
-#pragma unroll
-                    for (int q = 0; q < 12; ++q) nz[q] = (R)z[q];
-                }
-            } else if (NOISE == 2) {
-#pragma unroll
-                for (int q = 0; q < NS; ++q) nz[q] = c.cth * (R)noise_row[nrow_of(i) * NS + q];
-            }
-            substep_ref<R, AXIS_Z, TH, EULER>(c, st, aH, aL, TH ? nz : nullptr, guard);
+            substep_ref<R, AXIS_Z, TH, EULER>(c, st, aH, aL, nz, guard);
             if (SCALED && (i & 15) == 15) rescale(st);
             if (traj && i + 1 < traj_rows) {
                 traj[3 * (i + 1) + 0] = st.sx * st.inv_s; traj[3 * (i + 1) + 1] = st.sy * st.inv_s;
                 traj[3 * (i + 1) + 2] = st.z;
+            }
+        };
+        int i = 0;
+        if constexpr (NOISE == 1 && !EULER) {
+#pragma unroll 1
+            for (; i + 1 < n; i += 2) {
+                float z[24];
+                philox_normals24(ns, (uint32_t)i >> 1, nscale, z);
+                R nz[24];
+#pragma unroll
+                for (int q = 0; q < 24; ++q) nz[q] = (R)z[q];
+                one(i, nz);
+                one(i + 1, nz + 12);
+            }
+            for (; i < n; ++i) {
+                float z[12];
+                philox_normals12(ns, (uint32_t)i, nscale, z);
+                R nz[12];
+#pragma unroll
+                for (int q = 0; q < 12; ++q) nz[q] = (R)z[q];
+                one(i, nz);
+            }
+        } else {
+#pragma unroll kRefSubstepUnroll
+            for (; i < n; ++i) {
+                R nz[NS];
+                if (NOISE == 1) {       // Euler
+                    float z[4];
+                    philox_normals3(ns, (uint32_t)i, nscale, z);
+                    nz[0] = (R)z[0]; nz[1] = (R)z[1]; nz[2] = (R)z[2];
+                } else if (NOISE == 2) {
+#pragma unroll
+                    for (int q = 0; q < NS; ++q) nz[q] = c.cth * (R)noise_row[nrow_of(i) * NS + q];
+                }
+                one(i, TH ? nz : nullptr);
             }
         }
         mx = st.sx * st.inv_s; my = st.sy * st.inv_s; mz = st.z;
     }
 }
 
-// Two envs per thread through the packed FP32x2 path (FP32 stages, e = z^, RK4; NOISE 0 or 1). Env A lives in the .x halves,
+// Two envs per thread through the packed FP32x2 path (FP32 stages, e = z^, RK4, no thermal field). Env A lives in the .x halves,
 // env B in the .y halves. The envs may have different substep counts: the thread runs to the longer one with the finished
 // env's constants zeroed (its increments are then exactly 0) and its periodic / final renormalisations skipped, so each env's
 // result is bit-identical to the one-env-per-thread path whatever its partner is.
@@ -167,8 +210,6 @@ struct PairEnv {
     const double* f;
     double J, dt, t_pulse;
     int n;
-    uint32_t key_hi, step_id;
-    uint64_t gid;
 };
 // apply the packed rk4_fast result to ONE env (H = 0: .x halves, 1: .y halves) of a pair: FP64 master + its half of the
 // packed FP32 working copy
@@ -198,20 +239,17 @@ STG_HD void pair_renorm(ScaledState& st, F2& fx, F2& fy, F2& fz, F2& q, F2& nq, 
     else { fx.x = (float)st.sx; fy.x = (float)st.sy; fz.x = (float)st.z; q.x = st.inv_s2f; nq.x = -st.inv_s2f; }
 }
 
-template <int NOISE>
-STG_HD void integrate_pair(const PairEnv& A, const PairEnv& B, uint32_t seed_lo, double* mA, double* mB, int& guardA,
-                           int& guardB, int& illA, int& illB) {
-    constexpr bool TH = NOISE != 0;
-    constexpr bool TRACK = NOISE != 1;
+STG_HD void integrate_pair(const PairEnv& A, const PairEnv& B, double* mA, double* mB, int& guardA, int& guardB, int& illA,
+                           int& illB) {
+    constexpr bool TH = false;
+    constexpr bool TRACK = true;
     CondTrack ctA{0.0f, 0.0f}, ctB{0.0f, 0.0f};
-    constexpr bool SCALED = !TH;
+    constexpr bool SCALED = true;
     StepConsts<float> ca, cb;
     make_consts<float>(A.f, A.dt, A.J, 1.0 / 6.0, ca);
     make_consts<float>(B.f, B.dt, B.J, 1.0 / 6.0, cb);
     PackConsts<F2> pc;
     pack_consts<F2>(ca, cb, pc);
-    const float nsa = -1.3862943611198906f * ca.cth * ca.cth, nsb = -1.3862943611198906f * cb.cth * cb.cth;
-    const Philox pha{seed_lo, A.key_hi}, phb{seed_lo, B.key_hi};
     ScaledState sa{mA[0], mA[1], mA[2], 1.0, 1.0, 1.0f}, sb{mB[0], mB[1], mB[2], 1.0, 1.0, 1.0f};
     if (SCALED) { rescale(sa); rescale(sb); }
     // packed FP32 working copy: env A in the .x halves, env B in the .y halves
@@ -220,7 +258,6 @@ STG_HD void integrate_pair(const PairEnv& A, const PairEnv& B, uint32_t seed_lo,
     const int n_max = A.n > B.n ? A.n : B.n;
     const int edge_from = (A.n < B.n ? A.n : B.n) - 1;     // the env loop always passes t_end == t_pulse: i_safe = n - 1
     F2 aH = mk2(ca.a_hi, cb.a_hi), aL = mk2(ca.a_lo, cb.a_lo);
-    F2 nz[12];
     auto one = [&](int i, bool edge) {
         F2 aH4 = aH, aL4 = aL;
         bool runA = true, runB = true;
@@ -233,16 +270,8 @@ STG_HD void integrate_pair(const PairEnv& A, const PairEnv& B, uint32_t seed_lo,
             if (runA && i == A.n - 1 && !pulse_on(i, 2, A.dt, A.t_pulse)) { aH4.x = 0.0f; aL4.x = 0.0f; }
             if (runB && i == B.n - 1 && !pulse_on(i, 2, B.dt, B.t_pulse)) { aH4.y = 0.0f; aL4.y = 0.0f; }
         }
-        if (NOISE == 1) {
-            philox_normals12_half<0>(pha, A.gid, A.step_id, (uint32_t)i, nsa, nz);
-            philox_normals12_half<1>(phb, B.gid, B.step_id, (uint32_t)i, nsb, nz);
-            if (edge) {
-#pragma unroll
-                for (int k = 0; k < 12; ++k) { if (!runA) nz[k].x = 0.0f; if (!runB) nz[k].y = 0.0f; }
-            }
-        }
         F2 ix, iy, iz, cx, cy, cz, d;
-        rk4_fast<F2, TH, SCALED>(pc, fx, fy, fz, nq, q, aH, aL, aH, aL, aH4, aL4, TH ? nz : nullptr, ix, iy, iz, cx, cy, cz, d);
+        rk4_fast<F2, TH, SCALED>(pc, fx, fy, fz, nq, q, aH, aL, aH, aL, aH4, aL4, nullptr, ix, iy, iz, cx, cy, cz, d);
         if (runA) pair_apply<0>(sa, fx, fy, fz, q, nq, ix, iy, iz, cx, cy, cz, d, guardA);
         if (runB) pair_apply<1>(sb, fx, fy, fz, q, nq, ix, iy, iz, cx, cy, cz, d, guardB);
         if ((i & STG_RESYNC_MASK) == STG_RESYNC_MASK) {
@@ -350,7 +379,7 @@ STG_HD void env_step_prologue(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c)
     c.total_e = a.state.total_energy[e];
     c.step = a.state.step_count[e];
     parse_action(a.d_action[2 * e], a.d_action[2 * e + 1], c.f[FI_MAXCUR], c.f[FI_MAXDUR], c.J, c.T);
-    c.prev_align = c.mx * c.tx + c.my * c.ty + c.mz * c.tz;                   // envs/spin_torque_env.py:338-339
+    c.prev_align = dot3(c.mx, c.my, c.mz, c.tx, c.ty, c.tz);                  // envs/spin_torque_env.py:338-339
     c.plan = substep_plan(c.T, c.f[FI_MAXSTEP_DT]);
     c.w[0] = c.mx; c.w[1] = c.my; c.w[2] = c.mz;
     c.guard = 0;
@@ -370,7 +399,7 @@ STG_HD void env_step_epilogue(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c,
     int status = status_bits;
     if (c.valid) {
         // env-level renormalisation of the last trajectory row (envs/spin_torque_env.py:464)
-        const double inv = 1.0 / sqrt(c.w[0] * c.w[0] + c.w[1] * c.w[1] + c.w[2] * c.w[2]);
+        const double inv = 1.0 / sqrt(dot3(c.w[0], c.w[1], c.w[2], c.w[0], c.w[1], c.w[2]));
         nx = c.w[0] * inv; ny = c.w[1] * inv; nz = c.w[2] * inv;
         if (c.guard) {   // A3: a trajectory row failed validation => solver result discarded, m unchanged
             nx = mx; ny = my; nz = mz;
@@ -389,13 +418,13 @@ STG_HD void env_step_epilogue(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c,
     }
     double total_e = c.total_e + energy;
     int step = c.step + 1;
-    const double align = nx * tx + ny * ty + nz * tz;                           // :350-353
+    const double align = dot3(nx, ny, nz, tx, ty, tz);                          // :350-353
     const bool success = align >= f[FI_SUCC];
     // CompositeReward default components in dict order (:184-207), then validate_reward (utils/monitoring.py:332-348)
-    double reward = 0.0;
-    reward += 10.0 * (success ? 10.0 : 0.0);
-    reward += (-f[FI_WE]) * (-energy / 1e-12);
-    reward += 1.0 * (align - c.prev_align);
+    // (explicit products and sums: see dot3 in llgs_core.cuh)
+    double reward = success ? 100.0 : 0.0;                                       // 10.0 * (10.0 if success else 0.0)
+    reward = dadd(reward, dmul(-f[FI_WE], -energy / 1e-12));
+    reward = dadd(reward, dadd(align, -c.prev_align));
     if (!(fabs(reward) <= 1.7e308)) reward = -1.0;
     reward = fmin(fmax(reward, -1e6), 1e6);
     const bool truncated = step >= (int)f[FI_MAXSTEPS];                          // :371-372
@@ -433,20 +462,18 @@ STG_HD void env_step_epilogue(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c,
     if (a.out.status) a.out.status[e] = status;
 }
 
-// Philox stream of one env-step: key = (seed_lo, seed_hi ^ episode), counter = (global env id, step, 4*substep + block)
-// -> every (env, episode, step, substep) draws from its own counter block, independent of the batch partitioning
+// Thermal-field stream of one env-step (llgs_core.cuh NoiseStream): key = seed, counter = (global env id, episode, step, block)
+// -> every (env, episode, step, substep) draws from its own counter blocks, independent of the batch partitioning
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>
 STG_HD void env_step_integrate(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c) {
-    const Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ (uint32_t)a.state.episode[e]};
-    const uint64_t gid = a.env_offset + (uint64_t)e;
+    const NoiseStream ns = make_stream(a.seed, a.env_offset + (uint64_t)e, (uint32_t)a.state.episode[e], (uint32_t)c.step);
     const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
-    const uint32_t step_id = (uint32_t)c.step;
     if (c.f[FI_HTH] > 0.0 || NOISE == 0)
-        integrate<R, AXIS_Z, NOISE, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ph, gid, step_id,
+        integrate<R, AXIS_Z, NOISE, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ns,
                                            nrow, nullptr, c.guard, NOISE == 2 ? a.noise_stride : 0x7fffffff, 0x7fffffff,
                                            &c.illcond);
     else
-        integrate<R, AXIS_Z, 0, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ph, gid, step_id,
+        integrate<R, AXIS_Z, 0, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ns,
                                        nullptr, nullptr, c.guard, 0x7fffffff, 0x7fffffff, &c.illcond);
 }
 
@@ -464,23 +491,19 @@ STG_HD bool env_step_body(const StgSttStepArgs& a, int64_t e, EnvStepResult& r, 
     return true;
 }
 
-// Two envs (eA, eB) through the packed FP32x2 integrator (R = float, e = z^, RK4, NOISE 0 or 1). Returns a mask of the envs
+// Two envs (eA, eB) through the packed FP32x2 integrator (R = float, e = z^, RK4, no thermal field). Returns a mask of the envs
 // that were NOT stepped because their FP32 trajectory is ill-conditioned (bit 0: eA, bit 1: eB; see env_step_body).
-template <int NOISE>
 STG_HD int env_step_pair_body(const StgSttStepArgs& a, int64_t eA, int64_t eB, EnvStepResult& rA, EnvStepResult& rB) {
     EnvStepCtx ca, cb;
     env_step_prologue<float, true>(a, eA, ca);
     env_step_prologue<float, true>(a, eB, cb);
-    const bool noise_ok = NOISE == 0 || (ca.f[FI_HTH] > 0.0 && cb.f[FI_HTH] > 0.0);
-    if (ca.valid && cb.valid && noise_ok) {
-        PairEnv A{ca.f, ca.J, ca.plan.dt, ca.T, ca.plan.n, (uint32_t)(a.seed >> 32) ^ (uint32_t)a.state.episode[eA],
-                  (uint32_t)ca.step, a.env_offset + (uint64_t)eA};
-        PairEnv B{cb.f, cb.J, cb.plan.dt, cb.T, cb.plan.n, (uint32_t)(a.seed >> 32) ^ (uint32_t)a.state.episode[eB],
-                  (uint32_t)cb.step, a.env_offset + (uint64_t)eB};
-        integrate_pair<NOISE>(A, B, (uint32_t)a.seed, ca.w, cb.w, ca.guard, cb.guard, ca.illcond, cb.illcond);
+    if (ca.valid && cb.valid) {
+        PairEnv A{ca.f, ca.J, ca.plan.dt, ca.T, ca.plan.n};
+        PairEnv B{cb.f, cb.J, cb.plan.dt, cb.T, cb.plan.n};
+        integrate_pair(A, B, ca.w, cb.w, ca.guard, cb.guard, ca.illcond, cb.illcond);
     } else {
-        if (ca.valid) env_step_integrate<float, true, NOISE, false>(a, eA, ca);
-        if (cb.valid) env_step_integrate<float, true, NOISE, false>(a, eB, cb);
+        if (ca.valid) env_step_integrate<float, true, 0, false>(a, eA, ca);
+        if (cb.valid) env_step_integrate<float, true, 0, false>(a, eB, cb);
     }
     if (!ca.illcond) env_step_epilogue(a, eA, ca, rA);
     if (!cb.illcond) env_step_epilogue(a, eB, cb, rB);
@@ -539,7 +562,7 @@ STG_HD void solve_body(const StgSttSolveArgs& a, int64_t e) {
             plan.dt = ddiv(t_end, (double)nv);
         }
         nsub = plan.n;
-        Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+        const NoiseStream ns = make_stream(a.seed, a.env_offset + (uint64_t)e, 0u, 0u);
         const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
         double* traj = a.d_traj ? a.d_traj + (int64_t)e * a.traj_stride * 3 : nullptr;
         // the solver API repeats an ill-conditioned FP32 trajectory with FP64 stages on the spot (CondTrack, llgs_core.cuh)
@@ -547,22 +570,18 @@ STG_HD void solve_body(const StgSttSolveArgs& a, int64_t e) {
         const int guard0 = guard;
         int ill = 0;
         if (f[FI_HTH] > 0.0 || NOISE == 0)
-            integrate<R, AXIS_Z, NOISE, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph,
-                                               a.env_offset + (uint64_t)e, 0u, nrow, traj, guard,
+            integrate<R, AXIS_Z, NOISE, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ns, nrow, traj, guard,
                                                NOISE == 2 ? a.noise_stride : 0x7fffffff, traj ? a.traj_stride : 0x7fffffff, &ill);
         else
-            integrate<R, AXIS_Z, 0, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph, a.env_offset + (uint64_t)e,
-                                           0u, nullptr, traj, guard, 0x7fffffff, traj ? a.traj_stride : 0x7fffffff, &ill);
+            integrate<R, AXIS_Z, 0, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ns, nullptr, traj, guard, 0x7fffffff, traj ? a.traj_stride : 0x7fffffff, &ill);
         if (sizeof(R) == 4 && ill) {
             mx = sx; my = sy; mz = sz; guard = guard0;
             if (f[FI_HTH] > 0.0 || NOISE == 0)
-                integrate<double, AXIS_Z, NOISE, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph,
-                                                        a.env_offset + (uint64_t)e, 0u, nrow, traj, guard,
+                integrate<double, AXIS_Z, NOISE, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ns, nrow, traj, guard,
                                                         NOISE == 2 ? a.noise_stride : 0x7fffffff,
                                                         traj ? a.traj_stride : 0x7fffffff);
             else
-                integrate<double, AXIS_Z, 0, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ph,
-                                                    a.env_offset + (uint64_t)e, 0u, nullptr, traj, guard, 0x7fffffff,
+                integrate<double, AXIS_Z, 0, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, t_end, ns, nullptr, traj, guard, 0x7fffffff,
                                                     traj ? a.traj_stride : 0x7fffffff);
         }
     }
@@ -576,7 +595,7 @@ STG_HD void solve_body(const StgSttSolveArgs& a, int64_t e) {
 // general-geometry stages; a rectangular pulse (J, t_pulse) is used when only the field is sampled.
 template <int NOISE, bool EULER>
 STG_HD void integrate_grid(const double* f, double J, double& mx, double& my, double& mz, int n, double dt, double t_pulse,
-                           const double* jgrid, const double* hgrid, int64_t grid_rows, const Philox& ph, uint64_t gid,
+                           const double* jgrid, const double* hgrid, int64_t grid_rows, const NoiseStream& ns,
                            const double* noise_row, double* traj, int& guard, int64_t noise_rows, int64_t traj_rows) {
     constexpr bool TH = NOISE != 0;
     constexpr int NS = EULER ? 3 : 12;
@@ -591,8 +610,8 @@ STG_HD void integrate_grid(const double* f, double J, double& mx, double& my, do
         double nz[NS];
         if (NOISE == 1) {
             float z[12];
-            if (EULER) philox_normals4(ph, gid, 0u, (uint32_t)i, 0u, nscale, z);
-            else philox_normals12(ph, gid, 0u, (uint32_t)i, nscale, z);
+            if (EULER) philox_normals3(ns, (uint32_t)i, nscale, z);
+            else philox_normals12(ns, (uint32_t)i, nscale, z);
 #pragma unroll
             for (int q = 0; q < NS; ++q) nz[q] = (double)z[q];
         } else if (NOISE == 2) {
@@ -643,19 +662,17 @@ STG_HD void solve_grid_body(const StgSttSolveArgs& a, int64_t e) {
     if (t_end > 0.0) {
         const StepPlan plan = substep_plan(t_end, f[FI_MAXSTEP_DT]);
         nsub = plan.n;
-        Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+        const NoiseStream ns = make_stream(a.seed, a.env_offset + (uint64_t)e, 0u, 0u);
         const int64_t ge = a.grid_envs == 1 ? 0 : e;
         const double* jg = a.d_current_grid ? a.d_current_grid + ge * a.grid_stride * 3 : nullptr;
         const double* hg = a.d_field_grid ? a.d_field_grid + ge * a.grid_stride * 9 : nullptr;
         const double* nrow = (NOISE == 2) ? a.d_noise + (int64_t)e * a.noise_stride * (EULER ? 3 : 12) : nullptr;
         double* traj = a.d_traj ? a.d_traj + (int64_t)e * a.traj_stride * 3 : nullptr;
         if (f[FI_HTH] > 0.0 || NOISE == 0)
-            integrate_grid<NOISE, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, jg, hg, a.grid_stride, ph,
-                                         a.env_offset + (uint64_t)e, nrow, traj, guard,
+            integrate_grid<NOISE, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, jg, hg, a.grid_stride, ns, nrow, traj, guard,
                                          NOISE == 2 ? a.noise_stride : 0x7fffffff, traj ? a.traj_stride : 0x7fffffff);
         else
-            integrate_grid<0, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, jg, hg, a.grid_stride, ph,
-                                     a.env_offset + (uint64_t)e, nullptr, traj, guard, 0x7fffffff,
+            integrate_grid<0, EULER>(f, J, mx, my, mz, plan.n, plan.dt, t_pulse, jg, hg, a.grid_stride, ns, nullptr, traj, guard, 0x7fffffff,
                                      traj ? a.traj_stride : 0x7fffffff);
     }
     a.d_m_out[3 * e] = mx; a.d_m_out[3 * e + 1] = my; a.d_m_out[3 * e + 2] = mz;

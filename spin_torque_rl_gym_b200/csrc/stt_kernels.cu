@@ -49,13 +49,10 @@ using ResetArgs = StgSttResetArgs;
 using SolveArgs = StgSttSolveArgs;
 
 // An env the FP32 stages declined (env_step_body returned false, nothing written): append it to the list of the second pass.
-// Its rows of this launch's cooperative observation stores are zeros and are overwritten by that pass.
-__device__ __forceinline__ void redo_push(const StgSttStepArgs& a, int64_t e, EnvStepResult& r) {
+// This launch writes NOTHING for it - no observation row, no flags, no statistics; the second pass writes all of them.
+__device__ __forceinline__ void redo_push(const StgSttStepArgs& a, int64_t e) {
     const int pos = atomicAdd(a.d_redo, 1);
     a.d_redo[STG_REDO_HEADER + pos] = (int32_t)e;
-#pragma unroll
-    for (int q = 0; q < kObs; ++q) { r.obs[q] = 0.0f; r.final_obs[q] = 0.0f; }
-    r.did_reset = false;
 }
 
 __device__ __forceinline__ void store_row(float* dst, const float* o) {
@@ -69,6 +66,7 @@ template <typename R, bool AXIS_Z, int NOISE, bool EULER>
 __global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_MINBLOCKS_DET : (sizeof(R) == 4 ? STG_MINBLOCKS_NOISE_F32 : STG_MINBLOCKS_NOISE))
 stt_env_step_kernel(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) float s_obs[kBlock * kObs];
+    __shared__ uint8_t s_skip[kBlock];
     const int64_t slot = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool active = slot < a.n_envs;
     const bool sorted = (a.flags & STG_F_SORTED) != 0;
@@ -80,46 +78,32 @@ stt_env_step_kernel(const __grid_constant__ StepArgs a) {
     bool stepped = active;
     if (active) {
         stepped = env_step_body<R, AXIS_Z, NOISE, EULER>(a, e, r);
-        if (!stepped) redo_push(a, e, r);      // FP32 stages only: repeated with FP64 stages by stt_env_redo_kernel
+        if (!stepped) redo_push(a, e);      // FP32 stages only: repeated with FP64 stages by stt_env_redo_kernel
     }
 
     // ---- observation rows ------------------------------------------------------------------------------------------------
     if (!sorted) {
         // consecutive slots are consecutive envs: stage rows in shared memory, write the block's rows as coalesced float4s
+        // (rows of envs left to the second pass are skipped)
         const int64_t base = (int64_t)blockIdx.x * kBlock;
         const int64_t rows = (a.n_envs - base) < kBlock ? (a.n_envs - base) : kBlock;
         const int n4 = (int)(rows * kObs / 4);   // rows*12 floats is always a multiple of 4
-        if (active) {
+        if (stepped) {
 #pragma unroll
             for (int q = 0; q < kObs; ++q) s_obs[threadIdx.x * kObs + q] = r.obs[q];
         }
+        s_skip[threadIdx.x] = stepped ? 0 : 1;
         __syncthreads();
-        {
-            float4* dst = reinterpret_cast<float4*>(a.out.obs + base * kObs);
-            const float4* src = reinterpret_cast<const float4*>(s_obs);
-            for (int q = threadIdx.x; q < n4; q += kBlock) dst[q] = src[q];
-        }
-        if (want_fin) {   // rows of envs that did not reset are written as zeros
-            __syncthreads();
-            if (active) {
-#pragma unroll
-                for (int q = 0; q < kObs; ++q) s_obs[threadIdx.x * kObs + q] = r.did_reset ? r.final_obs[q] : 0.0f;
-            }
-            __syncthreads();
-            float4* dst = reinterpret_cast<float4*>(a.out.final_obs + base * kObs);
-            const float4* src = reinterpret_cast<const float4*>(s_obs);
-            for (int q = threadIdx.x; q < n4; q += kBlock) dst[q] = src[q];
-        }
-    } else if (active) {
+        float4* dst = reinterpret_cast<float4*>(a.out.obs + base * kObs);
+        const float4* src = reinterpret_cast<const float4*>(s_obs);
+        for (int q = threadIdx.x; q < n4; q += kBlock)
+            if (!s_skip[q / (kObs / 4)]) dst[q] = src[q];
+    } else if (stepped) {
         store_row(a.out.obs + e * kObs, r.obs);
-        if (want_fin) {
-            if (!r.did_reset) {
-#pragma unroll
-                for (int q = 0; q < kObs; ++q) r.final_obs[q] = 0.0f;
-            }
-            store_row(a.out.final_obs + e * kObs, r.final_obs);
-        }
     }
+    // last observation of an episode that ended in this step: written for those envs only (rows of the other envs keep what
+    // they held; the caller selects rows with terminated | truncated)
+    if (want_fin && stepped && r.did_reset) store_row(a.out.final_obs + e * kObs, r.final_obs);
 
     // ---- episode statistics: warp shuffle reduction, one atomic per warp and statistic (K5 input) ---------------------
     if (a.out.stats) {
@@ -146,7 +130,7 @@ stt_env_step_kernel(const __grid_constant__ StepArgs a) {
 }
 
 // ---- two envs per thread: packed FP32x2 (FFMA2) variant of the fast path ------------------------------------------------
-// R = float, e = z^, RK4, NOISE in {0 (none), 1 (Philox)}. Thread t of a CTA owns the adjacent slots 2t, 2t+1, so the FP64
+// R = float, e = z^, RK4, no thermal field. Thread t of a CTA owns the adjacent slots 2t, 2t+1, so the FP64
 // state planes are read as 16-byte pairs and one CTA covers 2*kBlock observation rows.
 __device__ __forceinline__ void accumulate_stats(double* v, const EnvStepResult& r) {
     const bool ended = r.terminated || r.truncated;
@@ -163,12 +147,9 @@ __device__ __forceinline__ void accumulate_stats(double* v, const EnvStepResult&
 #ifndef STG_PAIR_MINBLOCKS
 #define STG_PAIR_MINBLOCKS 8
 #endif
-#ifndef STG_PAIR_MINBLOCKS_TH
-#define STG_PAIR_MINBLOCKS_TH 1
-#endif
-template <int NOISE>
-__global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : STG_PAIR_MINBLOCKS_TH) stt_env_step_pair_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kBlock, STG_PAIR_MINBLOCKS) stt_env_step_pair_kernel(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) float s_obs[2 * kBlock * kObs];
+    __shared__ uint8_t s_skip[2 * kBlock];
     const int64_t base = (int64_t)blockIdx.x * (2 * kBlock);
     const int64_t slotA = base + 2 * threadIdx.x, slotB = slotA + 1;
     const bool actA = slotA < a.n_envs, actB = slotB < a.n_envs;
@@ -180,63 +161,41 @@ __global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : STG_
     EnvStepResult rA, rB;
     rA.did_reset = rB.did_reset = false;
     int redo = 0;
-    if (actB) redo = env_step_pair_body<NOISE>(a, eA, eB, rA, rB);
-    else if (actA) redo = env_step_body<float, true, NOISE, false>(a, eA, rA) ? 0 : 1;
-    if (redo & 1) redo_push(a, eA, rA);
-    if (redo & 2) redo_push(a, eB, rB);
+    if (actB) redo = env_step_pair_body(a, eA, eB, rA, rB);
+    else if (actA) redo = env_step_body<float, true, 0, false>(a, eA, rA) ? 0 : 1;
+    if (redo & 1) redo_push(a, eA);
+    if (redo & 2) redo_push(a, eB);
+    const bool doneA = actA && !(redo & 1), doneB = actB && !(redo & 2);
 
     if (!sorted) {
         const int64_t rows = (a.n_envs - base) < 2 * kBlock ? (a.n_envs - base) : 2 * kBlock;
         const int n4 = (int)(rows * kObs / 4);
 #pragma unroll
         for (int q = 0; q < kObs; ++q) {
-            if (actA) s_obs[(2 * threadIdx.x) * kObs + q] = rA.obs[q];
-            if (actB) s_obs[(2 * threadIdx.x + 1) * kObs + q] = rB.obs[q];
+            if (doneA) s_obs[(2 * threadIdx.x) * kObs + q] = rA.obs[q];
+            if (doneB) s_obs[(2 * threadIdx.x + 1) * kObs + q] = rB.obs[q];
         }
+        s_skip[2 * threadIdx.x] = doneA ? 0 : 1;
+        s_skip[2 * threadIdx.x + 1] = doneB ? 0 : 1;
         __syncthreads();
-        {
-            float4* dst = reinterpret_cast<float4*>(a.out.obs + base * kObs);
-            const float4* src = reinterpret_cast<const float4*>(s_obs);
-            for (int q = threadIdx.x; q < n4; q += kBlock) dst[q] = src[q];
-        }
-        if (want_fin) {   // rows of envs that did not reset are written as zeros
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < kObs; ++q) {
-                if (actA) s_obs[(2 * threadIdx.x) * kObs + q] = rA.did_reset ? rA.final_obs[q] : 0.0f;
-                if (actB) s_obs[(2 * threadIdx.x + 1) * kObs + q] = rB.did_reset ? rB.final_obs[q] : 0.0f;
-            }
-            __syncthreads();
-            float4* dst = reinterpret_cast<float4*>(a.out.final_obs + base * kObs);
-            const float4* src = reinterpret_cast<const float4*>(s_obs);
-            for (int q = threadIdx.x; q < n4; q += kBlock) dst[q] = src[q];
-        }
+        float4* dst = reinterpret_cast<float4*>(a.out.obs + base * kObs);
+        const float4* src = reinterpret_cast<const float4*>(s_obs);
+        for (int q = threadIdx.x; q < n4; q += kBlock)
+            if (!s_skip[q / (kObs / 4)]) dst[q] = src[q];
     } else {
-        if (actA) store_row(a.out.obs + eA * kObs, rA.obs);
-        if (actB) store_row(a.out.obs + eB * kObs, rB.obs);
-        if (want_fin) {
-            if (actA) {
-                if (!rA.did_reset) {
-#pragma unroll
-                    for (int q = 0; q < kObs; ++q) rA.final_obs[q] = 0.0f;
-                }
-                store_row(a.out.final_obs + eA * kObs, rA.final_obs);
-            }
-            if (actB) {
-                if (!rB.did_reset) {
-#pragma unroll
-                    for (int q = 0; q < kObs; ++q) rB.final_obs[q] = 0.0f;
-                }
-                store_row(a.out.final_obs + eB * kObs, rB.final_obs);
-            }
-        }
+        if (doneA) store_row(a.out.obs + eA * kObs, rA.obs);
+        if (doneB) store_row(a.out.obs + eB * kObs, rB.obs);
+    }
+    if (want_fin) {      // see stt_env_step_kernel
+        if (doneA && rA.did_reset) store_row(a.out.final_obs + eA * kObs, rA.final_obs);
+        if (doneB && rB.did_reset) store_row(a.out.final_obs + eB * kObs, rB.final_obs);
     }
     if (a.out.stats) {
         double v[STG_NSTATS];
 #pragma unroll
         for (int q = 0; q < STG_NSTATS; ++q) v[q] = 0.0;
-        if (actA && !(redo & 1)) accumulate_stats(v, rA);
-        if (actB && !(redo & 2)) accumulate_stats(v, rB);
+        if (doneA) accumulate_stats(v, rA);
+        if (doneB) accumulate_stats(v, rB);
 #pragma unroll
         for (int q = 0; q < STG_NSTATS; ++q) {
             const double sum = warp_sum(v[q]);
@@ -248,6 +207,7 @@ __global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : STG_
 // ---- second pass of stg_stt_step_f32: the envs the FP32 stages declined, compacted, with FP64 stages ---------------------
 // Grid-stride over the list d_redo[STG_REDO_HEADER ..] (count in d_redo[0], written by the first pass on the same stream).
 // Typically empty or a fraction of a per cent of the batch, so rows are stored per thread and statistics added per thread.
+// It is the only writer of these envs' outputs: the first pass leaves their rows untouched.
 template <int NOISE>
 __global__ void __launch_bounds__(kBlock) stt_env_redo_kernel(const __grid_constant__ StepArgs a) {
     const int64_t count = a.d_redo[0] < a.n_envs ? (int64_t)a.d_redo[0] : a.n_envs;
@@ -258,13 +218,7 @@ __global__ void __launch_bounds__(kBlock) stt_env_redo_kernel(const __grid_const
         r.did_reset = false;
         env_step_body<double, true, NOISE, false>(a, e, r, STG_STATUS_REDONE_F64);
         store_row(a.out.obs + e * kObs, r.obs);
-        if (want_fin) {
-            if (!r.did_reset) {
-#pragma unroll
-                for (int q = 0; q < kObs; ++q) r.final_obs[q] = 0.0f;
-            }
-            store_row(a.out.final_obs + e * kObs, r.final_obs);
-        }
+        if (want_fin && r.did_reset) store_row(a.out.final_obs + e * kObs, r.final_obs);
         if (a.out.stats) {
             double v[STG_NSTATS];
 #pragma unroll
@@ -398,7 +352,7 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
             // Measured (profiles/README.md): +12 % without thermal noise. With the Philox stream the packed variant needs
             // 201 registers and loses (the integer Philox rounds do not pack), so it is not dispatched there.
             const unsigned grid = (unsigned)((a.n_envs + 2 * kBlock - 1) / (2 * kBlock));
-            stt_env_step_pair_kernel<0><<<grid, kBlock, 0, s>>>(a);
+            stt_env_step_pair_kernel<<<grid, kBlock, 0, s>>>(a);
             err = cudaGetLastError();
         } else {
             err = noise == 0 ? launch_step2<float, true, 0>(a, s) : launch_step2<float, true, 2>(a, s);
