@@ -163,42 +163,6 @@ STG_HD float bits_as_float(uint32_t u) {
     return v.f;
 #endif
 }
-// Box-Muller pair from ONE 32-bit word: radius uniform U = (hi16 + 1/2) / 65536 in (0, 1), angle = 2 pi lo16 / 65536. Both are
-// formed by dropping the 16 bits into the mantissa of 1.0f (one PRMT / LOP3) and one exact FFMA, no int->float conversion.
-// `neg2ln2_scale2` = -2 ln(2) scale^2 folds the field strength into the radius.
-STG_HD void box_muller16(uint32_t w, float neg2ln2_scale2, float& n0, float& n1) {
-    const float vr = bits_as_float(0x3f800000u | (w >> 16));       // 1 + hi16 2^-23
-    const float va = bits_as_float(0x3f800000u | (w & 0xffffu));   // 1 + lo16 2^-23
-    const float U = fmaf(vr, 128.0f, -127.99999237060546875f);     // 128 vr - (128 - 2^-17) = (hi16 + 1/2) 2^-16, exact
-    const float ang = fmaf(va, 804.24771931898703f, -804.24771931898703f);   // 2 pi 128 (va - 1), one rounding
-    const float r = fast_sqrt(neg2ln2_scale2 * fast_lg2(U));
-    float s, c;
-    fast_sincos(ang, s, c);
-    n0 = r * c;
-    n1 = r * s;
-}
-// 24 samples N(0, scale^2): the 4 x 3 stage fields of the RK4 substeps 2g (xi[0..11]) and 2g+1 (xi[12..23])
-STG_HD void philox_normals24(const NoiseStream& ns, uint32_t g, float neg2ln2_scale2, float xi[24]) {
-    uint32_t w[12];
-    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3 + 3u * g, w);
-    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3 + 3u * g + 1u, w + 4);
-    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3 + 3u * g + 2u, w + 8);
-#pragma unroll
-    for (int k = 0; k < 12; ++k) box_muller16(w[k], neg2ln2_scale2, xi[2 * k], xi[2 * k + 1]);
-}
-// the 12 samples of ONE substep (same values as its half of philox_normals24; used around the pulse edge and for odd counts)
-STG_HD void philox_normals12(const NoiseStream& ns, uint32_t sub, float neg2ln2_scale2, float xi[12]) {
-    const uint32_t g = sub >> 1;
-    const bool odd = (sub & 1u) != 0;
-    // substep 2g: words 0..5 = block 3g + first half of block 3g+1; substep 2g+1: second half of block 3g+1 + block 3g+2
-    uint32_t a[4], b[4];
-    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3 + 3u * g + 1u, b);
-    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3 + 3u * g + (odd ? 2u : 0u), a);
-    const uint32_t w[6] = {odd ? b[2] : a[0], odd ? b[3] : a[1], odd ? a[0] : a[2], odd ? a[1] : a[3],
-                           odd ? a[2] : b[0], odd ? a[3] : b[1]};
-#pragma unroll
-    for (int k = 0; k < 6; ++k) box_muller16(w[k], neg2ln2_scale2, xi[2 * k], xi[2 * k + 1]);
-}
 // Euler: 3 samples per substep from its own block (full 32-bit uniforms; not a hot path)
 STG_HD void philox_normals3(const NoiseStream& ns, uint32_t sub, float neg2ln2_scale2, float xi[4]) {
     uint32_t o[4];
@@ -517,6 +481,93 @@ template <> struct Pk<F2> {
     static STG_HD F2 bc(float v) { return mk2(v, v); }
 };
 
+// lane access of a pack (compile-time lane index after unrolling)
+template <typename P> struct Ln;
+template <> struct Ln<float> {
+    static constexpr int N = 1;
+    static STG_HD float get(float v, int) { return v; }
+    static STG_HD void set(float& v, int, float x) { v = x; }
+};
+template <> struct Ln<F2> {
+    static constexpr int N = 2;
+    static STG_HD float get(const F2& v, int l) { return l ? v.y : v.x; }
+    static STG_HD void set(F2& v, int l, float x) { if (l) v.y = x; else v.x = x; }
+};
+
+// ---- thermal-field samples over a pack -----------------------------------------------------------------------------------------
+// P = float: one env per thread; F2: two envs per thread with one stream per lane. The integer Philox rounds and the MUFU
+// evaluations run per lane, the FP32 arithmetic of Box-Muller on whole packs (FFMA2 / FMUL2); lane l of xi[k] is sample k of
+// stream l, bit-identical to what the one-env form produces for that stream.
+//
+// Box-Muller pair from ONE 32-bit word per lane: radius uniform U = (hi16 + 1/2) / 65536 in (0, 1), angle = 2 pi lo16 / 65536.
+// Both are formed by dropping the 16 bits into the mantissa of 1.0f (one PRMT / LOP3) and one exact FFMA, no int->float
+// conversion. `nscale` = -2 ln(2) scale^2 folds the field strength into the radius.
+template <typename P>
+STG_HD void box_muller16(const uint32_t* w, P nscale, P& n0, P& n1) {
+    using K = Pk<P>;
+    using L = Ln<P>;
+    P vr, va, lg, r, sn, cs;
+#pragma unroll
+    for (int l = 0; l < L::N; ++l) {
+        L::set(vr, l, bits_as_float(0x3f800000u | (w[l] >> 16)));        // 1 + hi16 2^-23
+        L::set(va, l, bits_as_float(0x3f800000u | (w[l] & 0xffffu)));    // 1 + lo16 2^-23
+    }
+    const P U = K::fma(vr, K::bc(128.0f), K::bc(-127.99999237060546875f));     // 128 vr - (128 - 2^-17) = (hi16 + 1/2) 2^-16, exact
+    const P ang = K::fma(va, K::bc(804.24771931898703f), K::bc(-804.24771931898703f));   // 2 pi 128 (va - 1), one rounding
+#pragma unroll
+    for (int l = 0; l < L::N; ++l) L::set(lg, l, fast_lg2(L::get(U, l)));
+    const P t = K::mul(nscale, lg);
+#pragma unroll
+    for (int l = 0; l < L::N; ++l) {
+        float s_, c_;
+        fast_sincos(L::get(ang, l), s_, c_);
+        L::set(r, l, fast_sqrt(L::get(t, l)));
+        L::set(sn, l, s_);
+        L::set(cs, l, c_);
+    }
+    n0 = K::mul(r, cs);
+    n1 = K::mul(r, sn);
+}
+// one Philox block of every lane's stream: w[j][l] = word j of lane l
+template <int NL>
+STG_HD void philox_block(const NoiseStream* ns, uint32_t idx, uint32_t (*w)[NL]) {
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        uint32_t o[4];
+        ns[l].ph(ns[l].c0, ns[l].c1, ns[l].c2, ns[l].c3 + idx, o);
+        w[0][l] = o[0]; w[1][l] = o[1]; w[2][l] = o[2]; w[3][l] = o[3];
+    }
+}
+// 24 samples N(0, scale^2) per lane: the 4 x 3 stage fields of the RK4 substeps 2g (xi[0..11]) and 2g+1 (xi[12..23])
+template <typename P>
+STG_HD void philox_normals24(const NoiseStream* ns, uint32_t g, P nscale, P* xi) {
+    constexpr int NL = Ln<P>::N;
+    uint32_t w[12][NL];
+    philox_block<NL>(ns, 3u * g, w);
+    philox_block<NL>(ns, 3u * g + 1u, w + 4);
+    philox_block<NL>(ns, 3u * g + 2u, w + 8);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) box_muller16<P>(w[k], nscale, xi[2 * k], xi[2 * k + 1]);
+}
+// the 12 samples of ONE substep (same values as its half of philox_normals24; used around the pulse edge and for odd counts)
+template <typename P>
+STG_HD void philox_normals12(const NoiseStream* ns, uint32_t sub, P nscale, P* xi) {
+    constexpr int NL = Ln<P>::N;
+    const uint32_t g = sub >> 1;
+    const bool odd = (sub & 1u) != 0;
+    // substep 2g: words 0..5 = block 3g + first half of block 3g+1; substep 2g+1: second half of block 3g+1 + block 3g+2
+    uint32_t a[4][NL], b[4][NL], w[6][NL];
+    philox_block<NL>(ns, 3u * g + 1u, b);
+    philox_block<NL>(ns, 3u * g + (odd ? 2u : 0u), a);
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        w[0][l] = odd ? b[2][l] : a[0][l]; w[1][l] = odd ? b[3][l] : a[1][l]; w[2][l] = odd ? a[0][l] : a[2][l];
+        w[3][l] = odd ? a[1][l] : a[3][l]; w[4][l] = odd ? a[2][l] : b[0][l]; w[5][l] = odd ? a[3][l] : b[1][l];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) box_muller16<P>(w[k], nscale, xi[2 * k], xi[2 * k + 1]);
+}
+
 // constants of the fast path in pack form (hi/lo pairs, see StepConsts)
 template <typename P>
 struct PackConsts {
@@ -604,53 +655,78 @@ STG_HD void rk4_fast(const PackConsts<P>& c, P fx, P fy, P fz, P nq, P q, P aH1,
 // COMP: compensated (hi, lo) constants c and a, as the deterministic path carries them - the injected-noise mode, whose parity
 // with the FP64 reference is per trajectory (1e-4). With the in-kernel stream parity is statistical and the constants are plain
 // FP32 (a relative rate error of 3e-8).
+template <typename P>
 struct ThermalConsts {
-    float c_hi, c_lo, al;
+    P c_hi, c_lo, al;
 };
-template <bool COMP>
-STG_HD void stage_th(const ThermalConsts& c, float mx, float my, float mz, float aH, float aL, float bx, float by, float bz,
-                     float& kx, float& ky, float& kz) {
-    using K = Pk<float>;
-    const float Bz = COMP ? K::fma(c.c_hi, mz, K::fma(c.c_lo, mz, bz)) : K::fma(c.c_hi, mz, bz);
-    const float px = K::fma(my, Bz, K::mul(-mz, by));
-    const float py = K::fma(mz, bx, K::mul(-mx, Bz));
-    const float pz = K::fma(mx, by, K::mul(-my, bx));
-    float tx, ty;
+template <typename P, bool COMP>
+STG_HD void stage_th(const ThermalConsts<P>& c, P mx, P my, P mz, P aH, P aL, P bx, P by, P bz, P& kx, P& ky, P& kz) {
+    using K = Pk<P>;
+    const P Bz = COMP ? K::fma(c.c_hi, mz, K::fma(c.c_lo, mz, bz)) : K::fma(c.c_hi, mz, bz);
+    const P px = K::fma(my, Bz, K::mul(K::neg(mz), by));
+    const P py = K::fma(mz, bx, K::mul(K::neg(mx), Bz));
+    const P pz = K::fma(mx, by, K::mul(K::neg(my), bx));
+    P tx, ty;
     if (COMP) {
         tx = K::fma(c.al, px, K::fma(aH, my, K::mul(aL, my)));
-        ty = K::fma(c.al, py, K::fma(-aH, mx, K::mul(-aL, mx)));
+        ty = K::fma(c.al, py, K::fma(K::neg(aH), mx, K::mul(K::neg(aL), mx)));
     } else {
         tx = K::fma(aH, my, K::mul(c.al, px));
-        ty = K::fma(-aH, mx, K::mul(c.al, py));
+        ty = K::fma(K::neg(aH), mx, K::mul(c.al, py));
     }
-    const float tz = K::mul(c.al, pz);
-    kx = K::fma(my, tz, K::fma(-mz, ty, px));
-    ky = K::fma(mz, tx, K::fma(-mx, tz, py));
-    kz = K::fma(mx, ty, K::fma(-my, tx, pz));
+    const P tz = K::mul(c.al, pz);
+    kx = K::fma(my, tz, K::fma(K::neg(mz), ty, px));
+    ky = K::fma(mz, tx, K::fma(K::neg(mx), tz, py));
+    kz = K::fma(mx, ty, K::fma(K::neg(my), tx, pz));
 }
-// RK4 substep of the thermal fast path; same conventions as rk4_fast (constants carry 1/6; outputs increment, correction, d)
-template <bool COMP>
-STG_HD void rk4_thermal(const ThermalConsts& c, float fx, float fy, float fz, float aH1, float aL1, float aH2, float aL2,
-                        float aH4, float aL4, const float* nz, float& ix, float& iy, float& iz, float& cx, float& cy,
-                        float& cz, float& d) {
-    using K = Pk<float>;
-    float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
-    stage_th<COMP>(c, fx, fy, fz, aH1, aL1, nz[0], nz[1], nz[2], k1x, k1y, k1z);
-    stage_th<COMP>(c, K::fma(3.0f, k1x, fx), K::fma(3.0f, k1y, fy), K::fma(3.0f, k1z, fz), aH2, aL2, nz[3], nz[4], nz[5],
-                   k2x, k2y, k2z);
-    stage_th<COMP>(c, K::fma(3.0f, k2x, fx), K::fma(3.0f, k2y, fy), K::fma(3.0f, k2z, fz), aH2, aL2, nz[6], nz[7], nz[8],
-                   k3x, k3y, k3z);
-    stage_th<COMP>(c, K::fma(6.0f, k3x, fx), K::fma(6.0f, k3y, fy), K::fma(6.0f, k3z, fz), aH4, aL4, nz[9], nz[10], nz[11],
-                   k4x, k4y, k4z);
-    ix = K::add(K::fma(2.0f, K::add(k2x, k3x), k1x), k4x);
-    iy = K::add(K::fma(2.0f, K::add(k2y, k3y), k1y), k4y);
-    iz = K::add(K::fma(2.0f, K::add(k2z, k3z), k1z), k4z);
-    const float ux = K::add(fx, ix), uy = K::add(fy, iy), uz = K::add(fz, iz);
+// RK4 substep of the thermal fast path; same conventions as rk4_fast (constants carry 1/6; outputs increment, correction, d).
+// nz: the 12 noise rotation components of the substep (stage, xyz).
+template <typename P, bool COMP>
+STG_HD void rk4_thermal(const ThermalConsts<P>& c, P fx, P fy, P fz, P aH1, P aL1, P aH2, P aL2, P aH4, P aL4, const P* nz,
+                        P& ix, P& iy, P& iz, P& cx, P& cy, P& cz, P& d) {
+    using K = Pk<P>;
+    const P three = K::bc(3.0f), six = K::bc(6.0f), two = K::bc(2.0f);
+    P k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z, k4x, k4y, k4z;
+    stage_th<P, COMP>(c, fx, fy, fz, aH1, aL1, nz[0], nz[1], nz[2], k1x, k1y, k1z);
+    stage_th<P, COMP>(c, K::fma(three, k1x, fx), K::fma(three, k1y, fy), K::fma(three, k1z, fz), aH2, aL2, nz[3], nz[4], nz[5],
+                      k2x, k2y, k2z);
+    stage_th<P, COMP>(c, K::fma(three, k2x, fx), K::fma(three, k2y, fy), K::fma(three, k2z, fz), aH2, aL2, nz[6], nz[7], nz[8],
+                      k3x, k3y, k3z);
+    stage_th<P, COMP>(c, K::fma(six, k3x, fx), K::fma(six, k3y, fy), K::fma(six, k3z, fz), aH4, aL4, nz[9], nz[10], nz[11],
+                      k4x, k4y, k4z);
+    ix = K::add(K::fma(two, K::add(k2x, k3x), k1x), k4x);
+    iy = K::add(K::fma(two, K::add(k2y, k3y), k1y), k4y);
+    iz = K::add(K::fma(two, K::add(k2z, k3z), k1z), k4z);
+    const P ux = K::add(fx, ix), uy = K::add(fy, iy), uz = K::add(fz, iz);
     d = K::fma(iz, K::add(fz, uz), K::fma(ix, K::add(fx, ux), K::mul(iy, K::add(fy, uy))));
-    const float rho = K::mul(d, K::fma(d, K::fma(d, -0.3125f, 0.375f), -0.5f));
+    const P rho = K::mul(d, K::fma(d, K::fma(d, K::bc(-0.3125f), K::bc(0.375f)), K::bc(-0.5f)));
     cx = K::fma(rho, ux, ix);
     cy = K::fma(rho, uy, iy);
     cz = K::fma(rho, uz, iz);
+}
+
+// ---- FP32 master with a running compensation (in-kernel noise stream) -----------------------------------------------------
+// The thermal kicks are ~1e-9 per stage (the reference does not scale h_th with dt), far below one ulp of an O(1) FP32
+// component, so the state between substeps needs more than 24 bits. Instead of an FP64 master (3 F2F + 3 DADD + 3 F2F per
+// substep on the quarter-rate conversion pipe) the working copy f carries a Kahan compensation e with m = f + e to ~2^-48:
+//     y = corr + e;  t = f + y;  e = y - (t - f);  f = t          (4 FADD per component, packable)
+// The captured error is exact whenever |f| >= |y|; where the increment exceeds the component the loss is < 2^-24 |increment|,
+// i.e. the rounding the FP32 stages put into the increment anyway. Every STG_RESYNC_MASK+1 substeps f + e is renormalised
+// exactly in FP64 and split again.
+template <typename P>
+STG_HD void kahan_add(P& f, P& e, P corr) {
+    using K = Pk<P>;
+    const P y = K::add(corr, e);
+    const P t = K::add(f, y);
+    e = K::add(y, K::neg(K::add(t, K::neg(f))));
+    f = t;
+}
+// exact renormalisation of one env's (f + e) in FP64; guard as in guard_normalise (non-finite / zero norm -> (0,0,1) + flag)
+STG_HD void kahan_renorm(float& fx, float& fy, float& fz, float& ex, float& ey, float& ez, int& guard) {
+    ScaledState st{(double)fx + (double)ex, (double)fy + (double)ey, (double)fz + (double)ez, 1.0, 1.0, 1.0f};
+    guard_normalise<float>(st, guard);
+    fx = (float)st.sx; fy = (float)st.sy; fz = (float)st.z;
+    ex = (float)(st.sx - (double)fx); ey = (float)(st.sy - (double)fy); ez = (float)(st.z - (double)fz);
 }
 
 struct FastState {

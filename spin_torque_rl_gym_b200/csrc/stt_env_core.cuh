@@ -41,6 +41,134 @@ STG_HD void parse_action(float a0, float a1, double max_current, double max_dura
     T = fmin(fmax((double)a1, 1e-12), max_duration);
 }
 
+// One env of the thermal fast path (FP32 stages, e = z^, RK4, in-kernel noise stream)
+struct ThermalEnv {
+    const double* f;      // folded parameter set
+    double J, dt, t_pulse, t_end;
+    int n;
+    NoiseStream ns;
+};
+// The envs of one thread through the thermal fast path: P = float (one env) or F2 (two envs in the halves of 64-bit register
+// pairs on packed FFMA2 / FMUL2 / FADD2). Every operation is an explicit IEEE op per lane and every lane draws from its own
+// stream, so an env gets the same bits whatever it is paired with: lanes may have different substep counts - a finished lane is
+// frozen (its state is restored after every further substep of its partner). m: [lanes][3] in / out; traj: P = float only.
+template <typename P>
+STG_HD void integrate_thermal(const ThermalEnv* E, double (*m)[3], int* guard, double* traj = nullptr,
+                              int64_t traj_rows = 0x7fffffff) {
+    using K = Pk<P>;
+    using L = Ln<P>;
+    constexpr int NL = L::N;
+    ThermalConsts<P> tc;
+    P aH, aL, nscale, fx, fy, fz, ex, ey, ez;
+    NoiseStream ns[NL];
+    int n_max = 0, fast_to = 0x7fffffff, i_safe[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        StepConsts<float> c;
+        make_consts<float>(E[l].f, E[l].dt, E[l].J, 1.0 / 6.0, c);
+        L::set(tc.c_hi, l, c.c_hi); L::set(tc.c_lo, l, c.c_lo); L::set(tc.al, l, c.al_hi);
+        L::set(aH, l, c.a_hi); L::set(aL, l, c.a_lo);
+        L::set(nscale, l, -1.3862943611198906f * c.cth * c.cth);      // -2 ln2 * (G h_th / 6)^2
+        const float x = (float)m[l][0], y = (float)m[l][1], z = (float)m[l][2];
+        L::set(fx, l, x); L::set(fy, l, y); L::set(fz, l, z);
+        L::set(ex, l, (float)(m[l][0] - (double)x)); L::set(ey, l, (float)(m[l][1] - (double)y));
+        L::set(ez, l, (float)(m[l][2] - (double)z));
+        ns[l] = E[l].ns;
+        // substeps below i_safe are certainly inside the pulse (see integrate)
+        if (E[l].t_pulse >= E[l].t_end) {
+            i_safe[l] = E[l].n - 1;
+        } else {
+            const double qd = E[l].t_pulse / E[l].dt - 2.0;
+            i_safe[l] = qd < 0.0 ? 0 : (qd > (double)E[l].n ? E[l].n : (int)qd);
+        }
+        n_max = E[l].n > n_max ? E[l].n : n_max;
+        fast_to = i_safe[l] < fast_to ? i_safe[l] : fast_to;
+    }
+    if (traj) { traj[0] = m[0][0]; traj[1] = m[0][1]; traj[2] = m[0][2]; }
+    // exact FP64 renormalisation of lane l's f + e
+    auto renorm = [&](int l) {
+        float x = L::get(fx, l), y = L::get(fy, l), z = L::get(fz, l), a = L::get(ex, l), b = L::get(ey, l), c = L::get(ez, l);
+        kahan_renorm(x, y, z, a, b, c, guard[l]);
+        L::set(fx, l, x); L::set(fy, l, y); L::set(fz, l, z); L::set(ex, l, a); L::set(ey, l, b); L::set(ez, l, c);
+    };
+    // one substep of every lane; a1/a2/a4: aJ dt seen by stage 1, stages 2 + 3, stage 4 (pulse gate)
+    auto substep = [&](int i, const P* nz, P aH1, P aL1, P aH2, P aL2, P aH4, P aL4) {
+        P ix, iy, iz, cx, cy, cz, d;
+        rk4_thermal<P, false>(tc, fx, fy, fz, aH1, aL1, aH2, aL2, aH4, aL4, nz, ix, iy, iz, cx, cy, cz, d);
+        bool small = true;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) small = small && (fabsf(L::get(d, l)) < 0.015625f);
+        if (small) {
+            kahan_add<P>(fx, ex, cx);
+            kahan_add<P>(fy, ey, cy);
+            kahan_add<P>(fz, ez, cz);
+        } else {
+            // large or non-finite norm change in some lane (diverging parameters): that lane takes the plain increment and the
+            // exact FP64 renormalisation with the reference's guard
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                const bool ok = fabsf(L::get(d, l)) < 0.015625f;
+                float x = L::get(fx, l), y = L::get(fy, l), z = L::get(fz, l), a = L::get(ex, l), b = L::get(ey, l), c = L::get(ez, l);
+                kahan_add<float>(x, a, ok ? L::get(cx, l) : L::get(ix, l));
+                kahan_add<float>(y, b, ok ? L::get(cy, l) : L::get(iy, l));
+                kahan_add<float>(z, c, ok ? L::get(cz, l) : L::get(iz, l));
+                if (!ok) kahan_renorm(x, y, z, a, b, c, guard[l]);
+                L::set(fx, l, x); L::set(fy, l, y); L::set(fz, l, z); L::set(ex, l, a); L::set(ey, l, b); L::set(ez, l, c);
+            }
+        }
+        if ((i & STG_RESYNC_MASK) == STG_RESYNC_MASK || traj) {
+#pragma unroll
+            for (int l = 0; l < NL; ++l) renorm(l);
+        }
+        if (traj && i + 1 < traj_rows) {
+            traj[3 * (i + 1) + 0] = (double)L::get(fx, 0) + (double)L::get(ex, 0);
+            traj[3 * (i + 1) + 1] = (double)L::get(fy, 0) + (double)L::get(ey, 0);
+            traj[3 * (i + 1) + 2] = (double)L::get(fz, 0) + (double)L::get(ez, 0);
+        }
+    };
+    int i = 0;
+    // every lane running and inside its pulse: one draw of three Philox blocks per lane serves two substeps
+#pragma unroll kSubstepPairUnroll
+    for (; i + 1 < fast_to; i += 2) {
+        P nz[24];
+        philox_normals24<P>(ns, (uint32_t)i >> 1, nscale, nz);
+        substep(i, nz, aH, aL, aH, aL, aH, aL);
+        substep(i + 1, nz + 12, aH, aL, aH, aL, aH, aL);
+    }
+    // around the pulse edge / past the end of the shorter lane: per-lane gates, finished lanes frozen
+    for (; i < n_max; ++i) {
+        P nz[12];
+        philox_normals12<P>(ns, (uint32_t)i, nscale, nz);
+        P aH1 = aH, aL1 = aL, aH2 = aH, aL2 = aL, aH4 = aH, aL4 = aL;
+        const P sfx = fx, sfy = fy, sfz = fz, sex = ex, sey = ey, sez = ez;
+        const int g0 = guard[0], g1 = guard[NL - 1];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            if (i >= i_safe[l]) {
+                if (!pulse_on(i, 0, E[l].dt, E[l].t_pulse)) { L::set(aH1, l, 0.0f); L::set(aL1, l, 0.0f); }
+                if (!pulse_on(i, 1, E[l].dt, E[l].t_pulse)) { L::set(aH2, l, 0.0f); L::set(aL2, l, 0.0f); }
+                if (!pulse_on(i, 2, E[l].dt, E[l].t_pulse)) { L::set(aH4, l, 0.0f); L::set(aL4, l, 0.0f); }
+            }
+        }
+        substep(i, nz, aH1, aL1, aH2, aL2, aH4, aL4);
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            if (i >= E[l].n) {      // this lane had finished: undo
+                L::set(fx, l, L::get(sfx, l)); L::set(fy, l, L::get(sfy, l)); L::set(fz, l, L::get(sfz, l));
+                L::set(ex, l, L::get(sex, l)); L::set(ey, l, L::get(sey, l)); L::set(ez, l, L::get(sez, l));
+                guard[l] = l ? g1 : g0;
+            }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        renorm(l);
+        m[l][0] = (double)L::get(fx, l) + (double)L::get(ex, l);
+        m[l][1] = (double)L::get(fy, l) + (double)L::get(ey, l);
+        m[l][2] = (double)L::get(fz, l) + (double)L::get(ez, l);
+    }
+}
+
 // Integrate n substeps of size dt from (mx,my,mz); pulse of density J on while t <= t_pulse (envs/spin_torque_env.py:442-443).
 // NOISE: 0 none, 1 Philox stream `ns`, 2 injected tensor [n][S][3]. traj: optional [n+1][3] FP64 rows.
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>
@@ -67,12 +195,17 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
     }
     if (traj) { traj[0] = mx; traj[1] = my; traj[2] = mz; }
 
-    if constexpr (FAST) {
+    if constexpr (FAST && NOISE == 1) {
+        ThermalEnv E{f, J, dt, t_pulse, t_end, n, ns};
+        double w[1][3] = {{mx, my, mz}};
+        integrate_thermal<float>(&E, w, &guard, traj, traj_rows);
+        mx = w[0][0]; my = w[0][1]; mz = w[0][2];
+    } else if constexpr (FAST) {
         StepConsts<float> c;
         make_consts<float>(f, dt, J, 1.0 / 6.0, c);
         PackConsts<float> pc;
         pack_consts<float>(c, c, pc);
-        const ThermalConsts tc{c.c_hi, c.c_lo, c.al_hi};
+        const ThermalConsts<float> tc{c.c_hi, c.c_lo, c.al_hi};
         const float nscale = -1.3862943611198906f * c.cth * c.cth;      // -2 ln2 * (G h_th / 6)^2
         FastState s;
         s.st = ScaledState{mx, my, mz, 1.0, 1.0, 1.0f};
@@ -89,7 +222,7 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
             }
             float ix, iy, iz, cx, cy, cz, d;
             if constexpr (TH)
-                rk4_thermal<NOISE == 2>(tc, s.fx, s.fy, s.fz, aH1, aL1, aH2, aL2, aH4, aL4, nz, ix, iy, iz, cx, cy, cz, d);
+                rk4_thermal<float, true>(tc, s.fx, s.fy, s.fz, aH1, aL1, aH2, aL2, aH4, aL4, nz, ix, iy, iz, cx, cy, cz, d);
             else
                 rk4_fast<float, false, SCALED>(pc, s.fx, s.fy, s.fz, -s.q, s.q, aH1, aL1, aH2, aL2, aH4, aL4, nullptr,
                                                ix, iy, iz, cx, cy, cz, d);
@@ -109,19 +242,7 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
         };
         int i = 0;
         if constexpr (NOISE == 1) {
-            // the stream serves two substeps per draw (three Philox blocks -> 24 normals)
-#pragma unroll kSubstepPairUnroll
-            for (; i + 1 < i_safe; i += 2) {
-                float nz[24];
-                philox_normals24(ns, (uint32_t)i >> 1, nscale, nz);
-                one(i, nz, false);
-                one(i + 1, nz + 12, false);
-            }
-            for (; i < n; ++i) {
-                float nz[12];
-                philox_normals12(ns, (uint32_t)i, nscale, nz);
-                one(i, nz, i >= i_safe);
-            }
+            // handled by integrate_thermal above
         } else if constexpr (NOISE == 2) {
             for (; i < n; ++i) {
                 float nz[12];
@@ -168,7 +289,7 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
 #pragma unroll 1
             for (; i + 1 < n; i += 2) {
                 float z[24];
-                philox_normals24(ns, (uint32_t)i >> 1, nscale, z);
+                philox_normals24<float>(&ns, (uint32_t)i >> 1, nscale, z);
                 R nz[24];
 #pragma unroll
                 for (int q = 0; q < 24; ++q) nz[q] = (R)z[q];
@@ -177,7 +298,7 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
             }
             for (; i < n; ++i) {
                 float z[12];
-                philox_normals12(ns, (uint32_t)i, nscale, z);
+                philox_normals12<float>(&ns, (uint32_t)i, nscale, z);
                 R nz[12];
 #pragma unroll
                 for (int q = 0; q < 12; ++q) nz[q] = (R)z[q];
@@ -491,19 +612,35 @@ STG_HD bool env_step_body(const StgSttStepArgs& a, int64_t e, EnvStepResult& r, 
     return true;
 }
 
-// Two envs (eA, eB) through the packed FP32x2 integrator (R = float, e = z^, RK4, no thermal field). Returns a mask of the envs
-// that were NOT stepped because their FP32 trajectory is ill-conditioned (bit 0: eA, bit 1: eB; see env_step_body).
+// Two envs (eA, eB) through the packed FP32x2 integrators (R = float, e = z^, RK4; NOISE 0: integrate_pair, 1: integrate_thermal
+// with the in-kernel stream). Returns a mask of the envs that were NOT stepped because their FP32 trajectory is ill-conditioned
+// (bit 0: eA, bit 1: eB; see env_step_body; never set with the noise stream, where parity is statistical).
+template <int NOISE>
 STG_HD int env_step_pair_body(const StgSttStepArgs& a, int64_t eA, int64_t eB, EnvStepResult& rA, EnvStepResult& rB) {
     EnvStepCtx ca, cb;
     env_step_prologue<float, true>(a, eA, ca);
     env_step_prologue<float, true>(a, eB, cb);
-    if (ca.valid && cb.valid) {
-        PairEnv A{ca.f, ca.J, ca.plan.dt, ca.T, ca.plan.n};
-        PairEnv B{cb.f, cb.J, cb.plan.dt, cb.T, cb.plan.n};
-        integrate_pair(A, B, ca.w, cb.w, ca.guard, cb.guard, ca.illcond, cb.illcond);
+    const bool noise_ok = NOISE == 0 || (ca.f[FI_HTH] > 0.0 && cb.f[FI_HTH] > 0.0);
+    if (ca.valid && cb.valid && noise_ok) {
+        if constexpr (NOISE == 0) {
+            PairEnv A{ca.f, ca.J, ca.plan.dt, ca.T, ca.plan.n};
+            PairEnv B{cb.f, cb.J, cb.plan.dt, cb.T, cb.plan.n};
+            integrate_pair(A, B, ca.w, cb.w, ca.guard, cb.guard, ca.illcond, cb.illcond);
+        } else {
+            const ThermalEnv E[2] = {
+                {ca.f, ca.J, ca.plan.dt, ca.T, ca.T, ca.plan.n,
+                 make_stream(a.seed, a.env_offset + (uint64_t)eA, (uint32_t)a.state.episode[eA], (uint32_t)ca.step)},
+                {cb.f, cb.J, cb.plan.dt, cb.T, cb.T, cb.plan.n,
+                 make_stream(a.seed, a.env_offset + (uint64_t)eB, (uint32_t)a.state.episode[eB], (uint32_t)cb.step)}};
+            double w[2][3] = {{ca.w[0], ca.w[1], ca.w[2]}, {cb.w[0], cb.w[1], cb.w[2]}};
+            int g[2] = {ca.guard, cb.guard};
+            integrate_thermal<F2>(E, w, g);
+            ca.w[0] = w[0][0]; ca.w[1] = w[0][1]; ca.w[2] = w[0][2]; ca.guard = g[0];
+            cb.w[0] = w[1][0]; cb.w[1] = w[1][1]; cb.w[2] = w[1][2]; cb.guard = g[1];
+        }
     } else {
-        if (ca.valid) env_step_integrate<float, true, 0, false>(a, eA, ca);
-        if (cb.valid) env_step_integrate<float, true, 0, false>(a, eB, cb);
+        if (ca.valid) env_step_integrate<float, true, NOISE, false>(a, eA, ca);
+        if (cb.valid) env_step_integrate<float, true, NOISE, false>(a, eB, cb);
     }
     if (!ca.illcond) env_step_epilogue(a, eA, ca, rA);
     if (!cb.illcond) env_step_epilogue(a, eB, cb, rB);
@@ -611,7 +748,7 @@ STG_HD void integrate_grid(const double* f, double J, double& mx, double& my, do
         if (NOISE == 1) {
             float z[12];
             if (EULER) philox_normals3(ns, (uint32_t)i, nscale, z);
-            else philox_normals12(ns, (uint32_t)i, nscale, z);
+            else philox_normals12<float>(&ns, (uint32_t)i, nscale, z);
 #pragma unroll
             for (int q = 0; q < NS; ++q) nz[q] = (double)z[q];
         } else if (NOISE == 2) {

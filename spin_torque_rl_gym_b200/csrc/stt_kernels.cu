@@ -130,7 +130,7 @@ stt_env_step_kernel(const __grid_constant__ StepArgs a) {
 }
 
 // ---- two envs per thread: packed FP32x2 (FFMA2) variant of the fast path ------------------------------------------------
-// R = float, e = z^, RK4, no thermal field. Thread t of a CTA owns the adjacent slots 2t, 2t+1, so the FP64
+// R = float, e = z^, RK4, NOISE in {0 (none), 1 (in-kernel stream)}. Thread t of a CTA owns the adjacent slots 2t, 2t+1, so the FP64
 // state planes are read as 16-byte pairs and one CTA covers 2*kBlock observation rows.
 __device__ __forceinline__ void accumulate_stats(double* v, const EnvStepResult& r) {
     const bool ended = r.terminated || r.truncated;
@@ -147,7 +147,11 @@ __device__ __forceinline__ void accumulate_stats(double* v, const EnvStepResult&
 #ifndef STG_PAIR_MINBLOCKS
 #define STG_PAIR_MINBLOCKS 8
 #endif
-__global__ void __launch_bounds__(kBlock, STG_PAIR_MINBLOCKS) stt_env_step_pair_kernel(const __grid_constant__ StepArgs a) {
+#ifndef STG_PAIR_MINBLOCKS_TH
+#define STG_PAIR_MINBLOCKS_TH 8
+#endif
+template <int NOISE>
+__global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : STG_PAIR_MINBLOCKS_TH) stt_env_step_pair_kernel(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) float s_obs[2 * kBlock * kObs];
     __shared__ uint8_t s_skip[2 * kBlock];
     const int64_t base = (int64_t)blockIdx.x * (2 * kBlock);
@@ -161,8 +165,8 @@ __global__ void __launch_bounds__(kBlock, STG_PAIR_MINBLOCKS) stt_env_step_pair_
     EnvStepResult rA, rB;
     rA.did_reset = rB.did_reset = false;
     int redo = 0;
-    if (actB) redo = env_step_pair_body(a, eA, eB, rA, rB);
-    else if (actA) redo = env_step_body<float, true, 0, false>(a, eA, rA) ? 0 : 1;
+    if (actB) redo = env_step_pair_body<NOISE>(a, eA, eB, rA, rB);
+    else if (actA) redo = env_step_body<float, true, NOISE, false>(a, eA, rA) ? 0 : 1;
     if (redo & 1) redo_push(a, eA);
     if (redo & 2) redo_push(a, eB);
     const bool doneA = actA && !(redo & 1), doneB = actB && !(redo & 2);
@@ -352,7 +356,7 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
             // Measured (profiles/README.md): +12 % without thermal noise. With the Philox stream the packed variant needs
             // 201 registers and loses (the integer Philox rounds do not pack), so it is not dispatched there.
             const unsigned grid = (unsigned)((a.n_envs + 2 * kBlock - 1) / (2 * kBlock));
-            stt_env_step_pair_kernel<<<grid, kBlock, 0, s>>>(a);
+            stt_env_step_pair_kernel<0><<<grid, kBlock, 0, s>>>(a);
             err = cudaGetLastError();
         } else {
             err = noise == 0 ? launch_step2<float, true, 0>(a, s) : launch_step2<float, true, 2>(a, s);
@@ -361,6 +365,12 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
         return noise == 0 ? launch_redo<0>(a, s) : launch_redo<2>(a, s);
     }
     if (axis_z) {
+        if (sizeof(R) == 4 && noise == 1 && !(a.flags & STG_F_NO_PAIR)) {
+            // two envs per thread on packed FP32x2 arithmetic, one noise stream per lane (bit-identical to one env per thread)
+            const unsigned grid = (unsigned)((a.n_envs + 2 * kBlock - 1) / (2 * kBlock));
+            stt_env_step_pair_kernel<1><<<grid, kBlock, 0, s>>>(a);
+            return cudaGetLastError();
+        }
         if (noise == 0) return launch_step2<R, true, 0>(a, s);
         if (noise == 1) return launch_step2<R, true, 1>(a, s);
         return launch_step2<R, true, 2>(a, s);

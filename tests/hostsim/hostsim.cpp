@@ -57,16 +57,16 @@ struct FtzScope {
     ~FtzScope() { _mm_setcsr(old); }
 };
 
-// the two-envs-per-thread body with the host emulation of the FP32x2 pack (no thermal field, as the device dispatches it)
+// the two-envs-per-thread body with the host emulation of the FP32x2 pack
+template <int NOISE>
 static void step_pairs(const StgSttStepArgs& a) {
-    constexpr int NOISE = 0;
     for (int64_t s = 0; s < a.n_envs; s += 2) {
         const int64_t eA = (a.flags & STG_F_SORTED) ? a.d_perm[s] : s;
         EnvStepResult rA, rB;
         int redo = 0;
         if (s + 1 < a.n_envs) {
             const int64_t eB = (a.flags & STG_F_SORTED) ? a.d_perm[s + 1] : s + 1;
-            redo = env_step_pair_body(a, eA, eB, rA, rB);
+            redo = env_step_pair_body<NOISE>(a, eA, eB, rA, rB);
             if (redo & 2) redo_f64<true, NOISE>(a, eB); else store_rows(a, eB, rB);
         } else {
             redo = env_step_body<float, true, NOISE, false>(a, eA, rA) ? 0 : 1;
@@ -78,9 +78,8 @@ static void step_pairs(const StgSttStepArgs& a) {
 extern "C" int hostsim_stt_step(const StgSttStepArgs* a, int f64) {
     if (a->flags & STG_F_EULER) f64 = 1;      // as launch_step<> dispatches: Euler always runs FP64 stages
     FtzScope ftz(!f64);
-    if (!f64 && (a->flags & STG_F_AXIS_Z) &&
-        !(a->flags & (STG_F_THERMAL_INJECT | STG_F_THERMAL_PHILOX | STG_F_EULER | STG_F_NO_PAIR))) {
-        step_pairs(*a);      // the device dispatches the packed variant for the no-noise case
+    if (!f64 && (a->flags & STG_F_AXIS_Z) && !(a->flags & (STG_F_THERMAL_INJECT | STG_F_EULER | STG_F_NO_PAIR))) {
+        if (a->flags & STG_F_THERMAL_PHILOX) step_pairs<1>(*a); else step_pairs<0>(*a);      // as launch_step<> dispatches
         return 0;
     }
     const bool z = (a->flags & STG_F_AXIS_Z) != 0;
@@ -141,12 +140,14 @@ extern "C" void hostsim_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c
 }
 extern "C" void hostsim_normals12(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t step, uint32_t sub, float* out) {
     const float unit = -1.3862943611198906f;
-    philox_normals12(make_stream(seed, gid, episode, step), sub, unit, out);
+    const NoiseStream ns = make_stream(seed, gid, episode, step);
+    philox_normals12<float>(&ns, sub, unit, out);
 }
 // the 24 samples of the substep pair (2g, 2g+1): must equal the two single-substep draws
 extern "C" void hostsim_normals24(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t step, uint32_t g, float* out) {
     const float unit = -1.3862943611198906f;
-    philox_normals24(make_stream(seed, gid, episode, step), g, unit, out);
+    const NoiseStream ns = make_stream(seed, gid, episode, step);
+    philox_normals24<float>(&ns, g, unit, out);
 }
 
 extern "C" int hostsim_llgs_rk45(const StgRk45Args* a) {

@@ -232,13 +232,14 @@ def test_fp32_second_pass_equals_fp64_mode(pair, cuda_device):
         # host-output env (unsorted launch): same bits as the sorted device-output env, redone rows included
         assert torch.equal(oh, o32.cpu()) and torch.equal(teh, te32.cpu()) and torch.equal(ih["final_observation"], i32["final_observation"].cpu())
         assert torch.equal(ih["status"], i32["status"])
-        # envs whose flags differ between the modes sit within tol of the success threshold; align them for the next step
+        # envs whose flags differ between the modes sit within tol of the success threshold
         mism = te32 != te64
         align = (e64.magnetization * torch.as_tensor(tgt, device=cuda_device)).sum(1)
         assert bool(((align[mism] - 0.9).abs() < 1e-4).all())
-        if bool(mism.any()):
-            e32.load_state_dict(e64.state_dict())
-            eh.load_state_dict(e64.state_dict())
+        # every step is compared from identical start states (the statistics buffers are left alone)
+        for e in (e32, eh):
+            for name in ("_m", "_target", "_total_energy", "_last_action", "_step_count", "_episode"):
+                getattr(e, name).copy_(getattr(e64, name))
     assert 0 < seen < 0.05 * n * len(acts)
     st32, st64 = e32.episode_stats(), e64.episode_stats()
     assert st32["steps"] == st64["steps"] == n * len(acts) and st32["substeps"] == st64["substeps"]

@@ -235,7 +235,7 @@ def test_philox_normals_moments():
             assert np.array_equal(np.array(buf[:]), np.array(buf24[12 * half:12 * half + 12]))
 
 
-@pytest.mark.parametrize("thermal", [False])
+@pytest.mark.parametrize("thermal", [False, True])
 def test_pair_path_is_bit_identical_to_scalar_path(thermal):
     """Two envs per thread (FP32x2 pack) vs one env per thread: same IEEE operations per component, so bit-identical results,
     for ragged substep counts (partners finish at different substeps), odd batch sizes and a permuted launch."""
