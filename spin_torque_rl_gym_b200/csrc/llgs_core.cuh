@@ -481,6 +481,45 @@ template <> struct Pk<F2> {
     static STG_HD F2 bc(float v) { return mk2(v, v); }
 };
 
+// K independent F2 packs per thread (2K envs): every pack operation becomes K independent packed instructions, which gives the
+// in-order issue of one warp K dependent chains to interleave (the stage chain of one pack is ~5 cycles per instruction deep).
+template <int K>
+struct FN {
+    F2 p[K];
+};
+template <int K> struct Pk<FN<K>> {
+    typedef FN<K> T;
+    static STG_HD T fma(const T& a, const T& b, const T& c) {
+        T r;
+#pragma unroll
+        for (int i = 0; i < K; ++i) r.p[i] = Pk<F2>::fma(a.p[i], b.p[i], c.p[i]);
+        return r;
+    }
+    static STG_HD T mul(const T& a, const T& b) {
+        T r;
+#pragma unroll
+        for (int i = 0; i < K; ++i) r.p[i] = Pk<F2>::mul(a.p[i], b.p[i]);
+        return r;
+    }
+    static STG_HD T add(const T& a, const T& b) {
+        T r;
+#pragma unroll
+        for (int i = 0; i < K; ++i) r.p[i] = Pk<F2>::add(a.p[i], b.p[i]);
+        return r;
+    }
+    static STG_HD T neg(const T& a) {
+        T r;
+#pragma unroll
+        for (int i = 0; i < K; ++i) r.p[i] = Pk<F2>::neg(a.p[i]);
+        return r;
+    }
+    static STG_HD T bc(float v) {
+        T r;
+#pragma unroll
+        for (int i = 0; i < K; ++i) r.p[i] = mk2(v, v);
+        return r;
+    }
+};
 // lane access of a pack (compile-time lane index after unrolling)
 template <typename P> struct Ln;
 template <> struct Ln<float> {
@@ -492,6 +531,11 @@ template <> struct Ln<F2> {
     static constexpr int N = 2;
     static STG_HD float get(const F2& v, int l) { return l ? v.y : v.x; }
     static STG_HD void set(F2& v, int l, float x) { if (l) v.y = x; else v.x = x; }
+};
+template <int K> struct Ln<FN<K>> {
+    static constexpr int N = 2 * K;
+    static STG_HD float get(const FN<K>& v, int l) { return Ln<F2>::get(v.p[l >> 1], l & 1); }
+    static STG_HD void set(FN<K>& v, int l, float x) { Ln<F2>::set(v.p[l >> 1], l & 1, x); }
 };
 
 // ---- thermal-field samples over a pack -----------------------------------------------------------------------------------------

@@ -12,7 +12,8 @@ namespace stg {
 #endif
 constexpr int kSubstepUnroll = STG_SUBSTEP_UNROLL;
 #ifndef STG_SUBSTEP_PAIR_UNROLL
-#define STG_SUBSTEP_PAIR_UNROLL 2     // thermal fast path: substep pairs per loop iteration (one Philox draw serves two substeps)
+#define STG_SUBSTEP_PAIR_UNROLL 1     // thermal fast path: substep pairs per loop iteration (one Philox draw serves two substeps);
+                                      // 2 measured 2 % slower (10.67 vs 10.45 ms per 1M-env step, two envs per thread)
 #endif
 constexpr int kSubstepPairUnroll = STG_SUBSTEP_PAIR_UNROLL;
 #ifndef STG_REF_SUBSTEP_UNROLL
@@ -48,19 +49,60 @@ struct ThermalEnv {
     int n;
     NoiseStream ns;
 };
+STG_HD float thermal_nscale(const double* f, double dt) {      // -2 ln2 * (G h_th / 6)^2: field strength folded into Box-Muller
+    const float cth = (float)(-f[FI_GEFF] * dt * (1.0 / 6.0) * f[FI_HTH]);
+    return -1.3862943611198906f * cth * cth;
+}
+// substeps below this index are certainly inside the pulse; the few around the pulse edge evaluate current_func(t) exactly in
+// FP64 (the k4 stage of the LAST substep sees t_i + dt > T for ~16 % of float32 durations)
+STG_HD int pulse_safe_substeps(int n, double dt, double t_pulse, double t_end) {
+    if (t_pulse >= t_end) return n - 1;
+    const double qd = t_pulse / dt - 2.0;
+    return qd < 0.0 ? 0 : (qd > (double)n ? n : (int)qd);
+}
+// Noise source of integrate_thermal: the in-kernel stream, one per lane. first(g, nz) / second(g, nz): the 12 samples per lane
+// (already scaled) of substep 2g / 2g+1, always called in that order. One draw of three Philox blocks serves the pair: blocks
+// 3g and 3g+1 are evaluated for the first substep (6 of their 8 words), the two remaining words are carried to the second, which
+// adds block 3g+2 - so only 12 samples per lane are live at a time. (stt_kernels.cu has a second source: samples produced by
+// other warps of the CTA and handed over through shared memory.)
+template <typename P>
+struct PhiloxSource {
+    NoiseStream ns[Ln<P>::N];
+    P nscale;
+    uint32_t carry[2][Ln<P>::N];
+    STG_HD void first(uint32_t g, P* nz) {
+        constexpr int NL = Ln<P>::N;
+        uint32_t w[8][NL];
+        philox_block<NL>(ns, 3u * g, w);
+        philox_block<NL>(ns, 3u * g + 1u, w + 4);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) box_muller16<P>(w[k], nscale, nz[2 * k], nz[2 * k + 1]);
+#pragma unroll
+        for (int l = 0; l < NL; ++l) { carry[0][l] = w[6][l]; carry[1][l] = w[7][l]; }
+    }
+    STG_HD void second(uint32_t g, P* nz) {
+        constexpr int NL = Ln<P>::N;
+        uint32_t w[4][NL];
+        philox_block<NL>(ns, 3u * g + 2u, w);
+        box_muller16<P>(carry[0], nscale, nz[0], nz[1]);
+        box_muller16<P>(carry[1], nscale, nz[2], nz[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) box_muller16<P>(w[k], nscale, nz[4 + 2 * k], nz[5 + 2 * k]);
+    }
+};
 // The envs of one thread through the thermal fast path: P = float (one env) or F2 (two envs in the halves of 64-bit register
 // pairs on packed FFMA2 / FMUL2 / FADD2). Every operation is an explicit IEEE op per lane and every lane draws from its own
 // stream, so an env gets the same bits whatever it is paired with: lanes may have different substep counts - a finished lane is
 // frozen (its state is restored after every further substep of its partner). m: [lanes][3] in / out; traj: P = float only.
-template <typename P>
-STG_HD void integrate_thermal(const ThermalEnv* E, double (*m)[3], int* guard, double* traj = nullptr,
-                              int64_t traj_rows = 0x7fffffff) {
-    using K = Pk<P>;
+// fast_to / n_run: optional overrides shared by a group of threads that must run the same number of substep pairs (the
+// warp-specialised kernel): substep pairs below fast_to take the plain path in every thread, and the loop runs to n_run.
+template <typename P, typename SRC>
+STG_HD void integrate_thermal(const ThermalEnv* E, SRC& src, double (*m)[3], int* guard, double* traj = nullptr,
+                              int64_t traj_rows = 0x7fffffff, int fast_to_all = -1, int n_run = -1) {
     using L = Ln<P>;
     constexpr int NL = L::N;
     ThermalConsts<P> tc;
-    P aH, aL, nscale, fx, fy, fz, ex, ey, ez;
-    NoiseStream ns[NL];
+    P aH, aL, fx, fy, fz, ex, ey, ez;
     int n_max = 0, fast_to = 0x7fffffff, i_safe[NL];
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
@@ -68,22 +110,16 @@ STG_HD void integrate_thermal(const ThermalEnv* E, double (*m)[3], int* guard, d
         make_consts<float>(E[l].f, E[l].dt, E[l].J, 1.0 / 6.0, c);
         L::set(tc.c_hi, l, c.c_hi); L::set(tc.c_lo, l, c.c_lo); L::set(tc.al, l, c.al_hi);
         L::set(aH, l, c.a_hi); L::set(aL, l, c.a_lo);
-        L::set(nscale, l, -1.3862943611198906f * c.cth * c.cth);      // -2 ln2 * (G h_th / 6)^2
         const float x = (float)m[l][0], y = (float)m[l][1], z = (float)m[l][2];
         L::set(fx, l, x); L::set(fy, l, y); L::set(fz, l, z);
         L::set(ex, l, (float)(m[l][0] - (double)x)); L::set(ey, l, (float)(m[l][1] - (double)y));
         L::set(ez, l, (float)(m[l][2] - (double)z));
-        ns[l] = E[l].ns;
-        // substeps below i_safe are certainly inside the pulse (see integrate)
-        if (E[l].t_pulse >= E[l].t_end) {
-            i_safe[l] = E[l].n - 1;
-        } else {
-            const double qd = E[l].t_pulse / E[l].dt - 2.0;
-            i_safe[l] = qd < 0.0 ? 0 : (qd > (double)E[l].n ? E[l].n : (int)qd);
-        }
+        i_safe[l] = pulse_safe_substeps(E[l].n, E[l].dt, E[l].t_pulse, E[l].t_end);
         n_max = E[l].n > n_max ? E[l].n : n_max;
         fast_to = i_safe[l] < fast_to ? i_safe[l] : fast_to;
     }
+    if (fast_to_all >= 0) fast_to = fast_to_all;
+    if (n_run >= 0) n_max = n_run;
     if (traj) { traj[0] = m[0][0]; traj[1] = m[0][1]; traj[2] = m[0][2]; }
     // exact FP64 renormalisation of lane l's f + e
     auto renorm = [&](int l) {
@@ -126,25 +162,16 @@ STG_HD void integrate_thermal(const ThermalEnv* E, double (*m)[3], int* guard, d
             traj[3 * (i + 1) + 2] = (double)L::get(fz, 0) + (double)L::get(ez, 0);
         }
     };
-    int i = 0;
-    // every lane running and inside its pulse: one draw of three Philox blocks per lane serves two substeps
-#pragma unroll kSubstepPairUnroll
-    for (; i + 1 < fast_to; i += 2) {
-        P nz[24];
-        philox_normals24<P>(ns, (uint32_t)i >> 1, nscale, nz);
-        substep(i, nz, aH, aL, aH, aL, aH, aL);
-        substep(i + 1, nz + 12, aH, aL, aH, aL, aH, aL);
-    }
-    // around the pulse edge / past the end of the shorter lane: per-lane gates, finished lanes frozen
-    for (; i < n_max; ++i) {
-        P nz[12];
-        philox_normals12<P>(ns, (uint32_t)i, nscale, nz);
+    // a substep around the pulse edge / past the end of the shorter lane: per-lane gates, finished lanes frozen
+    auto substep_edge = [&](int i, const P* nz) {
         P aH1 = aH, aL1 = aL, aH2 = aH, aL2 = aL, aH4 = aH, aL4 = aL;
         const P sfx = fx, sfy = fy, sfz = fz, sex = ex, sey = ey, sez = ez;
-        const int g0 = guard[0], g1 = guard[NL - 1];
+        int gs[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) gs[l] = guard[l];
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
-            if (i >= i_safe[l]) {
+            if (i >= i_safe[l] && i < E[l].n) {
                 if (!pulse_on(i, 0, E[l].dt, E[l].t_pulse)) { L::set(aH1, l, 0.0f); L::set(aL1, l, 0.0f); }
                 if (!pulse_on(i, 1, E[l].dt, E[l].t_pulse)) { L::set(aH2, l, 0.0f); L::set(aL2, l, 0.0f); }
                 if (!pulse_on(i, 2, E[l].dt, E[l].t_pulse)) { L::set(aH4, l, 0.0f); L::set(aL4, l, 0.0f); }
@@ -156,9 +183,27 @@ STG_HD void integrate_thermal(const ThermalEnv* E, double (*m)[3], int* guard, d
             if (i >= E[l].n) {      // this lane had finished: undo
                 L::set(fx, l, L::get(sfx, l)); L::set(fy, l, L::get(sfy, l)); L::set(fz, l, L::get(sfz, l));
                 L::set(ex, l, L::get(sex, l)); L::set(ey, l, L::get(sey, l)); L::set(ez, l, L::get(sez, l));
-                guard[l] = l ? g1 : g0;
+                guard[l] = gs[l];
             }
         }
+    };
+    // one draw (three Philox blocks per lane) serves the substep pair (2g, 2g+1)
+    int g = 0;
+    const int g_fast = fast_to / 2, g_end = (n_max + 1) / 2;
+#pragma unroll kSubstepPairUnroll
+    for (; g < g_fast; ++g) {       // every lane running and inside its pulse
+        P nz[12];
+        src.first((uint32_t)g, nz);
+        substep(2 * g, nz, aH, aL, aH, aL, aH, aL);
+        src.second((uint32_t)g, nz);
+        substep(2 * g + 1, nz, aH, aL, aH, aL, aH, aL);
+    }
+    for (; g < g_end; ++g) {
+        P nz[12];
+        src.first((uint32_t)g, nz);
+        substep_edge(2 * g, nz);
+        src.second((uint32_t)g, nz);        // always taken: the hand-over of the shared-memory source counts on it
+        if (2 * g + 1 < n_max) substep_edge(2 * g + 1, nz);
     }
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
@@ -184,21 +229,14 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
     constexpr bool SCALED = sizeof(R) == 4 && AXIS_Z && !TH;            // block-scaled transverse pair
     constexpr bool TRACK = FAST && NOISE != 1;                          // with the Philox stream parity is statistical
     constexpr int NS = EULER ? 3 : 12;
-    // substeps whose stage times are certainly inside the pulse run with the constant a; the few around the pulse edge
-    // evaluate current_func(t) exactly in FP64 (the k4 stage of the LAST substep sees t_i+dt > T for ~16 % of f32 durations)
-    int i_safe;
-    if (t_pulse >= t_end) {
-        i_safe = n - 1;
-    } else {
-        const double qd = t_pulse / dt - 2.0;
-        i_safe = qd < 0.0 ? 0 : (qd > (double)n ? n : (int)qd);
-    }
+    const int i_safe = pulse_safe_substeps(n, dt, t_pulse, t_end);
     if (traj) { traj[0] = mx; traj[1] = my; traj[2] = mz; }
 
     if constexpr (FAST && NOISE == 1) {
         ThermalEnv E{f, J, dt, t_pulse, t_end, n, ns};
+        PhiloxSource<float> src{{ns}, thermal_nscale(f, dt), {}};
         double w[1][3] = {{mx, my, mz}};
-        integrate_thermal<float>(&E, w, &guard, traj, traj_rows);
+        integrate_thermal<float>(&E, src, w, &guard, traj, traj_rows);
         mx = w[0][0]; my = w[0][1]; mz = w[0][2];
     } else if constexpr (FAST) {
         StepConsts<float> c;
@@ -593,9 +631,19 @@ STG_HD void env_step_integrate(const StgSttStepArgs& a, int64_t e, EnvStepCtx& c
         integrate<R, AXIS_Z, NOISE, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ns,
                                            nrow, nullptr, c.guard, NOISE == 2 ? a.noise_stride : 0x7fffffff, 0x7fffffff,
                                            &c.illcond);
-    else
+    else {
+        // a parameter set without thermal field inside a launch with the noise stream (device mixes): deterministic path; such a
+        // launch has no second pass, so an ill-conditioned FP32 trajectory is repeated with FP64 stages on the spot
+        const double w0 = c.w[0], w1 = c.w[1], w2 = c.w[2];
+        const int guard0 = c.guard;
         integrate<R, AXIS_Z, 0, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ns,
                                        nullptr, nullptr, c.guard, 0x7fffffff, 0x7fffffff, &c.illcond);
+        if (sizeof(R) == 4 && c.illcond) {
+            c.w[0] = w0; c.w[1] = w1; c.w[2] = w2; c.guard = guard0; c.illcond = 0;
+            integrate<double, AXIS_Z, 0, EULER>(c.f, c.J, c.w[0], c.w[1], c.w[2], c.plan.n, c.plan.dt, c.T, c.T, ns,
+                                                nullptr, nullptr, c.guard);
+        }
+    }
 }
 
 // One env (index e of a.n_envs): reads and updates the FP64 state planes, returns the outputs in `r`.
@@ -634,7 +682,8 @@ STG_HD int env_step_pair_body(const StgSttStepArgs& a, int64_t eA, int64_t eB, E
                  make_stream(a.seed, a.env_offset + (uint64_t)eB, (uint32_t)a.state.episode[eB], (uint32_t)cb.step)}};
             double w[2][3] = {{ca.w[0], ca.w[1], ca.w[2]}, {cb.w[0], cb.w[1], cb.w[2]}};
             int g[2] = {ca.guard, cb.guard};
-            integrate_thermal<F2>(E, w, g);
+            PhiloxSource<F2> src{{E[0].ns, E[1].ns}, mk2(thermal_nscale(ca.f, ca.plan.dt), thermal_nscale(cb.f, cb.plan.dt)), {}};
+            integrate_thermal<F2>(E, src, w, g);
             ca.w[0] = w[0][0]; ca.w[1] = w[0][1]; ca.w[2] = w[0][2]; ca.guard = g[0];
             cb.w[0] = w[1][0]; cb.w[1] = w[1][1]; cb.w[2] = w[1][2]; cb.guard = g[1];
         }

@@ -452,16 +452,19 @@ def test_device_mix_param_index(cuda_device):
         assert int(i1["status"].max()) == 0 and float((m_after - m0n[sel]).__abs__().max()) > 1e-6
 
 
-def test_packed_pair_kernel_is_bit_identical(cuda_device):
-    """FP32 / e=z / RK4 / no noise dispatches the two-envs-per-thread FFMA2 kernel; it must reproduce the one-env-per-thread
-    kernel (FP32 outputs bit for bit, FP64 bookkeeping to 1e-12) for ragged substep counts, odd batch size, auto-reset, sorted and unsorted launches)."""
+@pytest.mark.parametrize("thermal", [False, True])
+def test_packed_pair_kernel_is_bit_identical(thermal, cuda_device):
+    """FP32 / e=z / RK4 dispatches two-envs-per-thread FFMA2 kernels (no noise: stt_env_step_pair_kernel; in-kernel noise stream:
+    the warp-specialised stt_env_step_ws_kernel, whose samples come from other warps through shared memory). They must reproduce
+    the one-env-per-thread kernel (FP32 outputs bit for bit, FP64 bookkeeping to 1e-12) for ragged substep counts, odd batch size,
+    auto-reset, sorted and unsorted launches)."""
     torch = _torch()
     n, jm = 4099, 1.1e-6
     m0, tgt, acts = _random_setup(n, 13, tmax=2e-9)
     res = {}
     for pair in (True, False):
         for sort in (False, True):
-            env = _make(n, "f32", cuda_device, max_current=jm, include_thermal_fluctuations=False, autoreset=True,
+            env = _make(n, "f32", cuda_device, max_current=jm, include_thermal_fluctuations=thermal, autoreset=True,
                         max_steps=2, rng_seed=4, pair_kernel=pair, sort_by_substeps=sort)
             env.reset(options={"initial_state": m0, "target_state": tgt})
             out = []

@@ -18,6 +18,8 @@ cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
        "-o", "/dev/null"] + defs
 err = subprocess.run(cmd, capture_output=True, text=True).stderr
 names = re.findall(r"Compiling entry function '(\S+)'", err)
+if not names:
+    sys.exit(err)
 dem = subprocess.run(["c++filt"] + names, capture_output=True, text=True).stdout.splitlines()
 blocks = re.split(r"Compiling entry function '\S+' for 'sm_100a'", err)[1:]
 for name, b in zip(dem, blocks):
