@@ -13,9 +13,14 @@ densities — at the env count the metric is quoted on: 1,048,576 envs per GPU (
   e2e        same metric through the public API (SpinTorqueVectorEnv.step) with HOST numpy actions: pinned H2D of the
              actions and D2H of obs/reward/flags inside the timed region
   roofline   dominant kernel (stt_env_step_kernel) against the FP32 FMA pipe (the path is not HBM- or tensor-bound)
-  cpu_baseline  the C restatement of the reference algorithm (oracle/c, kind "port") on all host cores, bounded sample
+  cpu_baseline  the reference's CPU path on the box's host cores, bounded sample: the LIVE reference (sanitised
+             SpinTorqueEnv.step, one process per core, kind "reference") when a checkout is reachable (tools/time_live_reference.py
+             probes $STG_REFERENCE, baseline/_ref, oracle/_ref, /root/reference), else the C restatement of the same algorithm
+             (oracle/c, kind "port"); the port's figure is reported in both cases
 
-`--impl reference` times that CPU port alone (the reference is pure Python and cannot travel to the GPU box).
+`--impl reference` times that CPU path alone, on all host cores (rank 0 only under torchrun). The reference is a pure-Python
+package whose own packaging installs 3 of its 62 modules, so it does not travel to the GPU box: there the arm is
+the port and its line says why.
 """
 from __future__ import annotations
 
@@ -36,6 +41,14 @@ N_ENVS_PER_GPU = 1 << 20
 PULSE_S = 1e-9                 # float32(1e-9) floors to 999 substeps (physics/simple_solver.py:137-139)
 FLOP_RK4_THERMAL = 329         # algorithmic flops per RK4 substep, thermal on
 FLOP_RK4 = 301
+# FP32 flops the dispatched thermal kernel EXECUTES per env-substep (FFMA2 = 4, FMUL2 / FADD2 = 2 per instruction and two envs;
+# SASS instruction mix of its substep loop, profiles/r02_sass_stats.txt): 190 in the four RK4 stages, the combination, the
+# renormalisation and the compensated state update + 42 in Box-Muller. The e = z stage drops the structural zeros of the 329.
+FLOP_RK4_THERMAL_EXECUTED = 232
+# one launch of the headline kernel at 1,048,576 envs x 999 substeps under `ncu --set full` (profiles/, condensed CSV):
+# dram__bytes_read.sum + dram__bytes_write.sum and the pipe utilisations (pct of peak sustained active)
+NCU_TRAFFIC_BYTES = None
+NCU_PIPES = None
 BYTES_PER_ENV_STEP = 150       # algorithmic HBM bytes per env-step
 FP32_LANES_PER_SM, N_SM = 128, 148
 
@@ -144,24 +157,51 @@ def python_port_rate(max_seconds: float = 4.0):
     return sub / (time.perf_counter() - t0)
 
 
+def live_reference_rate(seconds: float, thermal: bool = True):
+    """The live reference's own SpinTorqueEnv.step, one process per host core (tools/time_live_reference.py in a subprocess:
+    the workers are spawned processes and must not inherit a CUDA context). Returns the tool's dict; ['available'] False with a
+    reason when no checkout is reachable on this box."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "time_live_reference.py"), "--json", "--seconds", str(seconds)]
+    if not thermal:
+        cmd.append("--no-thermal")
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=seconds * 4 + 240)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # noqa: BLE001
+        return {"available": False, "why": f"time_live_reference.py failed: {exc!r}"}
+
+
 def run_reference(args, rank):
-    """`--impl reference`: the CPU implementation of the path on all host cores. Rank 0 only."""
+    """`--impl reference`: the reference's CPU implementation of the path on all host cores. Rank 0 only."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_sample = 2048 * threads          # bounded sample: ~0.5 s of CPU work per step on all host threads
-    for _ in range(args.warmup):
-        cpu_port_rate(max(threads, n_sample // 8), 1, threads)
-    t0 = time.perf_counter()
-    sub_rate, env_rate, dt = cpu_port_rate(n_sample, args.steps, threads)
+    live = live_reference_rate(min(60.0, max(5.0, 1.0 * args.steps)))
+    if live.get("available"):
+        sub_rate, env_rate = live["substeps_per_s"], live["env_steps_per_s"]
+        n_sample, kind = live["procs"], "reference"
+        ms_per_step = 1e3 * live["procs"] / env_rate                 # one env.step of each process's env
+        sample = (f"live reference at {live['path']}: {live['procs']} processes (one SpinTorqueEnv each, sanitised) x "
+                  f"{live['seconds_per_proc']:.0f} s = {live['env_steps']} env.step x 999 RK4 substeps, thermal on")
+        cores = live["procs"]
+        extra = {"vectorized_solver": live.get("vectorized_solver")}
+    else:
+        n_sample = 2048 * threads          # bounded sample: ~0.5 s of CPU work per step on all host threads
+        for _ in range(args.warmup):
+            cpu_port_rate(max(threads, n_sample // 8), 1, threads)
+        sub_rate, env_rate, dt = cpu_port_rate(n_sample, args.steps, threads)
+        ms_per_step, kind, cores = 1e3 * dt / args.steps, "port", threads
+        sample = (f"{n_sample} envs x {args.steps} steps x 999 RK4 substeps, thermal on, C restatement oracle/c on {threads} "
+                  f"threads (live reference not reachable: {live.get('why')})")
+        extra = {}
     line = {
         "impl": "reference", "metric": "llgs_substeps_per_sec", "value": sub_rate, "unit": "LLGS substeps/s",
         "env_steps_per_s": env_rate, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus, n_sample, "bounded sample of the same workload"),
-        "cpu_baseline": {"value": sub_rate, "unit": "LLGS substeps/s", "cores": threads, "kind": "port",
-                         "sample": f"{n_sample} envs x {args.steps} steps x 999 RK4 substeps, thermal on"},
+        "cpu_baseline": dict({"value": sub_rate, "unit": "LLGS substeps/s", "cores": cores, "kind": kind, "sample": sample},
+                             **extra),
         "e2e": {"value": sub_rate, "unit": "LLGS substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -216,7 +256,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints a banner)
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     n_local = args.envs_per_gpu
@@ -236,14 +275,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def fresh_actions(act):
+        """Random pulse sequences: a fresh current density per env and step, drawn on the device (the duration stays the
+        metric's 1 ns = 999 substeps). One torch fill kernel per step inside the timed region; not counted in gpu_launches."""
+        act[:, 0].uniform_(-1.1e-6, 1.1e-6)
+
     def timed_device_steps(env, act, steps, warmup):
         for _ in range(warmup):
+            fresh_actions(act)
             env.step(act)
         barrier()
         l0 = env.gpu_launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
+            fresh_actions(act)
             env.step(act)
         e1.record()
         barrier()
@@ -277,22 +323,30 @@ def main():
     env_h = SpinTorqueVectorEnv(num_envs=n_local, device=dev, dtype=tdtype, rng_seed=1234, env_offset=rank * n_local,
                                 host_outputs=True, **kw)
     env_h.reset(seed=1234)
-    act_pinned = torch.from_numpy(act_host).pin_memory()
+    # a different host action array every step (four pinned buffers of random pulses used in turn)
+    act_ring = [torch.from_numpy(make_actions(n_local, 200 + 10 * rank + k)).pin_memory() for k in range(4)]
 
-    def e2e_step():
-        o, r, te, tr, _ = env_h.step(act_pinned)             # H2D of the actions + kernel + results in host memory + sync
+    def e2e_step(k):
+        o, r, te, tr, _ = env_h.step(act_ring[k & 3])        # H2D of the actions + kernel + results in host memory + sync
         return float(r[0]) + float(o[0, 0]) + float(te[0]) + float(tr[0])      # the caller reads the host buffers every step
 
-    for _ in range(args.warmup):
-        e2e_step()
+    for k in range(args.warmup):
+        e2e_step(k)
     barrier()
-    t0 = time.perf_counter()
+    ended0 = env_h.episode_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    for k in range(args.steps):
+        e2e_step(k)
     e1.record()
     barrier()
+    ended1 = env_h.episode_stats()
+    # rows of final_obs cross PCIe only for the envs whose episode ended in the step (include/stg.h StgSttStepOut.final_obs)
+    resets_per_step = ((ended1["terminated"] + ended1["truncated"]) - (ended0["terminated"] + ended0["truncated"])) / args.steps
+    if world > 1:
+        t = torch.tensor([resets_per_step], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        resets_per_step = float(t[0])
     e2e_ms = max(e0.elapsed_time(e1), 0.0)
     if world > 1:
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -353,6 +407,61 @@ def main():
             except Exception as exc:  # noqa: BLE001 - secondary numbers must never break the contract line
                 extras["other_configs_error"] = repr(exc)
 
+    # ---- multi-GPU extras (every rank takes part): strong scaling at the north star's total, a short configs[4] rollout -----
+    if world > 1 and not args.no_extras and not args.total_envs:
+        total = N_ENVS_PER_GPU                                   # 1,048,576 envs over all ranks (131,072 per GPU at N = 8)
+        if total % world == 0:
+            n_s = total // world
+            env_s = SpinTorqueVectorEnv(num_envs=n_s, device=dev, dtype=tdtype, rng_seed=1234, env_offset=rank * n_s, **kw)
+            env_s.reset(seed=1234)
+            act_s = torch.from_numpy(make_actions(n_s, 300 + rank)).to(dev)
+            ms_s, _ = timed_device_steps(env_s, act_s, args.steps, args.warmup)
+            if rank == 0:
+                extras["strong_scaling_total_1048576"] = {
+                    "envs_per_gpu": n_s, "ms_per_step": ms_s / args.steps,
+                    "substeps_per_s": total * 999 * args.steps / (ms_s * 1e-3),
+                    "env_steps_per_s": total * args.steps / (ms_s * 1e-3)}
+            del env_s
+        # BASELINE configs[4]: 1M+ envs sharded over the ranks feeding an SB3-shaped rollout buffer; policy = fixed random MLP,
+        # pulse durations from the policy (ragged substep counts, counting sort active), statistics all-reduced once at the end.
+        # n_steps is cut to 128 of the 2048 so that the bench stays short; tools/rollout_bench.py runs the full length.
+        from spin_torque_rl_gym_b200 import RolloutCollector
+        n_r, n_steps_r = N_ENVS_PER_GPU // world if N_ENVS_PER_GPU % world == 0 else 131072, 128
+        env_r = SpinTorqueVectorEnv(num_envs=n_r, device=dev, dtype=tdtype, rng_seed=7, env_offset=rank * n_r,
+                                    **dict(kw, sort_by_substeps="auto"))
+        gen = torch.Generator(device=dev).manual_seed(0)
+        w1 = torch.randn(12, 64, device=dev, generator=gen) * 0.3
+        w2 = torch.randn(64, 2, device=dev, generator=gen) * 0.3
+
+        def policy(obs):
+            h = torch.tanh(obs @ w1) @ w2
+            a2 = torch.empty(obs.shape[0], 2, device=dev)
+            a2[:, 0] = torch.tanh(h[:, 0]) * 1.1e-6
+            a2[:, 1] = torch.sigmoid(h[:, 1]) * 1e-9 + 1e-11
+            return a2
+
+        RolloutCollector(env_r, n_steps=2, store_observations=False).collect(policy)       # warm-up
+        col = RolloutCollector(env_r, n_steps=n_steps_r)
+        env_r.reset(seed=7)
+        env_r.reset_stats()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st_r = col.collect(policy)                              # includes the one NCCL all-reduce of the statistics vector
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            ms_r = float(t[0])
+            extras["rollout_configs4"] = {
+                "envs_total": n_r * world, "envs_per_gpu": n_r, "n_steps": n_steps_r, "rollout_ms": ms_r,
+                "env_steps_per_s": n_r * world * n_steps_r / (ms_r * 1e-3), "substeps_per_s": st_r["substeps"] / (ms_r * 1e-3),
+                "episodes": st_r["episodes"], "success_rate": st_r["success_rate"],
+                "note": "policy-chosen pulse durations (ragged substeps, sorted launch), obs/actions/rewards/dones stored per step, "
+                        "stats all-reduced via NCCL once at the end; 128 of the 2048 steps of BASELINE configs[4]"}
+        del env_r, col
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -360,37 +469,56 @@ def main():
         cpu_port_rate(max(threads, n_sample // 64), 1, threads, thermal)
         cpu_steps = 8                                  # 131072 envs x 8 steps on 16 threads: ~13 s
         rate, _, dt = cpu_port_rate(n_sample, cpu_steps, threads, thermal)
-        cpu_baseline = {"value": rate, "unit": "LLGS substeps/s", "cores": threads, "kind": "port",
-                        "sample": f"{n_sample} envs x {cpu_steps} steps x 999 RK4 substeps (thermal {'on' if thermal else 'off'}), "
-                                  f"C restatement oracle/c on {threads} threads, {dt:.1f} s",
-                        "python_port_substeps_per_s_1core": python_port_rate(3.0)}
+        port = {"value": rate, "unit": "LLGS substeps/s", "cores": threads,
+                "sample": f"{n_sample} envs x {cpu_steps} steps x 999 RK4 substeps (thermal {'on' if thermal else 'off'}), "
+                          f"C restatement oracle/c on {threads} threads, {dt:.1f} s",
+                "python_port_substeps_per_s_1core": python_port_rate(3.0)}
+        live = live_reference_rate(10.0, thermal)
+        if live.get("available"):
+            cpu_baseline = {"value": live["substeps_per_s"], "unit": "LLGS substeps/s", "cores": live["procs"], "kind": "reference",
+                            "sample": f"live reference at {live['path']}: sanitised SpinTorqueEnv.step, {live['procs']} processes x "
+                                      f"{live['seconds_per_proc']:.0f} s = {live['env_steps']} env.step x 999 RK4 substeps",
+                            "env_steps_per_s": live["env_steps_per_s"], "vectorized_solver": live.get("vectorized_solver"),
+                            "port": port}
+        else:
+            cpu_baseline = dict(port, kind="port", reference_unavailable=live.get("why"))
 
     if rank == 0:
         achieved = value / n_gpus * flop_sub / 1e12            # per-GPU algorithmic TFLOP/s of the dominant kernel
-        peak = fma_probe_tflops if fma_probe_tflops else fp32_peak_theory
+        headline = n_local == N_ENVS_PER_GPU and thermal and args.dtype == "f32"
+        executed = value / n_gpus * FLOP_RK4_THERMAL_EXECUTED / 1e12 if thermal and args.dtype == "f32" else None
         line = {
             "metric": "llgs_substeps_per_sec", "value": value, "unit": "LLGS substeps/s",
             "env_steps_per_s": env_steps, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": args.dtype + " stages, f64 state", "data": "synthetic",
+            "dtype": args.dtype + " stages, " + ("compensated f32 state inside a step, " if thermal and args.dtype == "f32" else "")
+                     + "f64 state between steps", "data": "synthetic",
             "config": workload_config(n_gpus, n_local),
             "e2e": {"value": e2e_value, "unit": "LLGS substeps/s", "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": n_local * 8 * n_gpus, "d2h_bytes_per_step": n_local * (48 + 8 + 2) * n_gpus,
-                    "api": "SpinTorqueVectorEnv(host_outputs=True).step(pinned host actions): H2D of the actions, the kernel writes obs/reward/"
-                           "terminated/truncated into pinned host memory, stream synchronised every step"},
+                    "h2d_bytes_per_step": n_local * 8 * n_gpus,
+                    "d2h_bytes_per_step": int(n_local * (48 + 8 + 2) * n_gpus + 48 * resets_per_step),
+                    "final_obs_rows_per_step": resets_per_step,
+                    "api": "SpinTorqueVectorEnv(host_outputs=True).step(pinned host actions, a different array every step): H2D of "
+                           "the actions, the kernel writes obs / reward / terminated / truncated (58 B per env) and the final_obs rows "
+                           "of ended episodes (48 B each) into pinned host memory, stream synchronised every step"},
             "gpu_launches": launches,
             "roofline": {
-                "bound": "fp32_fma", "kernel": "stt_env_step_kernel<float, axis_z, philox, rk4>",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": ("stg_probe_fma measured in this run" if fma_probe_tflops else "theoretical"),
-                "peak_theoretical": fp32_peak_theory, "frac_of_theoretical": achieved / fp32_peak_theory,
-                "algorithmic_flop_per_substep": flop_sub, "substeps_per_launch": n_local * 999,
-                "kernel_ms": kernel_ms,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size from the ncu --set full capture
-                # (profiles/r01_ncu_stt_env_step_f32_thermal1.csv): 76.2 MB + 146.8 MB; algorithmic 150 B x 1M envs = 157 MB
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 1,048,576 envs from the ncu --set full capture of
-                # the shipped kernel (profiles/r01_ncu_stt_env_step_f32_thermal1.csv: 76.1 + 141.8 MB; algorithmic 157 MB)
-                "traffic": 217.9e6 if n_local == N_ENVS_PER_GPU and thermal and args.dtype == "f32" else None,
+                # the path is FP32-pipe bound (no contraction, 2,000 flop/B): the contract's "hbm" | "tensor" do not apply; the HBM
+                # figure is reported beside it
+                "bound": "fp32_fma",
+                "kernel": "stt_env_step_pair_kernel<1> (two envs per thread on FFMA2, axis z, Philox, RK4)" if thermal and args.dtype == "f32"
+                          else "stt_env_step_kernel",
+                "achieved": achieved, "peak": fp32_peak_theory, "unit": "TFLOP/s", "frac": achieved / fp32_peak_theory,
+                "peak_source": "theoretical 148 SM x 128 FP32 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json carries no FP32 figure)",
+                "peak_fma_probe": fma_probe_tflops,
+                "frac_of_fma_probe": achieved / fma_probe_tflops if fma_probe_tflops else None,
+                "algorithmic_flop_per_substep": flop_sub, "executed_flop_per_substep": FLOP_RK4_THERMAL_EXECUTED if executed else None,
+                "executed_tflops": executed, "executed_frac": executed / fp32_peak_theory if executed else None,
+                "substeps_per_launch": n_local * 999, "kernel_ms": kernel_ms,
+                # pipe utilisation and DRAM traffic of one launch at this size from the ncu --set full capture of the shipped kernel
+                # (profiles/r02_ncu_stt_env_step_pair_f32_thermal1.csv)
+                "pipes_pct_from_ncu": NCU_PIPES if headline else None,
+                "traffic": NCU_TRAFFIC_BYTES if headline else None,
                 "hbm": {"achieved_gbs": n_local * BYTES_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peaks_src},
             },

@@ -22,7 +22,6 @@ rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1
 dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
 torch.cuda.set_device(dev)
 if world > 1:
-    os.environ["NCCL_DEBUG"] = "WARN"
     torch.distributed.init_process_group("nccl", device_id=dev)
 lo, hi = stg.shard_range(a.envs * world, rank, world)
 env = stg.make("SpinTorque-v0", num_envs=hi - lo, device=dev, max_current=1.1e-6, rng_seed=7, env_offset=lo)
