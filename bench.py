@@ -47,8 +47,11 @@ FLOP_RK4 = 301
 FLOP_RK4_THERMAL_EXECUTED = 232
 # one launch of the headline kernel at 1,048,576 envs x 999 substeps under `ncu --set full` (profiles/, condensed CSV):
 # dram__bytes_read.sum + dram__bytes_write.sum and the pipe utilisations (pct of peak sustained active)
-NCU_TRAFFIC_BYTES = None
-NCU_PIPES = None
+# (profiles/r02_ncu_stt_env_step_pair_f32_thermal1.csv; 86.3 MB read + 134.5 MB written: the FP64 state planes and the per-step
+# diagnostics make it 1.4x the 150 B per env-step of SURVEY 8(d); 15 GB/s, irrelevant against the FP32 pipes)
+NCU_TRAFFIC_BYTES = 220.8e6
+NCU_PIPES = {"fma": 55.7, "fma_heavy": 68.9, "xu": 55.1, "alu": 30.3, "fp64": 0.9, "issue_slots_busy": 52.6,
+             "warp_instructions_per_env_substep": 192.3}
 BYTES_PER_ENV_STEP = 150       # algorithmic HBM bytes per env-step
 FP32_LANES_PER_SM, N_SM = 128, 148
 
