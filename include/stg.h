@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define STG_ABI_VERSION 6
+#define STG_ABI_VERSION 7
 
 /* error codes */
 #define STG_OK 0
@@ -292,8 +292,15 @@ typedef struct StgLlgParams {
     int32_t reserved;
 } StgLlgParams;
 
-/* Argument block of a batched LLGSSolver.solve(m_initial, (0, t_end), params, current_func, field_func, thermal_noise,
- * temperature) with current_func(t) = J if t <= t_pulse else 0 and a constant H_app per trajectory.
+/* Argument block of a batched LLGSSolver.solve(m_initial, (t_start, t_end), params, current_func, field_func, thermal_noise,
+ * temperature) with current_func(t) = J if t <= t_pulse else 0 and a constant H_app per trajectory, or - n_seg > 0 - with
+ * piecewise-constant current_func / field_func tables evaluated at the controller's data-dependent stage times:
+ *   d_seg_t       [seg_rows][n_seg]       ascending segment ends; segment k is (t_{k-1}, t_k] (right-closed, like `t <= t_pulse`),
+ *                                         segment n_seg is everything after the last end
+ *   d_seg_current [seg_rows][n_seg + 1]   current density of each segment (replaces d_current / d_t_pulse)
+ *   d_seg_field   [seg_rows][n_seg + 1][3] applied field of each segment, or NULL (= d_happ)
+ *   seg_rows      1 (one table shared by every trajectory) or n_envs
+ *   d_t_start     [n] or NULL (= 0): solve_ivp integrates in absolute time (its minimum step is 10 ulp(t)); t_end > t_start
  *   d_table [n_sets] (DEVICE copy of StgLlgParams), d_param_index [n] or NULL
  *   d_m0 [n][3]; d_t_end [n]; d_current [n] or NULL; d_t_pulse [n] or NULL (= always on); d_happ [n][3] or NULL;
  *   d_voltage [n] or NULL
@@ -332,6 +339,12 @@ typedef struct StgRk45Args {
     uint32_t flags;
     const int32_t* d_perm;           /* NULL or [n]: thread s integrates trajectory d_perm[s]; every array above stays indexed by
                                       * the trajectory, as does the Philox id (sort by (parameter set, t_end) for homogeneous warps) */
+    const double* d_t_start;
+    const double* d_seg_t;
+    const double* d_seg_current;
+    const double* d_seg_field;
+    int32_t n_seg;
+    int32_t seg_rows;
 } StgRk45Args;
 
 int stg_llgs_rk45_f64(const StgRk45Args* args, void* stream);
@@ -440,6 +453,26 @@ int stg_vcma_anisotropy_f64(const StgDeviceParams* p, const double* d_voltage, d
  * (offset + row, call_index). */
 int stg_thermal_field_f64(double strength, double decay, double* d_state, double* d_out, uint64_t seed, uint64_t offset,
                           uint64_t call_index, int64_t n, void* stream);
+
+/* ThermalFluctuations analytics (physics/thermal_model.py:46-73 compute_noise_strength, :139-258 compute_thermal_barrier /
+ * compute_switching_probability / compute_retention_time, i.e. the body of generate_temperature_sweep :274-336) on a grid of
+ * n_t temperatures x n_dev devices in one launch.
+ *   d_temperature [n_t]; d_ku, d_volume, d_damping, d_ms [n_dev]; d_barrier [n_dev] energy barriers in J or NULL (= K_u V)
+ *   d_out [4][n_t][n_dev]: stability factor, switching probability over measurement_time, retention time [s] at failure_rate,
+ *                          noise strength [A/m]; T <= 0 gives (inf, 0, inf, 0) like the reference */
+typedef struct StgThermalAnalyticsArgs {
+    const double* d_temperature;
+    const double* d_ku;
+    const double* d_volume;
+    const double* d_damping;
+    const double* d_ms;
+    const double* d_barrier;
+    double* d_out;
+    double k_b, mu0, gamma;          /* 1.380649e-23, 4 pi 1e-7, 2.21e5 (physics/thermal_model.py:31-33, 50) */
+    double attempt_frequency, measurement_time, failure_rate;
+    int32_t n_t, n_dev;
+} StgThermalAnalyticsArgs;
+int stg_thermal_analytics_f64(const StgThermalAnalyticsArgs* args, void* stream);
 
 /* EnergyLandscape.compute_energy / compute_energy_gradient (physics/energy_landscape.py:36-104) for n states: m is
  * normalised, E = Zeeman + uniaxial + demag, gradient = H_app + H_anis + H_demag. Either output may be NULL. */

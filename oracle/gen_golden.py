@@ -449,6 +449,85 @@ def gen_next():
     print("wrote next.npz")
 
 
+def gen_round2():
+    """Round-2 additions, all from the LIVE reference: (i) ThermalFluctuations analytics on a temperature x device grid
+    (physics/thermal_model.py:46-73, 139-258), (ii) LLGSSolver.solve with t_span[0] != 0 and with piecewise-constant
+    current_func / field_func (physics/llgs_solver.py:51-180), (iii) LLGSSolver.find_stable_states (:264-305) with its hard-coded
+    10 ns relaxation shortened - the method is re-run here line for line with (0, relax_time) so that it finishes in seconds."""
+    _import_reference()
+    from spin_torque_gym.physics import ThermalFluctuations
+    from spin_torque_gym.physics.llgs_solver import LLGSSolver
+    rng = np.random.default_rng(77)
+    out = {}
+    # ---- (i) thermal grid
+    temps = np.array([0.0, 4.2, 77.0, 150.0, 233.15, 300.0, 358.15, 398.15, 450.0, 600.0])
+    n_dev = 9
+    ku = rng.uniform(0.4e6, 1.6e6, n_dev); vol = rng.uniform(5e-26, 4e-25, n_dev)
+    al = rng.uniform(0.005, 0.05, n_dev); ms = rng.uniform(5e5, 1.2e6, n_dev)
+    f0, tm, fr = 2.5e9, 3.0e-3, 1e-6
+    grid = np.zeros((4, len(temps), n_dev))
+    for i, T in enumerate(temps):
+        th = ThermalFluctuations(temperature=float(T), seed=0)
+        for j in range(n_dev):
+            e = ku[j] * vol[j]
+            grid[0, i, j] = th.compute_thermal_barrier(ku[j], vol[j])
+            grid[1, i, j] = th.compute_switching_probability(e, attempt_frequency=f0, measurement_time=tm)
+            grid[2, i, j] = th.compute_retention_time(e, failure_rate=fr, attempt_frequency=f0)
+            grid[3, i, j] = th.compute_noise_strength(al[j], ms[j], vol[j])
+    out.update({'thg/temps': temps, 'thg/ku': ku, 'thg/vol': vol, 'thg/damping': al, 'thg/ms': ms, 'thg/f0': f0,
+                'thg/tm': tm, 'thg/fr': fr, 'thg/grid': grid})
+    # ---- (ii) LLGSSolver.solve: shifted time span; piecewise-constant controls
+    base = _stt_params(volume=1e-11)                 # V = 1e-11 m^3: currents of ~10 A/m^2 give torque rates ~1e11 1/s (gen_rk45)
+    base['demag_factors'] = np.array([0.05, 0.15, 0.8])
+    solver = LLGSSolver()
+    m0 = np.array([0.3, -0.2, 0.93])
+    cases = {
+        'shift': dict(span=(2.0e-11, 5.5e-11), cur=([3.1e-11], [14.0, 0.0]), fld=([], [[1.5e4, -0.5e4, 2e3]])),
+        'pwc': dict(span=(0.0, 5.0e-11), cur=([1.2e-11, 2.6e-11, 4.1e-11], [15.0, -9.0, 0.0, 6.0]),
+                    fld=([1.9e-11], [[2e4, 0.0, 0.0], [0.0, -1e4, 5e3]])),
+        'shift_pwc': dict(span=(-1.0e-11, 3.0e-11), cur=([0.0, 1.5e-11], [0.0, 18.0, -18.0]),
+                          fld=([0.7e-11], [[0.0, 0.0, 1e4], [1e4, 1e4, 0.0]])),
+    }
+    for name, c in cases.items():
+        cb, cv = np.array(c['cur'][0]), np.array(c['cur'][1])
+        fb, fv = np.array(c['fld'][0]), np.array(c['fld'][1], dtype=float)
+
+        def cur(t, cb=cb, cv=cv):
+            return float(cv[int(np.searchsorted(cb, t, side='left'))])
+
+        def fld(t, fb=fb, fv=fv):
+            return fv[int(np.searchsorted(fb, t, side='left'))].copy()
+
+        res = solver.solve(m0, c['span'], base, cur, fld, thermal_noise=False)
+        assert res['success']
+        for k in ('t', 'm', 'energy', 'torques'):
+            out[f'solve/{name}/{k}'] = np.asarray(res[k])
+        out[f'solve/{name}/span'] = np.array(c['span'])
+        out[f'solve/{name}/cur_breaks'] = cb; out[f'solve/{name}/cur_values'] = cv
+        out[f'solve/{name}/fld_breaks'] = fb; out[f'solve/{name}/fld_values'] = fv
+        print(name, len(res['t']), flush=True)
+    out['solve/m0'] = m0
+    out['solve/demag'] = base['demag_factors']
+    # ---- (iii) find_stable_states with a short relaxation (the reference hard-codes (0, 10e-9): ~1e5 RHS calls per trial)
+    fp = _stt_params(volume=1e-11, damping=0.3)
+    relax, n_trials, threshold, seed = 3.0e-10, 8, 0.2, 5
+    np.random.seed(seed)
+    stable, finals = [], []
+    for _ in range(n_trials):                                    # body of physics/llgs_solver.py:273-303
+        m_init = np.random.normal(0, 1, 3)
+        m_init = m_init / np.linalg.norm(m_init)
+        result = solver.solve(m_init, (0, relax), fp, lambda t: 0.0, lambda t: np.zeros(3), thermal_noise=False)
+        if result['success']:
+            m_final = result['m'][-1]
+            finals.append(m_final)
+            if all(np.linalg.norm(m_final - s_) >= threshold for s_ in stable):
+                stable.append(m_final)
+    out.update({'fss/relax': relax, 'fss/n_trials': n_trials, 'fss/threshold': threshold, 'fss/seed': seed,
+                'fss/damping': 0.3, 'fss/volume': 1e-11, 'solve/volume': 1e-11, 'fss/stable': np.array(stable), 'fss/finals': np.array(finals)})
+    print('find_stable_states', len(stable), 'of', n_trials, flush=True)
+    np.savez_compressed(os.path.join(GOLD, "round2.npz"), **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["stt", "multi", "array", "rk45", "devices"]
     os.makedirs(GOLD, exist_ok=True)

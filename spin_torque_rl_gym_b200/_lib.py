@@ -110,7 +110,15 @@ class StgRk45Args(C.Structure):
                 ("traj_stride", C.c_int64), ("d_noise", C.c_void_p), ("noise_stride", C.c_int64), ("rtol", C.c_double),
                 ("atol", C.c_double), ("max_step", C.c_double), ("max_attempts", C.c_int64), ("seed", C.c_uint64),
                 ("env_offset", C.c_uint64), ("n_envs", C.c_int64), ("n_sets", C.c_int32), ("flags", C.c_uint32),
-                ("d_perm", C.c_void_p)]
+                ("d_perm", C.c_void_p), ("d_t_start", C.c_void_p), ("d_seg_t", C.c_void_p), ("d_seg_current", C.c_void_p),
+                ("d_seg_field", C.c_void_p), ("n_seg", C.c_int32), ("seg_rows", C.c_int32)]
+
+
+class StgThermalAnalyticsArgs(C.Structure):
+    _fields_ = [("d_temperature", C.c_void_p), ("d_ku", C.c_void_p), ("d_volume", C.c_void_p), ("d_damping", C.c_void_p),
+                ("d_ms", C.c_void_p), ("d_barrier", C.c_void_p), ("d_out", C.c_void_p), ("k_b", C.c_double),
+                ("mu0", C.c_double), ("gamma", C.c_double), ("attempt_frequency", C.c_double),
+                ("measurement_time", C.c_double), ("failure_rate", C.c_double), ("n_t", C.c_int32), ("n_dev", C.c_int32)]
 
 
 ARRAY_MODES = {"individual": 0, "row": 1, "column": 2, "global": 3}
@@ -163,6 +171,7 @@ SYMBOLS = {
     "stg_device_sot_torque_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_int32, C.c_void_p,
                                             C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "stg_vcma_anisotropy_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "stg_thermal_analytics_f64": (C.c_int, [C.POINTER(StgThermalAnalyticsArgs), C.c_void_p]),
     "stg_thermal_field_f64": (C.c_int, [C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                                         C.c_uint64, C.c_int64, C.c_void_p]),
     "stg_energy_landscape_f64": (C.c_int, [C.POINTER(StgEnergyParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
@@ -178,7 +187,7 @@ SYMBOLS = {
     "stg_probe_fma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
-ABI_VERSION = 6          # include/stg.h STG_ABI_VERSION (2: sampled current / field grids; 3: replicated statistics buffer;
+ABI_VERSION = 7          # include/stg.h STG_ABI_VERSION (2: sampled current / field grids; 3: replicated statistics buffer;
                          # 4: zero-row counters of stg_device_field_f64 / stg_device_resistance_f64; 5: StgRk45Args.d_perm;
                          # 6: StgSttStepArgs.d_redo, status bit 2)
 _LIB: Optional[C.CDLL] = None

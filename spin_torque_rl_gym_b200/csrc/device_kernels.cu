@@ -108,6 +108,34 @@ __global__ void __launch_bounds__(256) thermal_field_kernel(double strength, dou
     out[3 * i] = strength * x; out[3 * i + 1] = strength * y; out[3 * i + 2] = strength * z;
 }
 
+// Neel-Brown analytics of ThermalFluctuations (physics/thermal_model.py:46-73, 139-258) on a (temperature x device) grid: one
+// thread per grid point, four output planes [n_t][n_dev] - thermal stability factor K_u V / k_B T, switching probability
+// 1 - exp(-f0 exp(-E / k_B T) t_m) (capped at 1), retention time -ln(failure_rate) / (f0 exp(-E / k_B T)) in seconds, noise
+// strength sqrt(2 alpha k_B T / (gamma mu0 Ms V)) - with the reference's T <= 0 conventions (inf, 0, inf, 0).
+__global__ void __launch_bounds__(256) thermal_analytics_kernel(const __grid_constant__ StgThermalAnalyticsArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = (int64_t)a.n_t * a.n_dev;
+    if (i >= n) return;
+    const int64_t it = i / a.n_dev, id = i - it * a.n_dev;
+    const double T = a.d_temperature[it];
+    const double ku = a.d_ku[id], vol = a.d_volume[id];
+    const double barrier = a.d_barrier ? a.d_barrier[id] : ku * vol;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double delta = inf, prob = 0.0, ret = inf, noise = 0.0;
+    if (T > 0.0) {
+        const double kt = a.k_b * T;
+        delta = ku * vol / kt;
+        const double rate = a.attempt_frequency * exp(-barrier / kt);
+        prob = fmin(1.0 - exp(-rate * a.measurement_time), 1.0);
+        if (a.failure_rate > 0.0) ret = -log(a.failure_rate) / (a.attempt_frequency * exp(-(barrier / kt)));
+        noise = sqrt(2.0 * a.d_damping[id] * a.k_b * T / (a.gamma * a.mu0 * a.d_ms[id] * vol));
+    }
+    a.d_out[i] = delta;
+    a.d_out[n + i] = prob;
+    a.d_out[2 * n + i] = ret;
+    a.d_out[3 * n + i] = noise;
+}
+
 // EnergyLandscape.compute_energy / compute_energy_gradient (physics/energy_landscape.py:36-104) for n states
 __global__ void __launch_bounds__(256) energy_landscape_kernel(const __grid_constant__ StgEnergyParams p, const double* m,
                                                                const double* happ, int happ_rows, double* energy,
@@ -248,6 +276,17 @@ extern "C" int stg_thermal_field_f64(double strength, double decay, double* d_st
     if (n == 0) return STG_OK;
     thermal_field_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(strength, decay, d_state, d_out, seed, offset,
                                                                         call_index, n);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int stg_thermal_analytics_f64(const StgThermalAnalyticsArgs* args, void* stream) {
+    if (!args) return STG_E_NULL;
+    const StgThermalAnalyticsArgs& a = *args;
+    if (!a.d_temperature || !a.d_ku || !a.d_volume || !a.d_damping || !a.d_ms || !a.d_out) return STG_E_NULL;
+    if (a.n_t < 0 || a.n_dev < 0) return STG_E_SIZE;
+    const int64_t n = (int64_t)a.n_t * a.n_dev;
+    if (n == 0) return STG_OK;
+    thermal_analytics_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }
 

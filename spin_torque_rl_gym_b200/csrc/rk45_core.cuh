@@ -53,6 +53,20 @@ struct LlgRhs {
     double hk;          // 2 K_eff /(mu0 Ms)
     double J, t_pulse;
     V3 happ;
+    // piecewise-constant current_func / field_func (StgRk45Args.d_seg_*): n_seg == 0 -> rectangular pulse + constant field
+    const double *seg_t, *seg_j, *seg_h;
+    int n_seg;
+    STG_HD void controls(double t, double& cur, V3& h) const {
+        if (n_seg == 0) {
+            cur = (t <= t_pulse) ? J : 0.0;
+            h = happ;
+            return;
+        }
+        int k = 0;
+        while (k < n_seg && t > seg_t[k]) ++k;
+        cur = seg_j[k];
+        h = seg_h ? V3{seg_h[3 * k], seg_h[3 * k + 1], seg_h[3 * k + 2]} : happ;
+    }
     // thermal
     int noise_mode;     // 0 none, 1 Philox, 2 injected
     Philox ph;
@@ -73,10 +87,12 @@ struct LlgRhs {
 #endif
             m.x = y.x * inv; m.y = y.y * inv; m.z = y.z * inv;
         }
-        const double cur = (t <= t_pulse) ? J : 0.0;
+        double cur;
+        V3 ha;
+        controls(t, cur, ha);
         const V3 e = {ex, ey, ez};
         const double s = hk * dot3(m, e);
-        V3 h = {happ.x + s * e.x, happ.y + s * e.y, happ.z + s * e.z};
+        V3 h = {ha.x + s * e.x, ha.y + s * e.y, ha.z + s * e.z};
         h.x += msnx * m.x;                                    // -Ms N (.) m
         h.y += msny * m.y;
         h.z += msnz * m.z;
@@ -119,14 +135,16 @@ struct LlgRhs {
         const StgLlgParams& q = *p;
         const V3 e = {q.easy_axis[0], q.easy_axis[1], q.easy_axis[2]};
         const double msv = q.saturation_magnetization * q.volume;
-        const double ez = -q.mu0 * msv * dot3(m, happ);
+        double cur;
+        V3 ha;
+        controls(t, cur, ha);
+        const double ez = -q.mu0 * msv * dot3(m, ha);
         const double c = dot3(m, e);
         const double ku = hk * q.mu0 * q.saturation_magnetization * 0.5;
         const double ea = -ku * q.volume * c * c;
         const double ed = 0.5 * q.mu0 * q.saturation_magnetization * msv *
                           (q.demag_n[0] * m.x * m.x + q.demag_n[1] * m.y * m.y + q.demag_n[2] * m.z * m.z);
         energy = ez + ea + ed;
-        const double cur = (t <= t_pulse) ? J : 0.0;
         torque = 0.0;
         if (!(fabs(cur) < 1e-12)) {
             const V3 ph3 = {q.p_hat[0], q.p_hat[1], q.p_hat[2]};
@@ -141,9 +159,11 @@ struct LlgRhs {
     }
 };
 
-STG_HD double ulp_above(double t) {   // |nextafter(t, +inf) - t| for t >= 0 (the integration always runs forward from 0)
+STG_HD double ulp_above(double t) {   // |nextafter(t, +inf) - t| (the integration always runs forward)
 #if defined(__CUDA_ARCH__)
-    return __longlong_as_double(__double_as_longlong(t) + 1LL) - t;
+    if (t > 0.0) return __longlong_as_double(__double_as_longlong(t) + 1LL) - t;
+    if (t < 0.0) return __longlong_as_double(__double_as_longlong(t) - 1LL) - t;
+    return 4.9406564584124654e-324;
 #else
     return nextafter(t, (double)INFINITY) - t;
 #endif
@@ -201,8 +221,15 @@ STG_HD void rk45_init(const StgRk45Args& a, int64_t e, Rk45State& S) {
     f.noise_row = a.d_noise ? a.d_noise + (int64_t)e * a.noise_stride * 3 : nullptr;
     f.noise_cap = a.noise_stride;
     f.n_eval = 0;
+    f.n_seg = a.n_seg > 0 && a.d_seg_t && a.d_seg_current ? a.n_seg : 0;
+    {
+        const int64_t row = a.seg_rows > 1 ? e : 0;
+        f.seg_t = f.n_seg ? a.d_seg_t + row * a.n_seg : nullptr;
+        f.seg_j = f.n_seg ? a.d_seg_current + row * (a.n_seg + 1) : nullptr;
+        f.seg_h = (f.n_seg && a.d_seg_field) ? a.d_seg_field + row * (a.n_seg + 1) * 3 : nullptr;
+    }
 
-    const double t0 = 0.0;
+    const double t0 = a.d_t_start ? a.d_t_start[e] : 0.0;
     S.e = e;
     S.tb = a.d_t_end[e];
     const double rtol = a.rtol, atol = a.atol, max_step = a.max_step;

@@ -36,6 +36,8 @@ extern "C" int stg_llgs_rk45_f64(const StgRk45Args* args, void* stream) {
     if ((a.flags & STG_F_THERMAL_PHILOX) && (a.flags & STG_F_THERMAL_INJECT)) return STG_E_ENUM;
     if ((a.flags & STG_F_THERMAL_INJECT) && (!a.d_noise || a.noise_stride <= 0)) return STG_E_NULL;
     if (a.d_traj && a.traj_stride <= 0) return STG_E_SIZE;
+    if (a.n_seg < 0 || (a.n_seg > 0 && (!a.d_seg_t || !a.d_seg_current || (a.seg_rows != 1 && a.seg_rows != a.n_envs))))
+        return a.n_seg < 0 ? STG_E_SIZE : (!a.d_seg_t || !a.d_seg_current ? STG_E_NULL : STG_E_SIZE);
     if (a.n_envs == 0) return STG_OK;
     const int64_t ctas = (a.n_envs + 63) / 64;
     stg::llgs_rk45_kernel<<<(unsigned)ctas, 64, 0, (cudaStream_t)stream>>>(a);

@@ -1,9 +1,11 @@
 """Batched LLGSSolver (reference: physics/llgs_solver.py:20-305) on the K2 adaptive-RK45 CUDA kernel.
 
 `solve()` keeps the reference signature for one trajectory and returns the same dict ('t', 'm', 'energy', 'torques', 'success');
-`solve_batch()` integrates N trajectories in one launch. Python callables cannot cross into a kernel: current_func must be a
-rectangular pulse, given as a number, a (J, t_pulse) tuple, or a callable that is sampled to recover (J, t_pulse) and verified
-to be rectangular; field_func must be constant in time."""
+`solve_batch()` integrates N trajectories in one launch. Python callables cannot cross into a kernel and an adaptive controller
+evaluates them at data-dependent times, so current_func / field_func must be PIECEWISE CONSTANT in time: a number / vector, a
+(J, t_pulse) tuple, a `PiecewiseConstant` table, or any callable that turns out to be piecewise constant on the time span (its
+break points are located by bisection to adjacent doubles and the table is evaluated inside the kernel). Anything else - a
+ramp, a sine - raises ValueError instead of being approximated."""
 from __future__ import annotations
 
 import ctypes as C
@@ -13,28 +15,93 @@ import numpy as np
 
 from .. import _lib, params as _params
 
+_MAX_SEGMENTS = 64
+
+
+class PiecewiseConstant:
+    """f(t) = values[k] for breaks[k-1] < t <= breaks[k] (right-closed like the env's `J if t <= t_pulse else 0`), values[-1]
+    after the last break. Callable, so the same object drives the reference's LLGSSolver.solve."""
+
+    def __init__(self, breaks: Sequence[float], values: Sequence[Any]):
+        self.breaks = np.asarray(breaks, dtype=np.float64).reshape(-1)
+        self.values = np.asarray(values, dtype=np.float64)
+        if self.values.shape[0] != self.breaks.size + 1:
+            raise ValueError("PiecewiseConstant needs len(values) == len(breaks) + 1")
+        if np.any(np.diff(self.breaks) <= 0):
+            raise ValueError("PiecewiseConstant breaks must be strictly ascending")
+
+    def __call__(self, t: float):
+        k = int(np.searchsorted(self.breaks, t, side="left"))       # first break >= t
+        v = self.values[k]
+        return float(v) if v.ndim == 0 else v.copy()
+
+
+def _table_from_callable(fn: Callable[[float], Any], t0: float, t1: float, what: str) -> PiecewiseConstant:
+    """Recover the break points of a piecewise-constant callable on [t0, t1]; ValueError if it is not one."""
+    ts = np.linspace(t0, t1, 1025)
+    vals = [np.asarray(fn(float(t)), dtype=np.float64) for t in ts]
+    change = [i for i in range(1, len(ts)) if not np.array_equal(vals[i], vals[i - 1])]
+    if len(change) > _MAX_SEGMENTS:
+        raise ValueError(f"{what} is not piecewise constant in time (more than {_MAX_SEGMENTS} changes on the time span): an "
+                         "adaptive solver evaluates it at data-dependent times, which a CUDA kernel cannot do for a Python callable")
+    breaks, values = [], [vals[0]]
+    for i in change:
+        lo, hi = float(ts[i - 1]), float(ts[i])
+        v_lo = vals[i - 1]
+        while True:                                   # last time with the left value, to adjacent doubles
+            mid = 0.5 * (lo + hi)
+            if mid <= lo or mid >= hi:
+                break
+            if np.array_equal(np.asarray(fn(mid), dtype=np.float64), v_lo):
+                lo = mid
+            else:
+                hi = mid
+        if not np.array_equal(np.asarray(fn(hi), dtype=np.float64), vals[i]):
+            raise ValueError(f"{what} changes more than once between two sample times: not representable as a table")
+        breaks.append(lo)
+        values.append(vals[i])
+    table = PiecewiseConstant(breaks, np.array(values))
+    rng = np.random.default_rng(0)
+    edges = [t0] + breaks + [t1]
+    for k in range(len(edges) - 1):                   # constant inside every segment?
+        for t in rng.uniform(edges[k], edges[k + 1], 4):
+            if np.nextafter(edges[k], np.inf) < t <= edges[k + 1] and not np.array_equal(
+                    np.asarray(fn(float(t)), dtype=np.float64), np.asarray(table(float(t)), dtype=np.float64)):
+                raise ValueError(f"{what} varies inside a segment: not piecewise constant in time")
+    return table
+
+
+def _as_table(x, t0: float, t1: float, what: str, vector: bool) -> PiecewiseConstant:
+    if x is None:
+        return PiecewiseConstant([], np.zeros((1, 3)) if vector else np.zeros(1))
+    if isinstance(x, PiecewiseConstant):
+        return x
+    if callable(x):
+        return _table_from_callable(x, t0, t1, what)
+    if not vector and isinstance(x, (tuple, list)) and len(x) == 2:
+        return PiecewiseConstant([float(x[1])], [float(x[0]), 0.0])          # (J, t_pulse)
+    v = np.asarray(x, dtype=np.float64)
+    return PiecewiseConstant([], v.reshape(1, 3) if vector else v.reshape(1))
+
 
 def _pulse_from_callable(fn: Callable[[float], float], t_end: float) -> Tuple[float, float]:
-    """Recover (J, t_pulse) of current_func(t) = J if t <= t_pulse else 0 by bisection; reject anything else."""
-    ts = np.linspace(0.0, t_end, 257)
-    vals = np.array([float(fn(float(t))) for t in ts])
-    j = vals[0]
-    on = vals == j
-    if on.all():
+    """(J, t_pulse) of current_func(t) = J if t <= t_pulse else 0 (physics/simple_solver.py mirror); ValueError for anything else."""
+    tab = _table_from_callable(fn, 0.0, t_end, "current_func")
+    if tab.breaks.size == 0:
+        j = float(tab.values[0])
         return j, float("inf") if j != 0.0 else 0.0
-    k = int(np.argmin(on))
-    if not on[:k].all() or np.any(vals[k:] != 0.0):
+    if tab.breaks.size != 1 or float(tab.values[1]) != 0.0:
         raise ValueError("current_func must be a rectangular pulse (J while t <= t_pulse, 0 afterwards) for the CUDA solver")
-    lo, hi = float(ts[k - 1]), float(ts[k])
-    for _ in range(200):
-        mid = 0.5 * (lo + hi)
-        if mid == lo or mid == hi:
-            break
-        if float(fn(mid)) == j:
-            lo = mid
-        else:
-            hi = mid
-    return j, lo
+    return float(tab.values[0]), float(tab.breaks[0])
+
+
+def _merge_tables(cur: PiecewiseConstant, fld: PiecewiseConstant):
+    """Common break points of the two tables -> (ends [K], current [K+1], field [K+1, 3])."""
+    ends = np.union1d(cur.breaks, fld.breaks)
+    probe = np.concatenate([ends, [np.inf]])          # a time inside every segment: its (closed) right end
+    j = np.array([float(cur(t)) if np.isfinite(t) else float(cur.values[-1]) for t in probe])
+    h = np.array([np.asarray(fld(t)) if np.isfinite(t) else fld.values[-1] for t in probe]).reshape(-1, 3)
+    return ends, j, h
 
 
 class LLGSSolver:
@@ -44,7 +111,8 @@ class LLGSSolver:
         t_end descending) so the lanes of a warp integrate trajectories of similar length (StgRk45Args.d_perm; results are
         identical, inputs and outputs are not moved)."""
         if method != "RK45":
-            raise ValueError("only method='RK45' (SciPy's default Dormand-Prince pair) is implemented on the GPU")
+            raise ValueError("only method='RK45' (SciPy's default Dormand-Prince pair, the reference's default) is implemented on "
+                             "the GPU; RK23 / DOP853 / Radau / BDF / LSODA are not")
         torch = _lib.require_cuda()
         self.method, self.rtol, self.atol, self.max_step, self.gamma = method, rtol, atol, max_step, gamma
         self.mu_0 = 4 * np.pi * 1e-7
@@ -59,8 +127,11 @@ class LLGSSolver:
                     t_pulse=None, applied_field=None, voltage=None, thermal_noise: bool = False,
                     temperature: float = 300.0, param_index=None, device_type=None, current_direction=None,
                     return_trajectory: bool = False, max_traj_rows: Optional[int] = None, noise=None,
-                    seed: int = 0, env_offset: int = 0) -> Dict[str, Any]:
-        """N trajectories of LLGSSolver.solve in one launch. Arrays may be NumPy or torch; outputs are CUDA tensors."""
+                    seed: int = 0, env_offset: int = 0, t_start=None, segments=None) -> Dict[str, Any]:
+        """N trajectories of LLGSSolver.solve in one launch. Arrays may be NumPy or torch; outputs are CUDA tensors.
+        `t_start`: [N] or scalar start times (default 0; t_end is absolute). `segments`: piecewise-constant controls
+        (ends [K] or [N,K], current [K+1] or [N,K+1], field [K+1,3] or [N,K+1,3] or None) replacing current / t_pulse / applied_field
+        (include/stg.h StgRk45Args.d_seg_*)."""
         torch = _lib.require_cuda()
         dev, f64 = self._device, torch.float64
 
@@ -105,6 +176,24 @@ class LLGSSolver:
             t = arr(val, shape)
             keep.append(t)
             setattr(a, name, _lib.ptr(t))
+        t_start_t = arr(t_start, (n,))
+        keep.append(t_start_t)
+        a.d_t_start = _lib.ptr(t_start_t)
+        if segments is not None:
+            ends, seg_j, seg_h = segments
+            ends = torch.as_tensor(np.asarray(ends, dtype=np.float64)).to(dev)
+            per_env = ends.dim() == 2
+            k = ends.shape[-1]
+            if k > 0:
+                rows = n if per_env else 1
+                ends = ends.reshape(rows, k).contiguous()
+                seg_j = torch.as_tensor(np.asarray(seg_j, dtype=np.float64)).to(dev).reshape(rows, k + 1).contiguous()
+                keep += [ends, seg_j]
+                a.d_seg_t, a.d_seg_current, a.n_seg, a.seg_rows = ends.data_ptr(), seg_j.data_ptr(), k, rows
+                if seg_h is not None:
+                    seg_h = torch.as_tensor(np.asarray(seg_h, dtype=np.float64)).to(dev).reshape(rows, k + 1, 3).contiguous()
+                    keep.append(seg_h)
+                    a.d_seg_field = seg_h.data_ptr()
         out = {
             "y": torch.empty(n, 3, dtype=f64, device=dev),
             "n_accepted": torch.zeros(n, dtype=torch.int32, device=dev),
@@ -117,7 +206,7 @@ class LLGSSolver:
         a.d_n_rhs, a.d_status, a.d_t_reached = out["n_rhs"].data_ptr(), out["status"].data_ptr(), out["t_reached"].data_ptr()
         if return_trajectory:
             if max_traj_rows is None:
-                tmax = float(t_end_t.max())
+                tmax = float((t_end_t - t_start_t).max()) if t_start_t is not None else float(t_end_t.max())
                 max_traj_rows = int(2.5 * tmax / self.max_step) + 64
             out["traj"] = torch.zeros(n, max_traj_rows, 6, dtype=f64, device=dev)
             a.d_traj, a.traj_stride = out["traj"].data_ptr(), max_traj_rows
@@ -146,25 +235,25 @@ class LLGSSolver:
               current_func: Union[Callable[[float], float], float, Tuple[float, float]],
               field_func: Optional[Callable[[float], np.ndarray]] = None, thermal_noise: bool = True,
               temperature: float = 300.0, seed: int = 0) -> Dict[str, np.ndarray]:
-        """Reference signature, one trajectory (physics/llgs_solver.py:51-180)."""
+        """Reference signature, one trajectory (physics/llgs_solver.py:51-180). current_func / field_func: see the module
+        docstring (piecewise constant in time, or ValueError)."""
         t0, t1 = float(time_span[0]), float(time_span[1])
-        if t0 != 0.0:
-            raise ValueError("time_span must start at 0 (the pulse and field are defined relative to the step start)")
-        if callable(current_func):
-            j, tp = _pulse_from_callable(current_func, t1)
-        elif isinstance(current_func, (tuple, list)):
-            j, tp = float(current_func[0]), float(current_func[1])
+        if not t1 > t0:
+            raise ValueError("time_span must run forward (t_end > t_start)")
+        cur = _as_table(current_func, t0, t1, "current_func", vector=False)
+        fld = _as_table(field_func, t0, t1, "field_func", vector=True)
+        if fld.values.ndim != 2 or fld.values.shape[1] != 3:
+            raise ValueError("field_func must return a 3-vector")
+        ends, seg_j, seg_h = _merge_tables(cur, fld)
+        kw: Dict[str, Any] = {}
+        if ends.size == 0:
+            kw = dict(current=np.array([seg_j[0]]), applied_field=seg_h[:1])
+        elif ends.size == 1 and seg_j[1] == 0.0 and np.array_equal(seg_h[0], seg_h[1]):
+            kw = dict(current=np.array([seg_j[0]]), t_pulse=np.array([min(ends[0], 1.0e300)]), applied_field=seg_h[:1])
         else:
-            j, tp = float(current_func), float("inf")
-        happ = np.zeros(3)
-        if field_func is not None:
-            happ = np.asarray(field_func(0.0), dtype=float)
-            if not np.array_equal(happ, np.asarray(field_func(t1), dtype=float)):
-                raise ValueError("field_func must be constant in time for the CUDA solver")
-        tp = min(tp, 1.0e300)
-        r = self.solve_batch(np.asarray(m_initial, dtype=float)[None], np.array([t1]), device_params, current=np.array([j]),
-                             t_pulse=np.array([tp]), applied_field=happ[None], thermal_noise=thermal_noise,
-                             temperature=temperature, return_trajectory=True, seed=seed)
+            kw = dict(segments=(ends, seg_j, seg_h))
+        r = self.solve_batch(np.asarray(m_initial, dtype=float)[None], np.array([t1]), device_params, t_start=np.array([t0]),
+                             thermal_noise=thermal_noise, temperature=temperature, return_trajectory=True, seed=seed, **kw)
         rows = int(r["n_accepted"][0]) + 1
         traj = r["traj"][0, :rows].cpu().numpy()
         status = int(r["status"][0])
@@ -176,11 +265,12 @@ class LLGSSolver:
     def find_stable_states(self, device_params: Dict[str, Any], n_trials: int = 100, threshold: float = 1e-6,
                            relax_time: float = 10e-9, seed: Optional[int] = None) -> np.ndarray:
         """Relax `n_trials` random starts for 10 ns without current / field / noise in ONE launch and return the distinct end
-        states (physics/llgs_solver.py:264-305)."""
-        rng = np.random.default_rng(seed)
-        m0 = rng.normal(0, 1, (n_trials, 3))
+        states (physics/llgs_solver.py:264-305). The starts come from NumPy's legacy stream like the reference's
+        (`np.random.normal(0, 1, 3)` per trial: the global stream when `seed` is None, RandomState(seed) otherwise)."""
+        rs = np.random if seed is None else np.random.RandomState(seed)
+        m0 = np.array([rs.normal(0, 1, 3) for _ in range(n_trials)])
         m0 /= np.linalg.norm(m0, axis=1, keepdims=True)
-        r = self.solve_batch(m0, relax_time, device_params, current=0.0, thermal_noise=False)
+        r = self.solve_batch(m0, relax_time, device_params, current=0.0, thermal_noise=False, return_trajectory=False)
         ok = r["success"].cpu().numpy()
         finals = r["m"].cpu().numpy()[ok]
         stable = []

@@ -30,7 +30,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True).stdout
     for name in declared:
         assert re.search(rf"\bT {name}\b", out), name
-    assert lib.stg_abi_version() == _lib.ABI_VERSION == 6
+    assert lib.stg_abi_version() == _lib.ABI_VERSION == 7
 
 
 def test_struct_layouts_match_the_c_header(tmp_path):
@@ -46,6 +46,9 @@ def test_struct_layouts_match_the_c_header(tmp_path):
         "StgSttStepOut": ["obs", "reward", "status", "final_obs", "stats"],
         "StgSttState": ["m", "episode"],
         "StgSttFolded": ["v"],
+        "StgRk45Args": ["d_table", "d_t_end", "d_traj", "traj_stride", "rtol", "max_attempts", "n_envs", "flags", "d_perm",
+                        "d_t_start", "d_seg_t", "d_seg_current", "d_seg_field", "n_seg", "seg_rows"],
+        "StgThermalAnalyticsArgs": ["d_temperature", "d_barrier", "d_out", "k_b", "failure_rate", "n_t", "n_dev"],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for s, fs in fields.items():
