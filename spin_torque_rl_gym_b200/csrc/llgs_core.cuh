@@ -284,6 +284,12 @@ STG_HD void stage_general(const StepConsts<R>& c, R mx, R my, R mz, R aH, R aL, 
     }
 }
 
+// explicit FP64 products / sums / fused multiply-adds: the compiler may not contract or split them, so the same env gets the same
+// bits from every kernel and from either half of a two-envs-per-thread pack (definitions below)
+STG_HD double dmul(double a, double b);
+STG_HD double dadd(double a, double b);
+STG_HD double dfma(double a, double b, double c) { return fma(a, b, c); }
+
 // reciprocal norm of an FP64 vector whose norm^2 is n2
 template <typename R>
 STG_HD double inv_norm(double n2);
@@ -299,8 +305,8 @@ STG_HD double inv_norm<float>(double n2) {
 #else
     double y = (double)(1.0f / sqrtf((float)n2));
 #endif
-    y = y * (1.5 - 0.5 * n2 * y * y);
-    return y * (1.5 - 0.5 * n2 * y * y);
+    y = dmul(y, dfma(-0.5, dmul(dmul(n2, y), y), 1.5));
+    return dmul(y, dfma(-0.5, dmul(dmul(n2, y), y), 1.5));
 }
 
 // ---- block-scaled state ----------------------------------------------------------------------------------------------------
@@ -363,7 +369,7 @@ STG_HD void rescale(ScaledState& st) {
 // Guard + normalise of the FP64 master (physics/simple_solver.py:208-229): non-finite or |m| < 1e-12 -> (0,0,1) + guard flag.
 template <typename R>
 STG_HD void guard_normalise(ScaledState& st, int& guard) {
-    const double n2 = st.z * st.z + (st.sx * st.sx + st.sy * st.sy) * st.inv_s2d;
+    const double n2 = dfma(st.z, st.z, dmul(dfma(st.sx, st.sx, dmul(st.sy, st.sy)), st.inv_s2d));
     if (n2 >= 1e-24 && n2 <= 1.0e300) {
         const double inv = inv_norm<R>(n2);
         st.sx *= inv; st.sy *= inv; st.z *= inv;
@@ -831,16 +837,18 @@ STG_HD float fast_ex2(float x) {
 // c, ac, a: the per-substep constants of the stages (already divided by 6); z: current m_z; s: current transverse magnitude
 // sin(theta); nb: substeps in the block
 STG_HD void cond_block(CondTrack& t, float c, float ac, float a, float z, float s, float nb) {
-    const float ac6 = 6.0f * ac, a6 = 6.0f * a;
+    // every product / sum explicit: the flag must not depend on which kernel or pack half evaluates the env
+    using K = Pk<float>;
+    const float ac6 = K::mul(6.0f, ac), a6 = K::mul(6.0f, a);
     s = fminf(s, 1.0f);
-    const float lam = fmaf(z, fmaf(ac6, z, a6), -ac6 * s * s);
-    const float g = fast_ex2(fminf(nb * lam * 1.4426950408889634f, 80.0f));
-    const float eps = 5.9604645e-8f * (fabsf(ac6) + fabsf(a6) + 0.06f * fabsf(c));
-    t.A = fmaf(t.A, g, nb * eps * s * fmaxf(1.0f, g));
-    t.Phi = fmaf(nb * fabsf(6.0f * c) * s, t.A, t.Phi);
+    const float lam = fmaf(z, fmaf(ac6, z, a6), K::mul(K::mul(-ac6, s), s));
+    const float g = fast_ex2(fminf(K::mul(K::mul(nb, lam), 1.4426950408889634f), 80.0f));
+    const float eps = K::mul(5.9604645e-8f, fmaf(0.06f, fabsf(c), K::add(fabsf(ac6), fabsf(a6))));
+    t.A = fmaf(t.A, g, K::mul(K::mul(K::mul(nb, eps), s), fmaxf(1.0f, g)));
+    t.Phi = fmaf(K::mul(K::mul(nb, fabsf(K::mul(6.0f, c))), s), t.A, t.Phi);
 }
 STG_HD float transverse_of(float fx, float fy, float inv_s) {      // sin(theta) from the (block-scaled) FP32 working copy
-    return fast_sqrt(fmaf(fx, fx, fy * fy)) * inv_s;
+    return Pk<float>::mul(fast_sqrt(fmaf(fx, fx, Pk<float>::mul(fy, fy))), inv_s);
 }
 STG_HD bool cond_exceeded(const CondTrack& t, float s_end) {
     return !(fmaf(fminf(s_end, 1.0f), t.Phi, t.A) <= STG_COND_TOL);        // NaN counts as exceeded

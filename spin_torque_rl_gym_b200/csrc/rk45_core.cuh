@@ -53,19 +53,27 @@ struct LlgRhs {
     double hk;          // 2 K_eff /(mu0 Ms)
     double J, t_pulse;
     V3 happ;
-    // piecewise-constant current_func / field_func (StgRk45Args.d_seg_*): n_seg == 0 -> rectangular pulse + constant field
-    const double *seg_t, *seg_j, *seg_h;
-    int n_seg;
-    STG_HD void controls(double t, double& cur, V3& h) const {
-        if (n_seg == 0) {
+    // current_func(t), field_func(t): rectangular pulse + constant field, or the piecewise-constant tables of the argument block
+    // (StgRk45Args.d_seg_*; read through the kernel parameter, so they cost the trajectory no registers)
+    // SEG: compile-time switch, so that the rectangular-pulse instantiation carries no trace of the tables
+    template <bool SEG>
+    STG_HD void controls(const StgRk45Args& a, int64_t e, double t, double& cur, V3& h) const {
+        if constexpr (!SEG) {
             cur = (t <= t_pulse) ? J : 0.0;
             h = happ;
             return;
         }
+        const int64_t row = a.seg_rows > 1 ? e : 0;
+        const double* st = a.d_seg_t + row * a.n_seg;
         int k = 0;
-        while (k < n_seg && t > seg_t[k]) ++k;
-        cur = seg_j[k];
-        h = seg_h ? V3{seg_h[3 * k], seg_h[3 * k + 1], seg_h[3 * k + 2]} : happ;
+        while (k < a.n_seg && t > st[k]) ++k;
+        cur = a.d_seg_current[row * (a.n_seg + 1) + k];
+        if (a.d_seg_field) {
+            const double* sh = a.d_seg_field + (row * (a.n_seg + 1) + k) * 3;
+            h = V3{sh[0], sh[1], sh[2]};
+        } else {
+            h = happ;
+        }
     }
     // thermal
     int noise_mode;     // 0 none, 1 Philox, 2 injected
@@ -76,7 +84,8 @@ struct LlgRhs {
     int n_eval;
 
     // llgs_rhs (physics/llgs_solver.py:92-126) generalised with the SOT terms (devices/sot_mram.py:163-194)
-    STG_HD V3 operator()(double t, V3 y) {
+    template <bool SEG>
+    STG_HD V3 eval(const StgRk45Args& a, int64_t e, double t, V3 y) {
         V3 m = {0.0, 0.0, 1.0};                               // :96-101 (y * (1/|y|): <= 1 ulp from NumPy's y / |y|)
         const double n2 = dot3(y, y);
         if (n2 > 1e-24) {
@@ -89,10 +98,10 @@ struct LlgRhs {
         }
         double cur;
         V3 ha;
-        controls(t, cur, ha);
-        const V3 e = {ex, ey, ez};
-        const double s = hk * dot3(m, e);
-        V3 h = {ha.x + s * e.x, ha.y + s * e.y, ha.z + s * e.z};
+        controls<SEG>(a, e, t, cur, ha);
+        const V3 ea = {ex, ey, ez};
+        const double s = hk * dot3(m, ea);
+        V3 h = {ha.x + s * ea.x, ha.y + s * ea.y, ha.z + s * ea.z};
         h.x += msnx * m.x;                                    // -Ms N (.) m
         h.y += msny * m.y;
         h.z += msnz * m.z;
@@ -131,13 +140,14 @@ struct LlgRhs {
     }
 
     // _compute_energy (physics/llgs_solver.py:239-262) and the torque norm of :168-172 for a NORMALISED m
-    STG_HD void diagnostics(double t, V3 m, double& energy, double& torque) const {
+    template <bool SEG>
+    STG_HD void diagnostics(const StgRk45Args& a, int64_t env, double t, V3 m, double& energy, double& torque) const {
         const StgLlgParams& q = *p;
         const V3 e = {q.easy_axis[0], q.easy_axis[1], q.easy_axis[2]};
         const double msv = q.saturation_magnetization * q.volume;
         double cur;
         V3 ha;
-        controls(t, cur, ha);
+        controls<SEG>(a, env, t, cur, ha);
         const double ez = -q.mu0 * msv * dot3(m, ha);
         const double c = dot3(m, e);
         const double ku = hk * q.mu0 * q.saturation_magnetization * 0.5;
@@ -188,17 +198,19 @@ struct Rk45State {
     STG_HD bool running() const { return t != tb && status == 0; }
 };
 
+template <bool SEG>
 STG_HD void rk45_record(const StgRk45Args& a, Rk45State& S, int row, double tt, V3 yy) {
     if (!S.traj) return;
     if (row >= a.traj_stride) { S.overflow = 2; return; }   // keeps integrating; only the recording stops
     const double n = sqrt(dot3(yy, yy));
     const V3 m = {yy.x / n, yy.y / n, yy.z / n};            // :152-153
     double en, tq;
-    S.f.diagnostics(tt, m, en, tq);
+    S.f.template diagnostics<SEG>(a, S.e, tt, m, en, tq);
     double* r = S.traj + 6 * (int64_t)row;
     r[0] = tt; r[1] = m.x; r[2] = m.y; r[3] = m.z; r[4] = en; r[5] = tq;
 }
 
+template <bool SEG>
 STG_HD void rk45_init(const StgRk45Args& a, int64_t e, Rk45State& S) {
     const StgLlgParams& q = a.d_table[a.d_param_index ? a.d_param_index[e] : 0];
     LlgRhs& f = S.f;
@@ -221,13 +233,6 @@ STG_HD void rk45_init(const StgRk45Args& a, int64_t e, Rk45State& S) {
     f.noise_row = a.d_noise ? a.d_noise + (int64_t)e * a.noise_stride * 3 : nullptr;
     f.noise_cap = a.noise_stride;
     f.n_eval = 0;
-    f.n_seg = a.n_seg > 0 && a.d_seg_t && a.d_seg_current ? a.n_seg : 0;
-    {
-        const int64_t row = a.seg_rows > 1 ? e : 0;
-        f.seg_t = f.n_seg ? a.d_seg_t + row * a.n_seg : nullptr;
-        f.seg_j = f.n_seg ? a.d_seg_current + row * (a.n_seg + 1) : nullptr;
-        f.seg_h = (f.n_seg && a.d_seg_field) ? a.d_seg_field + row * (a.n_seg + 1) * 3 : nullptr;
-    }
 
     const double t0 = a.d_t_start ? a.d_t_start[e] : 0.0;
     S.e = e;
@@ -247,9 +252,9 @@ STG_HD void rk45_init(const StgRk45Args& a, int64_t e, Rk45State& S) {
     S.h_abs = 0.0;
     S.fk = V3{0.0, 0.0, 0.0};
     S.traj = a.d_traj ? a.d_traj + (int64_t)e * a.traj_stride * 6 : nullptr;
-    rk45_record(a, S, 0, S.t, y);
+    rk45_record<SEG>(a, S, 0, S.t, y);
     if (S.tb > t0) {
-        const V3 fk = f(S.t, y);                                // rk.py:94
+        const V3 fk = f.template eval<SEG>(a, e, S.t, y);                          // rk.py:94
         // select_initial_step (common.py:68-133), order = 4
         const double interval = fabs(S.tb - t0);
         const V3 sc = {atol + fabs(y.x) * rtol, atol + fabs(y.y) * rtol, atol + fabs(y.z) * rtol};
@@ -258,7 +263,7 @@ STG_HD void rk45_init(const StgRk45Args& a, int64_t e, Rk45State& S) {
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
         h0 = fmin(h0, interval);
         const V3 y1 = y + h0 * fk;
-        const V3 f1 = f(t0 + h0, y1);
+        const V3 f1 = f.template eval<SEG>(a, e, t0 + h0, y1);
         const double d2 = rms3({(f1.x - fk.x) / sc.x, (f1.y - fk.y) / sc.y, (f1.z - fk.z) / sc.z}) / h0;
         double h1;
         if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
@@ -274,6 +279,7 @@ STG_HD void rk45_init(const StgRk45Args& a, int64_t e, Rk45State& S) {
 // SciPy nests "while not step_accepted" inside the stepping loop; here one flat loop performs one attempt per iteration for
 // every lane that is still integrating, so the lanes of a warp stay converged on the six RHS evaluations whether their previous
 // attempt was accepted or rejected (nested loops make the whole warp pay for every lane's rejection).
+template <bool SEG>
 STG_HD void rk45_attempt(const StgRk45Args& a, Rk45State& S) {
     using T = Rk45Tableau;
     const double rtol = a.rtol, atol = a.atol, max_step = a.max_step;
@@ -297,13 +303,13 @@ STG_HD void rk45_attempt(const StgRk45Args& a, Rk45State& S) {
     S.h_abs = fabs(h);
     // rk_step (rk.py:14-72)
     const V3 k1 = S.fk;
-    const V3 k2 = f(t + T::c2 * h, y + h * (T::a21 * k1));
-    const V3 k3 = f(t + T::c3 * h, y + h * (T::a31 * k1 + T::a32 * k2));
-    const V3 k4 = f(t + T::c4 * h, y + h * (T::a41 * k1 + T::a42 * k2 + T::a43 * k3));
-    const V3 k5 = f(t + T::c5 * h, y + h * (T::a51 * k1 + T::a52 * k2 + T::a53 * k3 + T::a54 * k4));
-    const V3 k6 = f(t + h, y + h * (T::a61 * k1 + T::a62 * k2 + T::a63 * k3 + T::a64 * k4 + T::a65 * k5));
+    const V3 k2 = f.template eval<SEG>(a, S.e, t + T::c2 * h, y + h * (T::a21 * k1));
+    const V3 k3 = f.template eval<SEG>(a, S.e, t + T::c3 * h, y + h * (T::a31 * k1 + T::a32 * k2));
+    const V3 k4 = f.template eval<SEG>(a, S.e, t + T::c4 * h, y + h * (T::a41 * k1 + T::a42 * k2 + T::a43 * k3));
+    const V3 k5 = f.template eval<SEG>(a, S.e, t + T::c5 * h, y + h * (T::a51 * k1 + T::a52 * k2 + T::a53 * k3 + T::a54 * k4));
+    const V3 k6 = f.template eval<SEG>(a, S.e, t + h, y + h * (T::a61 * k1 + T::a62 * k2 + T::a63 * k3 + T::a64 * k4 + T::a65 * k5));
     const V3 y_new = y + h * (T::b1 * k1 + T::b3 * k3 + T::b4 * k4 + T::b5 * k5 + T::b6 * k6);
-    const V3 f_new = f(t + h, y_new);
+    const V3 f_new = f.template eval<SEG>(a, S.e, t + h, y_new);
     const V3 err = h * (T::e1 * k1 + T::e3 * k3 + T::e4 * k4 + T::e5 * k5 + T::e6 * k6 + T::e7 * f_new);
     const V3 mx = vabs_max(y, y_new);
     const double en = rms3({err.x / (atol + mx.x * rtol), err.y / (atol + mx.y * rtol), err.z / (atol + mx.z * rtol)});
@@ -314,7 +320,7 @@ STG_HD void rk45_attempt(const StgRk45Args& a, Rk45State& S) {
         S.t = t_new; S.y = y_new; S.fk = f_new;
         ++S.n_acc;
         S.new_step = true;
-        rk45_record(a, S, S.n_acc, S.t, S.y);
+        rk45_record<SEG>(a, S, S.n_acc, S.t, S.y);
     } else if (en >= 1.0) {
         S.h_abs *= fmax(0.2, 0.9 * pow_m02(en));
         S.rejected = true;
@@ -334,10 +340,11 @@ STG_HD void rk45_finish(const StgRk45Args& a, const Rk45State& S) {
     if (a.d_t_reached) a.d_t_reached[e] = S.t;
 }
 
+template <bool SEG>
 STG_HD void rk45_body(const StgRk45Args& a, int64_t e) {
     Rk45State S;
-    rk45_init(a, e, S);
-    while (S.running()) rk45_attempt(a, S);
+    rk45_init<SEG>(a, e, S);
+    while (S.running()) rk45_attempt<SEG>(a, S);
     rk45_finish(a, S);
 }
 

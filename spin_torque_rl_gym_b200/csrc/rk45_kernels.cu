@@ -17,12 +17,13 @@ namespace stg {
 // The kernel waits on dependent FP64 chains (ncu: `wait` 2.1 stalls per issue at 1.9 warps per scheduler), so warps beat registers.
 #define STG_RK45_MINBLOCKS 8
 #endif
+template <bool SEG>      // SEG: piecewise-constant control tables (StgRk45Args.d_seg_*) instead of pulse + constant field
 __global__ void __launch_bounds__(64, STG_RK45_MINBLOCKS) llgs_rk45_kernel(const __grid_constant__ StgRk45Args a) {
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= a.n_envs) return;
     // d_perm (optional): thread `slot` integrates trajectory perm[slot]. Inputs, outputs and the Philox id stay indexed by the
     // trajectory, so a permutation that sorts by (parameter set, t_end) makes the lanes of a warp homogeneous without moving data.
-    rk45_body(a, a.d_perm ? (int64_t)a.d_perm[slot] : slot);
+    rk45_body<SEG>(a, a.d_perm ? (int64_t)a.d_perm[slot] : slot);
 }
 
 }  // namespace stg
@@ -40,6 +41,7 @@ extern "C" int stg_llgs_rk45_f64(const StgRk45Args* args, void* stream) {
         return a.n_seg < 0 ? STG_E_SIZE : (!a.d_seg_t || !a.d_seg_current ? STG_E_NULL : STG_E_SIZE);
     if (a.n_envs == 0) return STG_OK;
     const int64_t ctas = (a.n_envs + 63) / 64;
-    stg::llgs_rk45_kernel<<<(unsigned)ctas, 64, 0, (cudaStream_t)stream>>>(a);
+    if (a.n_seg > 0) stg::llgs_rk45_kernel<true><<<(unsigned)ctas, 64, 0, (cudaStream_t)stream>>>(a);
+    else stg::llgs_rk45_kernel<false><<<(unsigned)ctas, 64, 0, (cudaStream_t)stream>>>(a);
     return (int)cudaGetLastError();
 }

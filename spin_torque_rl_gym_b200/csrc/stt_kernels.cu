@@ -147,6 +147,9 @@ __device__ __forceinline__ void accumulate_stats(double* v, const EnvStepResult&
 #ifndef STG_PAIR_MINBLOCKS
 #define STG_PAIR_MINBLOCKS 8
 #endif
+#ifndef STG_PAIR_THERMAL_MIN_ENVS
+#define STG_PAIR_THERMAL_MIN_ENVS (1 << 19)
+#endif
 #ifndef STG_PAIR_MINBLOCKS_TH
 #define STG_PAIR_MINBLOCKS_TH 8
 #endif
@@ -564,8 +567,11 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
         return noise == 0 ? launch_redo<0>(a, s) : launch_redo<2>(a, s);
     }
     if (axis_z) {
-        if (sizeof(R) == 4 && noise == 1 && !(a.flags & STG_F_NO_PAIR)) {
-            // two envs per thread on packed FP32x2 arithmetic, one noise stream per lane (bit-identical to one env per thread)
+        if (sizeof(R) == 4 && noise == 1 && !(a.flags & STG_F_NO_PAIR) && a.n_envs >= STG_PAIR_THERMAL_MIN_ENVS) {
+            // two envs per thread on packed FP32x2 arithmetic, one noise stream per lane (bit-identical to one env per thread).
+            // Measured (profiles/README.md, 999 substeps): it only wins when the GPU is many waves deep - 10.40 vs 10.53 ms at
+            // 1,048,576 envs, equal at 524,288 - and loses below (1.59 vs 1.38 ms at 131,072 envs, 0.59 vs 0.31 ms up to 16,384:
+            // half as many threads, each twice as long), so smaller batches take the one-env-per-thread kernel.
 #ifdef STG_THERMAL_WS      // experiment, slower as measured (profiles/README.md): noise produced by separate warps of the CTA
             const unsigned grid = (unsigned)((a.n_envs + kWsEnvs - 1) / kWsEnvs);
             stt_env_step_ws_kernel<<<grid, kWsThreads, 0, s>>>(a);

@@ -151,7 +151,9 @@ extern "C" void hostsim_normals24(uint64_t seed, uint64_t gid, uint32_t episode,
 }
 
 extern "C" int hostsim_llgs_rk45(const StgRk45Args* a) {
-    for (int64_t e = 0; e < a->n_envs; ++e) rk45_body(*a, e);
+    for (int64_t e = 0; e < a->n_envs; ++e) {
+        if (a->n_seg > 0) rk45_body<true>(*a, e); else rk45_body<false>(*a, e);
+    }
     return 0;
 }
 
