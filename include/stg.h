@@ -348,6 +348,12 @@ typedef struct StgRk45Args {
 } StgRk45Args;
 
 int stg_llgs_rk45_f64(const StgRk45Args* args, void* stream);
+/* Estimated attempted steps per trajectory (d_cost [n]), the sort key for d_perm: (t_end - t_start) * max(1 / max_step,
+ * 8 * (gamma |H_eff(m0)| + torque rate)). Reads the inputs of the argument block only. */
+int stg_llgs_rk45_cost_f64(const StgRk45Args* args, double* d_cost, void* stream);
+/* d_perm [n] int32 out: the trajectories counting-sorted by (parameter set, estimated cost descending, 1.5 % bins) - three small
+ * launches; d_work >= STG_SORT_WORK_INTS int32. Pass the result as args->d_perm of stg_llgs_rk45_f64. */
+int stg_llgs_rk45_sort_f64(const StgRk45Args* args, int32_t* d_perm, int32_t* d_work, void* stream);
 
 /* ---- K3: SpinTorqueArray-v0 (envs/array_env.py) ------------------------------------------------------------------------- */
 #define STG_ARRAY_INDIVIDUAL 0

@@ -162,6 +162,8 @@ SYMBOLS = {
     "stg_stt_solve_f32": (C.c_int, [C.POINTER(StgSttSolveArgs), C.c_void_p]),
     "stg_stt_solve_f64": (C.c_int, [C.POINTER(StgSttSolveArgs), C.c_void_p]),
     "stg_llgs_rk45_f64": (C.c_int, [C.POINTER(StgRk45Args), C.c_void_p]),
+    "stg_llgs_rk45_cost_f64": (C.c_int, [C.POINTER(StgRk45Args), C.c_void_p, C.c_void_p]),
+    "stg_llgs_rk45_sort_f64": (C.c_int, [C.POINTER(StgRk45Args), C.c_void_p, C.c_void_p, C.c_void_p]),
     "stg_array_step_f64": (C.c_int, [C.POINTER(StgArrayStepArgs), C.c_void_p]),
     "stg_array_reset": (C.c_int, [C.POINTER(StgArrayStepArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
     "stg_device_field_f64": (C.c_int, [C.POINTER(StgDeviceParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,

@@ -16,6 +16,7 @@
 #include "../../include/stg.h"
 #include "llgs_core.cuh"
 #include "stt_env_core.cuh"
+#include "sort_utils.cuh"
 
 namespace stg {
 
@@ -444,52 +445,12 @@ __global__ void __launch_bounds__(128) stt_env_reset_kernel(const __grid_constan
     env_reset_body(a, e);
 }
 
-// ---- counting sort of envs by substep count (descending) -------------------------------------------------------------
-// Warp-aggregated atomics: lanes that fall into the same bin elect a leader which issues ONE atomicAdd for the group
-// (with a fixed pulse duration all 1M envs share a bin; un-aggregated that is 1M serialised atomics on one address).
-__device__ __forceinline__ int warp_aggregated_inc(int32_t* counters, int bin, bool valid) {
-    const unsigned active = __ballot_sync(0xffffffffu, valid);
-    int pos = 0;
-    if (valid) {
-        const unsigned peers = __match_any_sync(active, bin);
-        const int leader = __ffs(peers) - 1;
-        const int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(counters + bin, __popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        pos = base + __popc(peers & ((1u << lane) - 1u));
-    }
-    return pos;
-}
+// ---- counting sort of envs by substep count (descending); helpers in sort_utils.cuh ---------------------------------------
 __global__ void sort_hist_kernel(const StgSttFolded* table, const int32_t* pidx, const float* action, int32_t* hist,
                                  int64_t n) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = e < n;
     warp_aggregated_inc(hist, valid ? action_bin(table, pidx, action, e) : 0, valid);
-}
-__global__ void sort_scan_kernel(int32_t* hist) {   // one block of 1024 threads, 8 bins each: exclusive scan in place
-    __shared__ int32_t s[1024];
-    __shared__ int32_t s_nonempty;
-    const int t = threadIdx.x;
-    if (t == 0) s_nonempty = 0;
-    __syncthreads();
-    int32_t loc[8];
-    int32_t sum = 0, ne = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { loc[q] = hist[t * 8 + q]; sum += loc[q]; ne += loc[q] != 0; }
-    if (ne) atomicAdd(&s_nonempty, ne);
-    s[t] = sum;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        const int32_t v = (t >= off) ? s[t - off] : 0;
-        __syncthreads();
-        s[t] += v;
-        __syncthreads();
-    }
-    int32_t run = s[t] - sum;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { hist[t * 8 + q] = run; run += loc[q]; }
-    if (t == 0) hist[STG_SORT_BINS] = s_nonempty;   // number of distinct substep counts
 }
 __global__ void sort_scatter_kernel(const StgSttFolded* table, const int32_t* pidx, const float* action, int32_t* hist,
                                     int32_t* perm, int64_t n) {

@@ -161,15 +161,6 @@ class LLGSSolver:
         a = _lib.StgRk45Args()
         t_end_t = arr(t_end, (n,))
         keep = [table, pidx, m0, t_end_t]
-        if self.sort_trajectories and n >= 64:
-            # lanes whose trajectory has ended idle until the slowest lane of the warp is done: launch in an order that puts
-            # trajectories of the same parameter set and similar length into the same warp (longest first)
-            perm = torch.argsort(t_end_t, descending=True, stable=True)
-            if pidx is not None and len(structs) > 1:
-                perm = perm[torch.argsort(pidx[perm], stable=True)]
-            perm = perm.to(torch.int32).contiguous()
-            keep.append(perm)
-            a.d_perm = perm.data_ptr()
         a.d_table, a.d_param_index, a.d_m0, a.d_t_end = table.data_ptr(), _lib.ptr(pidx), m0.data_ptr(), t_end_t.data_ptr()
         for name, val, shape in (("d_current", current, (n,)), ("d_t_pulse", t_pulse, (n,)),
                                  ("d_happ", applied_field, (n, 3)), ("d_voltage", voltage, (n,))):
@@ -194,6 +185,21 @@ class LLGSSolver:
                     seg_h = torch.as_tensor(np.asarray(seg_h, dtype=np.float64)).to(dev).reshape(rows, k + 1, 3).contiguous()
                     keep.append(seg_h)
                     a.d_seg_field = seg_h.data_ptr()
+        a.rtol, a.atol, a.max_step = self.rtol, self.atol, self.max_step
+        a.n_envs, a.n_sets = n, len(structs)
+        if self.sort_trajectories and n >= 64:
+            # lanes whose trajectory has ended idle until the slowest lane of the warp is done: launch in an order that puts
+            # trajectories of the same parameter set and similar estimated cost into the same warp (most expensive first).
+            # The estimate is span length x max(1/max_step, 8 (gamma |H_eff(m0)| + torque rate)); counting sort on the device
+            # (stg_llgs_rk45_sort_f64: three small launches, no host synchronisation).
+            perm = torch.empty(n, dtype=torch.int32, device=dev)
+            work = torch.empty(_lib.SORT_WORK_INTS, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(self._lib.stg_llgs_rk45_sort_f64(C.byref(a), perm.data_ptr(), work.data_ptr(),
+                                                            torch.cuda.current_stream(dev).cuda_stream), "stg_llgs_rk45_sort_f64")
+            keep.append(work)
+            keep.append(perm)
+            a.d_perm = perm.data_ptr()
         out = {
             "y": torch.empty(n, 3, dtype=f64, device=dev),
             "n_accepted": torch.zeros(n, dtype=torch.int32, device=dev),
