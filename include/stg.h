@@ -386,7 +386,7 @@ typedef struct StgArrayParams {
  *   d_action    [n][3] f32 (idx, J, T); `global` mode: [n][2] f32 (J, T) with action_stride = 2
  *   outputs     d_obs [n][D][6] f32 (pattern, target), d_reward/d_step_energy/d_similarity [n] f64, flags [n] u8
  *   STG_F_AUTORESET: arrays that terminate/truncate are reset in the same call (random unit vectors from the Philox stream,
- *   target kept), d_final_obs receives the pre-reset observation. */
+ *   target kept), d_final_obs receives the pre-reset observation (rows of arrays that keep running are not written). */
 typedef struct StgArrayStepArgs {
     StgArrayParams params;
     const double* d_coupling;

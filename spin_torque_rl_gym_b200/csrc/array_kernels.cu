@@ -115,9 +115,7 @@ __global__ void __launch_bounds__(kArrayBlock, kArrayMinBlocks) array_step_kerne
         if (threadIdx.x == 0) a.d_episode[arr] = (int32_t)ep;
         array_draw_pattern(a, arr, ep, nd, pattern);
         __syncthreads();
-    } else if ((a.flags & STG_F_AUTORESET) && a.d_final_obs) {
-        for (int q = threadIdx.x; q < nd * 6; q += blockDim.x) a.d_final_obs[arr * nd * 6 + q] = 0.0f;
-    }
+    }       // final_obs of a running array is not written (include/stg.h: valid where terminated | truncated)
     for (int q = threadIdx.x; q < nd * 3; q += blockDim.x) gp[q] = pattern[q];
     array_store_obs(a.d_obs + arr * nd * 6, pattern, target, nd);
 }
@@ -315,6 +313,7 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
     double* target = pattern + 3 * nd;
     double* scratch = target + 3 * nd;              // coupling row during the device update, per-device norms afterwards
     bool reset = false;
+    int aff_first = 0, aff_count = 0, aff_stride = 1;     // devices this step updated (pattern write-back)
     double st_v[STG_NSTATS];
 #pragma unroll
     for (int q = 0; q < STG_NSTATS; ++q) st_v[q] = 0.0;
@@ -327,6 +326,7 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
         auto dots = [&](int i) { return dot_u(pattern + 3 * i, target + 3 * i); };
         const double prev = over_nd(group_numpy_sum<ND_T>(gmask, l8, nd, dots));
         const ArrayAction act = array_parse_action(p, act_raw);
+        aff_first = act.first; aff_count = act.count; aff_stride = act.stride;
         const double energy = group_apply_action<ND_T>(p, a.d_coupling, pattern, scratch, act, gmask, l8);
         const double sim = over_nd(group_numpy_sum<ND_T>(gmask, l8, nd, dots));
 #pragma unroll
@@ -391,26 +391,34 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
         for (int q = 0; q < STG_NSTATS; ++q)
             if (st_v[q] != 0.0) atomicAdd(st + q, st_v[q]);
     }
-    const unsigned reset_bits = __ballot_sync(0xffffffffu, reset && l8 == 0);      // bit 8*ar: array ar of this warp was reset
     __syncwarp();
-    // the four arrays are contiguous in HBM: whole-warp coalesced stores of patterns, observations, final-observation zeros
-    const bool zero_final = (a.flags & STG_F_AUTORESET) && a.d_final_obs;
+    // Pattern write-back: only the rows this step changed - the affected devices (1 of 64 in individual mode) - unless the array
+    // was reset (new random pattern) or every device was driven; the final-observation rows of running arrays are not written
+    // (include/stg.h: valid where terminated | truncated). The observations of the four arrays are contiguous in HBM:
+    // whole-warp coalesced stores.
+    const bool bulk_pattern = reset || 2 * aff_count > nd;
+    if (valid && !bulk_pattern) {
+        double* gp = gp0 + (int64_t)g * nd * 3;
+        for (int q = l8; q < 3 * aff_count; q += kGroupLanes) {
+            const int d = aff_first + (q / 3) * aff_stride, c = q - 3 * (q / 3);
+            gp[3 * d + c] = pattern[3 * d + c];
+        }
+    }
+    const unsigned bulk_bits = __ballot_sync(0xffffffffu, valid && bulk_pattern && l8 == 0);   // bit 8*ar: whole pattern of array ar
     if (VEC) {
         const int n2 = 3 * nd / 2;
         double2* gp2 = reinterpret_cast<double2*>(gp0);
         double2* go2 = reinterpret_cast<double2*>(a.d_obs + arr0 * nd * 6);
-        double2* gf2 = zero_final ? reinterpret_cast<double2*>(a.d_final_obs + arr0 * nd * 6) : nullptr;
 #pragma unroll
         for (int ar = 0; ar < kGroupsPerWarp; ++ar) {
             if (ar < narr) {
                 const double2* sp = reinterpret_cast<const double2*>(smem + ar * per);
                 const double2* so = reinterpret_cast<const double2*>(smem + ar * per + 3 * nd);
-                const bool zf = zero_final && !((reset_bits >> (8 * ar)) & 1u);
+                const bool bp = (bulk_bits >> (8 * ar)) & 1u;
 #pragma unroll
                 for (int q = lane; q < n2; q += 32) {
-                    gp2[ar * n2 + q] = sp[q];
+                    if (bp) gp2[ar * n2 + q] = sp[q];
                     go2[ar * n2 + q] = so[q];
-                    if (zf) gf2[ar * n2 + q] = make_double2(0.0, 0.0);
                 }
             }
         }
@@ -419,12 +427,10 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
             const double* pat = smem + ar * per;
             const double* so = pat + 3 * nd;
             double* go = reinterpret_cast<double*>(a.d_obs + (arr0 + ar) * nd * 6);      // 6 f32 = 3 f64 slots per device
-            const bool zf = zero_final && !((reset_bits >> (8 * ar)) & 1u);
-            double* gf = zf ? reinterpret_cast<double*>(a.d_final_obs + (arr0 + ar) * nd * 6) : nullptr;
+            const bool bp = (bulk_bits >> (8 * ar)) & 1u;
             for (int q = lane; q < 3 * nd; q += 32) {
-                gp0[ar * 3 * nd + q] = pat[q];
+                if (bp) gp0[ar * 3 * nd + q] = pat[q];
                 go[q] = so[q];
-                if (zf) gf[q] = 0.0;
             }
         }
     }

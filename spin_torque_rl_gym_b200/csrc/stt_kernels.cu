@@ -479,6 +479,9 @@ __global__ void __launch_bounds__(kBlock) stt_solve_grid_kernel(const __grid_con
 }
 
 // ---- dispatch --------------------------------------------------------------------------------------------------------
+// (Measured and dropped in round 2: capping the residency with unused dynamic shared memory so that a grid of 1.73 waves - the
+// strong-scaling shard of 131,072 envs - runs as two equal waves at 14 warps/SM instead of a full and a 73 % one: 1.415 ms
+// against 1.373 ms as it is, the kernel's throughput still grows from 14 to 16 warps per SM. profiles/README.md.)
 template <typename R, bool AXIS_Z, int NOISE>
 static cudaError_t launch_step2(const StepArgs& a, cudaStream_t s) {
     const unsigned grid = (unsigned)((a.n_envs + kBlock - 1) / kBlock);
