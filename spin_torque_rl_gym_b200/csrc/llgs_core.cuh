@@ -78,7 +78,9 @@ struct Philox {
 
 // ---- fast device intrinsics (MUFU) with libm fallbacks for the host build ---------------------------------------------
 STG_HD float fast_lg2(float x) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(STG_EXP_NO_LGSQRT)
+    return x - 1.0f;                    // timing experiment only
+#elif defined(__CUDA_ARCH__)
     float r;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // x >= 2^-33 here: no denormal fix-up needed
     return r;
@@ -87,7 +89,9 @@ STG_HD float fast_lg2(float x) {
 #endif
 }
 STG_HD float fast_sqrt(float x) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(STG_EXP_NO_LGSQRT)
+    return x * 0.5f;                    // timing experiment only
+#elif defined(__CUDA_ARCH__)
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;

@@ -207,9 +207,20 @@ STG_HD double ulp_above(double t) {   // |nextafter(t, +inf) - t| (the integrati
     return nextafter(t, (double)INFINITY) - t;
 #endif
 }
-// en^(-1/5) of the step-size controller (rk.py:102): exp(-0.2 log en) instead of pow(), whose data-dependent special-case
-// branches diverge across the lanes of a warp; the two agree to a few ulp, far below anything that changes a decision
-STG_HD double pow_m02(double en) { return exp(-0.2 * log(en)); }
+// en^(-1/5) of the step-size controller (rk.py:102) from en^2 (the RMS norm's square root is never taken): x = (en^2)^(-1/10)
+// by one Newton step on x^-10 = en^2 from a single-precision seed (lg2 / ex2, relative error ~1e-7 -> ~1e-13 after the step,
+// far below anything that changes an accept / reject decision or a step count). pow() and exp(log()) in FP64 were 12 % of the
+// kernel's stall samples.
+STG_HD double pow_m01(double en2) {
+#if defined(__CUDA_ARCH__)
+    if (!(en2 > 1e-30 && en2 < 1e30)) return exp(-0.1 * log(en2));
+    double x = (double)exp2f(-0.1f * __log2f((float)en2));
+    const double x2 = x * x, x4 = x2 * x2, x5 = x4 * x;
+    return x * (1.1 - 0.1 * en2 * (x5 * x5));
+#else
+    return pow(en2, -0.1);
+#endif
+}
 STG_HD V3 vabs_max(V3 a, V3 b) { return {fmax(fabs(a.x), fabs(b.x)), fmax(fabs(a.y), fabs(b.y)), fmax(fabs(a.z), fabs(b.z))}; }
 
 // One trajectory of LLGSSolver.solve. Returns through the StgRk45Args output arrays of env e.
@@ -340,17 +351,20 @@ STG_HD void rk45_attempt(const StgRk45Args& a, Rk45State& S) {
     const V3 f_new = f.template eval<SEG>(a, S.e, t + h, y_new);
     const V3 err = h * (RKT(e1) * k1 + RKT(e3) * k3 + RKT(e4) * k4 + RKT(e5) * k5 + RKT(e6) * k6 + RKT(e7) * f_new);
     const V3 mx = vabs_max(y, y_new);
-    const double en = rms3({err.x / (atol + mx.x * rtol), err.y / (atol + mx.y * rtol), err.z / (atol + mx.z * rtol)});
-    if (en < 1.0) {
-        double factor = (en == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow_m02(en));
+    // en^2 = mean((err / scale)^2) with ONE division: sum_i (err_i prod_{j != i} s_j)^2 / (3 (s_x s_y s_z)^2)
+    const double sx = atol + mx.x * rtol, sy = atol + mx.y * rtol, sz = atol + mx.z * rtol;
+    const double sxy = sx * sy, ax = err.x * (sy * sz), ay = err.y * (sx * sz), az = err.z * sxy, sp = sxy * sz;
+    const double en2 = (ax * ax + ay * ay + az * az) / (3.0 * (sp * sp));
+    if (en2 < 1.0) {
+        double factor = (en2 == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow_m01(en2));
         if (S.rejected) factor = fmin(1.0, factor);
         S.h_abs *= factor;
         S.t = t_new; S.y = y_new; S.fk = f_new;
         ++S.n_acc;
         S.new_step = true;
         rk45_record<SEG>(a, S, S.n_acc, S.t, S.y);
-    } else if (en >= 1.0) {
-        S.h_abs *= fmax(0.2, 0.9 * pow_m02(en));
+    } else if (en2 >= 1.0) {
+        S.h_abs *= fmax(0.2, 0.9 * pow_m01(en2));
         S.rejected = true;
         ++S.n_rej;
     } else {               // NaN error norm: SciPy would never terminate; flag and stop

@@ -121,6 +121,7 @@ class LLGSSolver:
         self._device = torch.device(device)
         self._lib = _lib.load()
         self.sort_trajectories = bool(sort_trajectories)
+        self._tables: Dict[bytes, Any] = {}
 
     # -----------------------------------------------------------------------------------------------------------------
     def solve_batch(self, m_initial, t_end, device_params: Union[Dict[str, Any], Sequence[Dict[str, Any]]], current=0.0,
@@ -152,7 +153,15 @@ class LLGSSolver:
         structs = [_params.make_llg_struct(t, p, thermal=thermal_noise, temperature=temperature,
                                            current_direction=current_direction, gamma=self.gamma)
                    for t, p in zip(types, plist)]
-        table = torch.from_numpy(_params.llg_table(structs)).to(dev)
+        # the device copy of the parameter table is kept across calls with the same parameters (a pageable H2D copy per call
+        # otherwise: the host path is a visible share of a 2 ms solve)
+        raw = _params.llg_table(structs)
+        key = raw.tobytes()
+        table = self._tables.get(key)
+        if table is None:
+            if len(self._tables) >= 16:
+                self._tables.clear()
+            table = self._tables[key] = torch.from_numpy(raw).to(dev)
         pidx = None
         if param_index is not None:
             pidx = torch.as_tensor(param_index, dtype=torch.int32).to(dev).contiguous()
@@ -200,13 +209,11 @@ class LLGSSolver:
             keep.append(work)
             keep.append(perm)
             a.d_perm = perm.data_ptr()
+        counts = torch.empty(4, n, dtype=torch.int32, device=dev)          # every entry is written by the kernel
         out = {
             "y": torch.empty(n, 3, dtype=f64, device=dev),
-            "n_accepted": torch.zeros(n, dtype=torch.int32, device=dev),
-            "n_rejected": torch.zeros(n, dtype=torch.int32, device=dev),
-            "n_rhs": torch.zeros(n, dtype=torch.int32, device=dev),
-            "status": torch.zeros(n, dtype=torch.int32, device=dev),
-            "t_reached": torch.zeros(n, dtype=f64, device=dev),
+            "n_accepted": counts[0], "n_rejected": counts[1], "n_rhs": counts[2], "status": counts[3],
+            "t_reached": torch.empty(n, dtype=f64, device=dev),
         }
         a.d_y_out, a.d_n_accepted, a.d_n_rejected = out["y"].data_ptr(), out["n_accepted"].data_ptr(), out["n_rejected"].data_ptr()
         a.d_n_rhs, a.d_status, a.d_t_reached = out["n_rhs"].data_ptr(), out["status"].data_ptr(), out["t_reached"].data_ptr()
