@@ -56,9 +56,13 @@ class SpinTorqueArrayVectorEnv:
                  action_mode: str = "individual", observation_mode: str = "array", success_threshold: float = 0.9,
                  energy_penalty_weight: float = 0.1, render_mode: Optional[str] = None, seed: Optional[int] = None, *,
                  device: Union[str, Any] = "cuda", rng_seed: Optional[int] = None, array_offset: int = 0,
-                 autoreset: bool = True, collect_stats: bool = True, one_warp_kernel: bool = False):
+                 autoreset: bool = True, collect_stats: bool = True, one_warp_kernel: bool = False,
+                 host_outputs: bool = False):
         torch = _lib.require_cuda()
         self.one_warp_kernel = bool(one_warp_kernel)      # STG_F_ARRAY_ONE_WARP: A/B against the four-arrays-per-warp kernel
+        # host_outputs: obs / final_obs / reward / terminated / truncated live in PINNED HOST memory, the kernel writes them there
+        # directly (for consumers on the CPU); step() then synchronises the stream before it returns (as SpinTorqueVectorEnv)
+        self.host_outputs = bool(host_outputs)
         self._args_cache = None
         self._torch = torch
         self._lib = _lib.load()
@@ -140,11 +144,15 @@ class SpinTorqueArrayVectorEnv:
             self._total_energy = torch.zeros(N, dtype=f64, device=dev)
             self._step_count = torch.zeros(N, dtype=torch.int32, device=dev)
             self._episode = torch.zeros(N, dtype=torch.int32, device=dev)
-            self._obs = torch.zeros(N, self.n_rows, self.n_cols, 6, dtype=torch.float32, device=dev)
-            self._final_obs = torch.zeros_like(self._obs)
-            self._reward = torch.zeros(N, dtype=f64, device=dev)
-            self._terminated = torch.zeros(N, dtype=torch.uint8, device=dev)
-            self._truncated = torch.zeros(N, dtype=torch.uint8, device=dev)
+            def out_buf(shape, dtype):
+                if self.host_outputs:
+                    return torch.zeros(shape, dtype=dtype).pin_memory()
+                return torch.zeros(shape, dtype=dtype, device=dev)
+            self._obs = out_buf((N, self.n_rows, self.n_cols, 6), torch.float32)
+            self._final_obs = out_buf((N, self.n_rows, self.n_cols, 6), torch.float32)
+            self._reward = out_buf((N,), f64)
+            self._terminated = out_buf((N,), torch.uint8)
+            self._truncated = out_buf((N,), torch.uint8)
             self._step_energy = torch.zeros(N, dtype=f64, device=dev)
             self._similarity = torch.zeros(N, dtype=f64, device=dev)
             self._stats = torch.zeros(_lib.STAT_REPLICAS, _lib.NSTATS, dtype=f64, device=dev)
@@ -177,10 +185,10 @@ class SpinTorqueArrayVectorEnv:
         a.d_pattern, a.d_target = self._pattern.data_ptr(), self._target.data_ptr()
         a.d_total_energy, a.d_step_count, a.d_episode = (self._total_energy.data_ptr(), self._step_count.data_ptr(),
                                                          self._episode.data_ptr())
-        a.d_obs, a.d_reward = self._obs.data_ptr(), self._reward.data_ptr()
-        a.d_terminated, a.d_truncated = self._terminated.data_ptr(), self._truncated.data_ptr()
+        a.d_obs, a.d_reward = _lib.ptr(self._obs), _lib.ptr(self._reward)
+        a.d_terminated, a.d_truncated = _lib.ptr(self._terminated), _lib.ptr(self._truncated)
         a.d_step_energy, a.d_similarity = self._step_energy.data_ptr(), self._similarity.data_ptr()
-        a.d_final_obs = self._final_obs.data_ptr() if self.autoreset else None
+        a.d_final_obs = _lib.ptr(self._final_obs) if self.autoreset else None
         a.d_stats = self._stats.data_ptr() if self.collect_stats else None
         a.seed, a.array_offset, a.n_arrays = self.rng_seed, self.array_offset, self.num_envs
         a.action_stride = self._adim
@@ -220,6 +228,7 @@ class SpinTorqueArrayVectorEnv:
         self.gpu_launches += 1
         self._needs_reset = False
         self._keep = keep
+        self._sync_host_outputs()
         return self._obs, {}
 
     def step(self, actions):
@@ -243,7 +252,13 @@ class SpinTorqueArrayVectorEnv:
                 "total_energy": self._total_energy, "step_count": self._step_count}
         if self.autoreset:
             info["final_observation"] = self._final_obs
+        self._sync_host_outputs()
         return self._obs, self._reward, self._terminated_b, self._truncated_b, info
+
+    def _sync_host_outputs(self) -> None:
+        """host_outputs: the kernel wrote obs / reward / flags into pinned host memory; readable once the stream has drained."""
+        if self.host_outputs and not self._torch.cuda.is_current_stream_capturing():
+            self._torch.cuda.current_stream(self.device).synchronize()
 
     @property
     def current_pattern(self):

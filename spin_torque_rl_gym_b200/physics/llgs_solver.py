@@ -128,11 +128,12 @@ class LLGSSolver:
                     t_pulse=None, applied_field=None, voltage=None, thermal_noise: bool = False,
                     temperature: float = 300.0, param_index=None, device_type=None, current_direction=None,
                     return_trajectory: bool = False, max_traj_rows: Optional[int] = None, noise=None,
-                    seed: int = 0, env_offset: int = 0, t_start=None, segments=None) -> Dict[str, Any]:
+                    seed: int = 0, env_offset: int = 0, t_start=None, segments=None, host_outputs: bool = False) -> Dict[str, Any]:
         """N trajectories of LLGSSolver.solve in one launch. Arrays may be NumPy or torch; outputs are CUDA tensors.
         `t_start`: [N] or scalar start times (default 0; t_end is absolute). `segments`: piecewise-constant controls
         (ends [K] or [N,K], current [K+1] or [N,K+1], field [K+1,3] or [N,K+1,3] or None) replacing current / t_pulse / applied_field
-        (include/stg.h StgRk45Args.d_seg_*)."""
+        (include/stg.h StgRk45Args.d_seg_*). `host_outputs`: end states, counters and status are written by the kernel straight
+        into pinned host memory (CPU tensors are returned, the stream is synchronised before returning)."""
         torch = _lib.require_cuda()
         dev, f64 = self._device, torch.float64
 
@@ -209,14 +210,17 @@ class LLGSSolver:
             keep.append(work)
             keep.append(perm)
             a.d_perm = perm.data_ptr()
-        counts = torch.empty(4, n, dtype=torch.int32, device=dev)          # every entry is written by the kernel
+        def out_buf(shape, dtype):                                          # every entry is written by the kernel
+            return torch.empty(shape, dtype=dtype).pin_memory() if host_outputs else torch.empty(shape, dtype=dtype, device=dev)
+        counts = out_buf((4, n), torch.int32)
         out = {
-            "y": torch.empty(n, 3, dtype=f64, device=dev),
+            "y": out_buf((n, 3), f64),
             "n_accepted": counts[0], "n_rejected": counts[1], "n_rhs": counts[2], "status": counts[3],
-            "t_reached": torch.empty(n, dtype=f64, device=dev),
+            "t_reached": out_buf((n,), f64),
         }
-        a.d_y_out, a.d_n_accepted, a.d_n_rejected = out["y"].data_ptr(), out["n_accepted"].data_ptr(), out["n_rejected"].data_ptr()
-        a.d_n_rhs, a.d_status, a.d_t_reached = out["n_rhs"].data_ptr(), out["status"].data_ptr(), out["t_reached"].data_ptr()
+        a.d_y_out, a.d_t_reached = _lib.ptr(out["y"]), _lib.ptr(out["t_reached"])
+        cbase = _lib.ptr(counts)
+        a.d_n_accepted, a.d_n_rejected, a.d_n_rhs, a.d_status = cbase, cbase + 4 * n, cbase + 8 * n, cbase + 12 * n
         if return_trajectory:
             if max_traj_rows is None:
                 tmax = float((t_end_t - t_start_t).max()) if t_start_t is not None else float(t_end_t.max())
@@ -238,6 +242,8 @@ class LLGSSolver:
         with torch.cuda.device(dev):
             _lib.check(self._lib.stg_llgs_rk45_f64(C.byref(a), torch.cuda.current_stream(dev).cuda_stream),
                        "stg_llgs_rk45_f64")
+        if host_outputs:
+            torch.cuda.current_stream(dev).synchronize()
         out["m"] = out["y"] / out["y"].norm(dim=1, keepdim=True)
         out["success"] = out["status"] == 0
         self._keep = keep

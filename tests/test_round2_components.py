@@ -178,3 +178,38 @@ def test_cuda_thermal_analytics_grid_vs_live_reference(cuda_device):
     # a device axis on the sweep
     sw2 = th2.generate_temperature_sweep((50.0, 450.0), [tp, dict(tp, volume=3e-25)], n_points=23)
     assert sw2["retention_time"].shape == (23, 2) and np.allclose(sw2["retention_time"][:, 0], sweep["retention_time"], rtol=1e-12)
+
+
+# ---- host_outputs for K2 and K3: the kernels write their results straight into pinned host memory --------------------------------
+@pytest.mark.gpu
+def test_cuda_host_outputs_of_rk45_and_array_env_equal_device_outputs(cuda_device):
+    import torch
+    from spin_torque_rl_gym_b200 import SpinTorqueArrayVectorEnv
+    from spin_torque_rl_gym_b200.physics import LLGSSolver
+    rng = np.random.default_rng(3)
+    # K2
+    n = 1000
+    p = _solve_params()
+    m0 = rng.normal(size=(n, 3))
+    cur = rng.uniform(-15.0, 15.0, n)
+    solver = LLGSSolver(device=cuda_device)
+    rd = solver.solve_batch(m0, 4e-11, p, current=cur)
+    rh = solver.solve_batch(m0, 4e-11, p, current=cur, host_outputs=True)
+    for k in ("y", "n_accepted", "n_rejected", "n_rhs", "status", "t_reached"):
+        assert rh[k].device.type == "cpu" and torch.equal(rh[k], rd[k].cpu()), k
+    assert torch.allclose(rh["m"], rd["m"].cpu(), rtol=0, atol=1e-15)        # y / |y| by torch on the host vs on the device
+    # K3
+    na, size = 37, (8, 8)
+    kw = dict(num_envs=na, array_size=size, action_mode="row", device=cuda_device, rng_seed=4, max_steps=3)
+    ed, eh = SpinTorqueArrayVectorEnv(**kw), SpinTorqueArrayVectorEnv(host_outputs=True, **kw)
+    od, _ = ed.reset(seed=4)
+    oh, _ = eh.reset(seed=4)
+    assert oh.is_pinned() and torch.equal(oh, od.cpu())
+    for s in range(5):
+        act = np.stack([rng.uniform(0, 7.49, na), rng.uniform(-2e6, 2e6, na), rng.uniform(0, 5e-9, na)], 1).astype(np.float32)
+        od, rd_, ted, trd, idv = ed.step(act)
+        oh, rh_, teh, trh, ih = eh.step(act)
+        assert torch.equal(oh, od.cpu()) and torch.equal(rh_, rd_.cpu()) and torch.equal(teh, ted.cpu()) and torch.equal(trh, trd.cpu())
+        done = (ted | trd).cpu()
+        assert torch.equal(ih["final_observation"][done], idv["final_observation"].cpu()[done])
+    assert eh.episode_stats()["steps"] == 5 * na and ed.episode_stats()["truncated"] > 0

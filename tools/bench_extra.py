@@ -53,6 +53,16 @@ def collect(dev=None):
     out["rk45_mix_262144"] = {"ms_per_solve": ms, "attempted_steps_per_s": attempts / (ms * 1e-3),
                               "rhs_evals_per_s": float(res["r"]["n_rhs"].sum()) / (ms * 1e-3),
                               "accepted_per_env": attempts / n, "fp64_tflops_algorithmic": attempts * 766 / (ms * 1e-3) / 1e12}
+    # end to end: host NumPy inputs (pageable -> device inside the call), results written by the kernel into pinned host memory
+    h_m0, h_pidx, h_cur, h_volt = m0.cpu().numpy(), pidx.cpu().numpy(), cur.cpu().numpy(), volt.cpu().numpy()
+
+    def rk_e2e():
+        r = solver.solve_batch(h_m0, 1e-10, [sot, vcma], current=h_cur, voltage=h_volt, param_index=h_pidx,
+                               device_type=["sot_mram", "vcma_mram"], host_outputs=True)
+        res["e"] = float(r["y"][0, 0]) + int(r["n_accepted"][0])
+    ms_e = timed(rk_e2e, reps=5, warm=2)
+    out["rk45_mix_262144"]["e2e"] = {"ms_per_solve": ms_e, "attempted_steps_per_s": attempts / (ms_e * 1e-3),
+                                     "h2d_bytes": n * (24 + 8 + 8 + 4), "d2h_bytes": n * (24 + 16 + 8)}
     # ---- configs[3]: 16,384 8x8 dipolar crossbars --------------------------------------------------------------------------
     A = 16384
     for mode in ("individual", "row", "global"):
@@ -69,6 +79,19 @@ def collect(dev=None):
         ms = timed(lambda: env.step(act), reps=10, warm=3)
         out[f"array_8x8_{mode}_16384"] = {"ms_per_step": ms, "array_steps_per_s": A / (ms * 1e-3),
                                           "hbm_gbs_algorithmic": A * 64 * 96 / (ms * 1e-3) / 1e9}
+        if mode == "individual":
+            # end to end: pinned host actions in, observations / rewards / flags written by the kernel into pinned host memory
+            env_h = stg.SpinTorqueArrayVectorEnv(num_envs=A, array_size=(8, 8), action_mode=mode, device=dev, rng_seed=1,
+                                                 host_outputs=True)
+            env_h.reset(seed=1)
+            act_h = act.cpu().pin_memory()
+
+            def arr_e2e():
+                o, r, te, tr, _ = env_h.step(act_h)
+                return float(o[0, 0, 0, 0]) + float(r[0])
+            ms_e = timed(arr_e2e, reps=10, warm=3)
+            out[f"array_8x8_{mode}_16384"]["e2e"] = {"ms_per_step": ms_e, "array_steps_per_s": A / (ms_e * 1e-3),
+                                                     "h2d_bytes_per_step": A * k * 4, "d2h_bytes_per_step": A * (64 * 24 + 10)}
     # ---- configs[1] with ragged durations T ~ U(1e-12, 5e-9): unsorted vs sorted launch -------------------------------------
     N = 1 << 20
     act = torch.zeros(N, 2, dtype=torch.float32, device=dev)
