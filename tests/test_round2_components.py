@@ -213,3 +213,62 @@ def test_cuda_host_outputs_of_rk45_and_array_env_equal_device_outputs(cuda_devic
         done = (ted | trd).cpu()
         assert torch.equal(ih["final_observation"][done], idv["final_observation"].cpu()[done])
     assert eh.episode_stats()["steps"] == 5 * na and ed.episode_stats()["truncated"] > 0
+
+
+# ---- torch.library registration ---------------------------------------------------------------------------------------
+def test_torch_library_ops_registered_with_fake_impls_and_no_cpu_kernel():
+    import torch
+    from spin_torque_rl_gym_b200 import torch_ops  # noqa: F401  (defines the stg:: namespace)
+    for name in ("vec3_cross", "vec3_dot", "vec3_normalize", "stt_env_step"):
+        assert hasattr(torch.ops.stg, name), name
+    schema = str(torch.ops.stg.stt_env_step.default._schema)
+    for arg in ("m", "target", "total_energy", "last_action", "step_count", "episode"):
+        assert f"Tensor(a" in schema and f") {arg}" in schema, schema           # declared as mutated
+    a = torch.empty(7, 3, dtype=torch.float64, device="meta")
+    assert torch.ops.stg.vec3_cross(a, a).shape == (7, 3) and torch.ops.stg.vec3_dot(a, a).shape == (7,)
+    assert torch.ops.stg.vec3_normalize(a).shape == (7, 3)
+    act = torch.empty(5, 2, dtype=torch.float32, device="meta")
+    st = [torch.empty(3, 5, device="meta", dtype=torch.float64)] * 2 + [torch.empty(5, device="meta", dtype=torch.float64),
+          torch.empty(2, 5, device="meta", dtype=torch.float64)] + [torch.empty(5, device="meta", dtype=torch.int32)] * 2
+    obs, r, te, tr = torch.ops.stg.stt_env_step(1, act, *st)
+    assert obs.shape == (5, 12) and obs.dtype == torch.float32 and r.dtype == torch.float64 and te.dtype == tr.dtype == torch.bool
+    with pytest.raises((NotImplementedError, RuntimeError)):                      # no CPU kernel behind the op: loud, not a fallback
+        torch.ops.stg.vec3_cross(torch.zeros(2, 3, dtype=torch.float64), torch.zeros(2, 3, dtype=torch.float64))
+
+
+@pytest.mark.gpu
+def test_cuda_torch_library_ops_match_the_classes_and_trace_without_graph_breaks(cuda_device):
+    import torch
+    from spin_torque_rl_gym_b200 import SpinTorqueVectorEnv, torch_ops
+    from spin_torque_rl_gym_b200.physics import VectorizedMagneticsOperations as V
+    rng = np.random.default_rng(5)
+    a, b = (torch.from_numpy(rng.normal(size=(1000, 3))).to(cuda_device) for _ in range(2))
+    assert torch.equal(torch.ops.stg.vec3_cross(a, b), V.batch_cross_product(a, b))
+    assert torch.equal(torch.ops.stg.vec3_dot(a, b), V.batch_dot_product(a, b))
+    assert torch.equal(torch.ops.stg.vec3_normalize(a), V.batch_normalize(a))
+    kw = dict(num_envs=512, device=cuda_device, max_current=1.1e-6, rng_seed=11, dtype=torch.float64, max_steps=4)
+    e_ref, e_op = SpinTorqueVectorEnv(**kw), SpinTorqueVectorEnv(**kw)
+    e_ref.reset(seed=3)
+    e_op.reset(seed=3)
+    h = torch_ops.register_env(e_op)
+    state = torch_ops.state_tensors(e_op)
+
+    def rollout(acts):
+        tot = torch.zeros((), dtype=torch.float64, device=acts.device)
+        for k in range(acts.shape[0]):
+            obs, r, te, tr = torch.ops.stg.stt_env_step(h, acts[k], *state)
+            tot = tot + r.sum() + obs.sum().double()
+        return tot, obs, te | tr
+
+    acts = torch.from_numpy(np.stack([np.stack([rng.uniform(-1.1e-6, 1.1e-6, 512), rng.uniform(1e-11, 1e-9, 512)], 1)
+                                      for _ in range(3)]).astype(np.float32)).to(cuda_device)
+    compiled = torch.compile(rollout, backend="aot_eager", fullgraph=True)        # fullgraph: a graph break would raise
+    tot, obs, done = compiled(acts)
+    want = torch.zeros((), dtype=torch.float64, device=cuda_device)
+    for k in range(3):
+        o, r, te, tr, _ = e_ref.step(acts[k])
+        want = want + r.sum() + o.sum().double()
+    assert torch.equal(obs, o) and torch.equal(done, te | tr) and torch.equal(tot, want)
+    assert torch.equal(e_op.magnetization, e_ref.magnetization)
+    with pytest.raises(RuntimeError):
+        torch.ops.stg.stt_env_step(h, acts[0], state[0][:, :100].contiguous(), *state[1:])     # wrong layout is refused
