@@ -6,7 +6,7 @@
 
 A "step" is one env.step() of every env of the workload = one launch of the fused K1 kernel per GPU.
 Workload (config.workload): BASELINE configs[1] physics — SpinTorque-v0, stt_mram reference defaults, T = 300 K thermal
-fluctuations from the in-kernel Philox stream, RK4 fixed dt (pulse 1 ns -> 999 substeps per step), random current
+fluctuations from the in-kernel stream (xoshiro128++ seeded per env-step from Philox4x32-10), RK4 fixed dt (pulse 1 ns -> 999 substeps per step), random current
 densities — at the env count the metric is quoted on: 1,048,576 envs per GPU (weak scaling: every rank owns that many).
 
   value      LLGS substeps/s, whole job, actions/state/obs resident in HBM (device-timed, max over ranks)
@@ -47,11 +47,11 @@ FLOP_RK4 = 301
 FLOP_RK4_THERMAL_EXECUTED = 232
 # one launch of the headline kernel at 1,048,576 envs x 999 substeps under `ncu --set full` (profiles/, condensed CSV):
 # dram__bytes_read.sum + dram__bytes_write.sum and the pipe utilisations (pct of peak sustained active)
-# (profiles/r02_ncu_stt_env_step_pair_f32_thermal1.csv; 86.3 MB read + 134.5 MB written: the FP64 state planes and the per-step
-# diagnostics make it 1.4x the 150 B per env-step of SURVEY 8(d); 15 GB/s, irrelevant against the FP32 pipes)
-NCU_TRAFFIC_BYTES = 220.8e6
-NCU_PIPES = {"fma": 55.7, "fma_heavy": 68.9, "xu": 55.1, "alu": 30.3, "fp64": 0.9, "issue_slots_busy": 52.6,
-             "warp_instructions_per_env_substep": 192.3}
+# (profiles/r02_ncu_stt_env_step_pair_f32_thermal1_xoshiro.csv; 84.6 MB read + 115.2 MB written: the FP64 state planes and the
+# per-step diagnostics make it 1.3x the 150 B per env-step of SURVEY 8(d); 23 GB/s, irrelevant against the FP32 pipes)
+NCU_TRAFFIC_BYTES = 199.8e6
+NCU_PIPES = {"fma": 51.5, "fma_heavy": 51.2, "xu": 65.7, "alu": 43.3, "fp64": 1.2, "issue_slots_busy": 59.2,
+             "warp_instructions_per_env_substep": 181.7}
 BYTES_PER_ENV_STEP = 150       # algorithmic HBM bytes per env-step
 FP32_LANES_PER_SM, N_SM = 128, 148
 
@@ -213,7 +213,7 @@ def run_reference(args, rank):
 
 def workload_config(n_gpus, n_envs_per_gpu, note=""):
     return {
-        "workload": "SpinTorque-v0 stt_mram (reference default device), T=300K thermal (Philox), RK4 fixed dt, "
+        "workload": "SpinTorque-v0 stt_mram (reference default device), T=300K thermal (in-kernel stream: Philox-seeded xoshiro128++), RK4 fixed dt, "
                     "1 ns pulses = 999 substeps/step, random J in the well-conditioned regime (BASELINE configs[1] physics "
                     "at the metric's 1M envs per GPU)" + (f"; {note}" if note else ""),
         "envs_per_gpu": n_envs_per_gpu, "total_envs": n_envs_per_gpu * n_gpus, "substeps_per_env_step": 999,
@@ -509,7 +509,7 @@ def main():
                 # the path is FP32-pipe bound (no contraction, 2,000 flop/B): the contract's "hbm" | "tensor" do not apply; the HBM
                 # figure is reported beside it
                 "bound": "fp32_fma",
-                "kernel": "stt_env_step_pair_kernel<1> (two envs per thread on FFMA2, axis z, Philox, RK4)" if thermal and args.dtype == "f32"
+                "kernel": "stt_env_step_pair_kernel<1> (two envs per thread on FFMA2, axis z, in-kernel thermal stream, RK4)" if thermal and args.dtype == "f32"
                           else "stt_env_step_kernel",
                 "achieved": achieved, "peak": fp32_peak_theory, "unit": "TFLOP/s", "frac": achieved / fp32_peak_theory,
                 "peak_source": "theoretical 148 SM x 128 FP32 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json carries no FP32 figure)",

@@ -137,7 +137,9 @@ STG_HD void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
     box_muller_scaled(u0, u1, -1.3862943611198906f, n0, n1);
 }
 
-// ---- thermal-field stream ------------------------------------------------------------------------------------------------
+// ---- thermal-field stream identity ---------------------------------------------------------------------------------------------
+// (the RK4 paths seed a xoshiro128++ state from block 0 of this stream, see ThermalSource below; Euler and the resets draw
+// their samples from the blocks themselves)
 // Philox4x32-10, key = the 64-bit seed (uniform over a launch: the key schedule lives in uniform registers), counter =
 // (global env id low word, episode, env step, block index | global env id bits 32..42 << 20): every (env, episode, step, block)
 // owns one counter value, independent of how the batch is partitioned over launches or GPUs (global ids < 2^43, checked by the
@@ -145,9 +147,8 @@ STG_HD void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
 // loop-invariant.
 //
 // Bit budget of the RK4 path: one 32-bit word per Box-Muller pair (16-bit radius uniform, tail to 4.85 sigma; 16-bit angle =
-// 65,536 directions), i.e. THREE Philox blocks per TWO substeps (12 words -> 12 pairs -> 24 normals = 2 substeps x 4 stages x 3
-// components, drawn in the reference's order: substep, stage, xyz). The Philox multiplies (IMAD.WIDE) are the most expensive
-// instructions of the thermal kernel; round 1 spent two blocks per substep (23-bit radius + 19-bit angle), see profiles/README.md.
+// 65,536 directions): six words -> six pairs -> the 12 normals of one substep (4 stages x 3 components, drawn in the reference's
+// order: substep, stage, xyz). Round 1 spent two Philox blocks per substep (23-bit radius + 19-bit angle), see profiles/README.md.
 struct NoiseStream {
     Philox ph;
     uint32_t c0, c1, c2, c3;      // c3: (gid >> 32) << 20, the block index is added to it
@@ -556,6 +557,13 @@ template <int K> struct Ln<FN<K>> {
 // Box-Muller pair from ONE 32-bit word per lane: radius uniform U = (hi16 + 1/2) / 65536 in (0, 1), angle = 2 pi lo16 / 65536.
 // Both are formed by dropping the 16 bits into the mantissa of 1.0f (one PRMT / LOP3) and one exact FFMA, no int->float
 // conversion. `nscale` = -2 ln(2) scale^2 folds the field strength into the radius.
+STG_HD uint32_t lo16_over_one(uint32_t w) {       // 0x3f800000 | (w & 0xffff) as ONE byte permute (the AND + OR are two LOP3)
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0x3f800000u, 0x7610);
+#else
+    return 0x3f800000u | (w & 0xffffu);
+#endif
+}
 template <typename P>
 STG_HD void box_muller16(const uint32_t* w, P nscale, P& n0, P& n1) {
     using K = Pk<P>;
@@ -564,7 +572,7 @@ STG_HD void box_muller16(const uint32_t* w, P nscale, P& n0, P& n1) {
 #pragma unroll
     for (int l = 0; l < L::N; ++l) {
         L::set(vr, l, bits_as_float(0x3f800000u | (w[l] >> 16)));        // 1 + hi16 2^-23
-        L::set(va, l, bits_as_float(0x3f800000u | (w[l] & 0xffffu)));    // 1 + lo16 2^-23
+        L::set(va, l, bits_as_float(lo16_over_one(w[l])));                // 1 + lo16 2^-23
     }
     const P U = K::fma(vr, K::bc(128.0f), K::bc(-127.99999237060546875f));     // 128 vr - (128 - 2^-17) = (hi16 + 1/2) 2^-16, exact
     const P ang = K::fma(va, K::bc(804.24771931898703f), K::bc(-804.24771931898703f));   // 2 pi 128 (va - 1), one rounding
@@ -592,35 +600,102 @@ STG_HD void philox_block(const NoiseStream* ns, uint32_t idx, uint32_t (*w)[NL])
         w[0][l] = o[0]; w[1][l] = o[1]; w[2][l] = o[2]; w[3][l] = o[3];
     }
 }
-// 24 samples N(0, scale^2) per lane: the 4 x 3 stage fields of the RK4 substeps 2g (xi[0..11]) and 2g+1 (xi[12..23])
-template <typename P>
-STG_HD void philox_normals24(const NoiseStream* ns, uint32_t g, P nscale, P* xi) {
-    constexpr int NL = Ln<P>::N;
-    uint32_t w[12][NL];
-    philox_block<NL>(ns, 3u * g, w);
-    philox_block<NL>(ns, 3u * g + 1u, w + 4);
-    philox_block<NL>(ns, 3u * g + 2u, w + 8);
-#pragma unroll
-    for (int k = 0; k < 12; ++k) box_muller16<P>(w[k], nscale, xi[2 * k], xi[2 * k + 1]);
-}
-// the 12 samples of ONE substep (same values as its half of philox_normals24; used around the pulse edge and for odd counts)
-template <typename P>
-STG_HD void philox_normals12(const NoiseStream* ns, uint32_t sub, P nscale, P* xi) {
-    constexpr int NL = Ln<P>::N;
-    const uint32_t g = sub >> 1;
-    const bool odd = (sub & 1u) != 0;
-    // substep 2g: words 0..5 = block 3g + first half of block 3g+1; substep 2g+1: second half of block 3g+1 + block 3g+2
-    uint32_t a[4][NL], b[4][NL], w[6][NL];
-    philox_block<NL>(ns, 3u * g + 1u, b);
-    philox_block<NL>(ns, 3u * g + (odd ? 2u : 0u), a);
-#pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        w[0][l] = odd ? b[2][l] : a[0][l]; w[1][l] = odd ? b[3][l] : a[1][l]; w[2][l] = odd ? a[0][l] : a[2][l];
-        w[3][l] = odd ? a[1][l] : a[3][l]; w[4][l] = odd ? a[2][l] : b[0][l]; w[5][l] = odd ? a[3][l] : b[1][l];
+// ---- the in-kernel thermal stream of the RK4 paths ---------------------------------------------------------------------------
+// xoshiro128++ 1.0 (Blackman & Vigna, "Scrambled linear pseudorandom number generators", ACM TOMS 2021; passes BigCrush, period
+// 2^128 - 1): 4 x 32-bit state per env, output rotl(s0 + s3, 7) + s0 - nine ALU-pipe instructions per 32-bit word and no
+// multiplies, where a Philox4x32-10 word costs four IMAD.WIDE on the FMA-heavy pipe that the packed FP32 stage arithmetic also
+// needs (profiles/README.md: 10.44 -> 8.83 ms per 1M-env x 999-substep step). The state of an env-step is SEEDED from block 0 of
+// that env-step's Philox stream (key = seed, counter = (global env id, episode, step, 0)): the stream of an env-step is a pure
+// function of (seed, global id, episode, step) - independent of sharding, launch geometry and thread mapping, like the all-Philox
+// stream it replaces - and sequential only inside the step (substep i consumes words 6 i .. 6 i + 5, which is the order every
+// integrator runs in). 2^31 env-steps x 2^13 words from random 128-bit starting points overlap with probability ~2^-53.
+struct Xoshiro128pp {
+    uint32_t s0, s1, s2, s3;
+    static STG_HD uint32_t rotl(uint32_t x, int k) {
+#if defined(__CUDA_ARCH__)
+        return __funnelshift_l(x, x, k);
+#else
+        return (x << k) | (x >> (32 - k));
+#endif
     }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) box_muller16<P>(w[k], nscale, xi[2 * k], xi[2 * k + 1]);
+    STG_HD uint32_t next() {
+        const uint32_t r = rotl(s0 + s3, 7) + s0;
+        const uint32_t t = s1 << 9;
+        const uint32_t n2 = s2 ^ s0, n3 = s3 ^ s1;
+        s1 ^= n2;
+        s0 ^= n3;
+        s2 = n2 ^ t;
+        s3 = rotl(n3, 11);
+        return r;
+    }
+};
+STG_HD Xoshiro128pp seed_xoshiro(const NoiseStream& ns) {
+    uint32_t o[4];
+    ns.ph(ns.c0, ns.c1, ns.c2, ns.c3, o);
+    if ((o[0] | o[1] | o[2] | o[3]) == 0u) o[0] = 1u;        // the all-zero state is the generator's one fixed point
+    return Xoshiro128pp{o[0], o[1], o[2], o[3]};
 }
+// Noise source of the RK4 integrators, one stream per lane of the pack. first(g, nz) / second(g, nz): the 12 samples per lane
+// (already scaled) of substep 2g / 2g+1, called strictly in that order from g = 0 (a trailing odd substep calls first() only).
+#ifndef STG_THERMAL_PHILOX10
+template <typename P>
+struct ThermalSource {
+    Xoshiro128pp st[Ln<P>::N];
+    P nscale;
+    STG_HD void init(const NoiseStream* ns, P scale) {
+        nscale = scale;
+#pragma unroll
+        for (int l = 0; l < Ln<P>::N; ++l) st[l] = seed_xoshiro(ns[l]);
+    }
+    STG_HD void draw12(P* nz) {
+        constexpr int NL = Ln<P>::N;
+        uint32_t w[6][NL];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+#pragma unroll
+            for (int l = 0; l < NL; ++l) w[k][l] = st[l].next();
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) box_muller16<P>(w[k], nscale, nz[2 * k], nz[2 * k + 1]);
+    }
+    STG_HD void first(uint32_t, P* nz) { draw12(nz); }
+    STG_HD void second(uint32_t, P* nz) { draw12(nz); }
+};
+#else
+// -DSTG_THERMAL_PHILOX10: the whole stream from Philox4x32-10 (counter-based down to the substep; the round-2 record of
+// profiles/README.md). One draw of three blocks serves a substep pair: blocks 3g and 3g+1 are evaluated for the first substep
+// (6 of their 8 words), the two remaining words are carried to the second, which adds block 3g+2.
+template <typename P>
+struct ThermalSource {
+    NoiseStream ns[Ln<P>::N];
+    P nscale;
+    uint32_t carry[2][Ln<P>::N];
+    STG_HD void init(const NoiseStream* s, P scale) {
+        nscale = scale;
+#pragma unroll
+        for (int l = 0; l < Ln<P>::N; ++l) ns[l] = s[l];
+    }
+    STG_HD void first(uint32_t g, P* nz) {
+        constexpr int NL = Ln<P>::N;
+        uint32_t w[8][NL];
+        philox_block<NL>(ns, 3u * g, w);
+        philox_block<NL>(ns, 3u * g + 1u, w + 4);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) box_muller16<P>(w[k], nscale, nz[2 * k], nz[2 * k + 1]);
+#pragma unroll
+        for (int l = 0; l < NL; ++l) { carry[0][l] = w[6][l]; carry[1][l] = w[7][l]; }
+    }
+    STG_HD void second(uint32_t g, P* nz) {
+        constexpr int NL = Ln<P>::N;
+        uint32_t w[4][NL];
+        philox_block<NL>(ns, 3u * g + 2u, w);
+        box_muller16<P>(carry[0], nscale, nz[0], nz[1]);
+        box_muller16<P>(carry[1], nscale, nz[2], nz[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) box_muller16<P>(w[k], nscale, nz[4 + 2 * k], nz[5 + 2 * k]);
+    }
+};
+#endif
 
 // constants of the fast path in pack form (hi/lo pairs, see StepConsts)
 template <typename P>

@@ -12,8 +12,8 @@ namespace stg {
 #endif
 constexpr int kSubstepUnroll = STG_SUBSTEP_UNROLL;
 #ifndef STG_SUBSTEP_PAIR_UNROLL
-#define STG_SUBSTEP_PAIR_UNROLL 1     // thermal fast path: substep pairs per loop iteration (one Philox draw serves two substeps);
-                                      // 2 measured 2 % slower (10.67 vs 10.45 ms per 1M-env step, two envs per thread)
+#define STG_SUBSTEP_PAIR_UNROLL 1     // thermal fast path: substep pairs per loop iteration;
+                                      // 2 measured 5 % slower (9.70 vs 9.21 ms per 1M-env step, two envs per thread)
 #endif
 constexpr int kSubstepPairUnroll = STG_SUBSTEP_PAIR_UNROLL;
 #ifndef STG_REF_SUBSTEP_UNROLL
@@ -60,45 +60,13 @@ STG_HD int pulse_safe_substeps(int n, double dt, double t_pulse, double t_end) {
     const double qd = t_pulse / dt - 2.0;
     return qd < 0.0 ? 0 : (qd > (double)n ? n : (int)qd);
 }
-// Noise source of integrate_thermal: the in-kernel stream, one per lane. first(g, nz) / second(g, nz): the 12 samples per lane
-// (already scaled) of substep 2g / 2g+1, always called in that order. One draw of three Philox blocks serves the pair: blocks
-// 3g and 3g+1 are evaluated for the first substep (6 of their 8 words), the two remaining words are carried to the second, which
-// adds block 3g+2 - so only 12 samples per lane are live at a time. (stt_kernels.cu has a second source: samples produced by
-// other warps of the CTA and handed over through shared memory.)
-template <typename P>
-struct PhiloxSource {
-    NoiseStream ns[Ln<P>::N];
-    P nscale;
-    uint32_t carry[2][Ln<P>::N];
-    STG_HD void first(uint32_t g, P* nz) {
-        constexpr int NL = Ln<P>::N;
-        uint32_t w[8][NL];
-        philox_block<NL>(ns, 3u * g, w);
-        philox_block<NL>(ns, 3u * g + 1u, w + 4);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) box_muller16<P>(w[k], nscale, nz[2 * k], nz[2 * k + 1]);
-#pragma unroll
-        for (int l = 0; l < NL; ++l) { carry[0][l] = w[6][l]; carry[1][l] = w[7][l]; }
-    }
-    STG_HD void second(uint32_t g, P* nz) {
-        constexpr int NL = Ln<P>::N;
-        uint32_t w[4][NL];
-        philox_block<NL>(ns, 3u * g + 2u, w);
-        box_muller16<P>(carry[0], nscale, nz[0], nz[1]);
-        box_muller16<P>(carry[1], nscale, nz[2], nz[3]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) box_muller16<P>(w[k], nscale, nz[4 + 2 * k], nz[5 + 2 * k]);
-    }
-};
 // The envs of one thread through the thermal fast path: P = float (one env) or F2 (two envs in the halves of 64-bit register
 // pairs on packed FFMA2 / FMUL2 / FADD2). Every operation is an explicit IEEE op per lane and every lane draws from its own
 // stream, so an env gets the same bits whatever it is paired with: lanes may have different substep counts - a finished lane is
 // frozen (its state is restored after every further substep of its partner). m: [lanes][3] in / out; traj: P = float only.
-// fast_to / n_run: optional overrides shared by a group of threads that must run the same number of substep pairs (the
-// warp-specialised kernel): substep pairs below fast_to take the plain path in every thread, and the loop runs to n_run.
 template <typename P, typename SRC>
 STG_HD void integrate_thermal(const ThermalEnv* E, SRC& src, double (*m)[3], int* guard, double* traj = nullptr,
-                              int64_t traj_rows = 0x7fffffff, int fast_to_all = -1, int n_run = -1) {
+                              int64_t traj_rows = 0x7fffffff) {
     using L = Ln<P>;
     constexpr int NL = L::N;
     ThermalConsts<P> tc;
@@ -118,8 +86,6 @@ STG_HD void integrate_thermal(const ThermalEnv* E, SRC& src, double (*m)[3], int
         n_max = E[l].n > n_max ? E[l].n : n_max;
         fast_to = i_safe[l] < fast_to ? i_safe[l] : fast_to;
     }
-    if (fast_to_all >= 0) fast_to = fast_to_all;
-    if (n_run >= 0) n_max = n_run;
     if (traj) { traj[0] = m[0][0]; traj[1] = m[0][1]; traj[2] = m[0][2]; }
     // exact FP64 renormalisation of lane l's f + e
     auto renorm = [&](int l) {
@@ -187,7 +153,7 @@ STG_HD void integrate_thermal(const ThermalEnv* E, SRC& src, double (*m)[3], int
             }
         }
     };
-    // one draw (three Philox blocks per lane) serves the substep pair (2g, 2g+1)
+    // the substep pair (2g, 2g+1): two draws of 12 samples per lane from the thermal stream
     int g = 0;
     const int g_fast = fast_to / 2, g_end = (n_max + 1) / 2;
 #pragma unroll kSubstepPairUnroll
@@ -202,8 +168,10 @@ STG_HD void integrate_thermal(const ThermalEnv* E, SRC& src, double (*m)[3], int
         P nz[12];
         src.first((uint32_t)g, nz);
         substep_edge(2 * g, nz);
-        src.second((uint32_t)g, nz);        // always taken: the hand-over of the shared-memory source counts on it
-        if (2 * g + 1 < n_max) substep_edge(2 * g + 1, nz);
+        if (2 * g + 1 < n_max) {
+            src.second((uint32_t)g, nz);
+            substep_edge(2 * g + 1, nz);
+        }
     }
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
@@ -234,7 +202,8 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
 
     if constexpr (FAST && NOISE == 1) {
         ThermalEnv E{f, J, dt, t_pulse, t_end, n, ns};
-        PhiloxSource<float> src{{ns}, thermal_nscale(f, dt), {}};
+        ThermalSource<float> src;
+        src.init(&ns, thermal_nscale(f, dt));
         double w[1][3] = {{mx, my, mz}};
         integrate_thermal<float>(&E, src, w, &guard, traj, traj_rows);
         mx = w[0][0]; my = w[0][1]; mz = w[0][2];
@@ -324,23 +293,22 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
         };
         int i = 0;
         if constexpr (NOISE == 1 && !EULER) {
+            ThermalSource<float> src;
+            src.init(&ns, nscale);
 #pragma unroll 1
-            for (; i + 1 < n; i += 2) {
-                float z[24];
-                philox_normals24<float>(&ns, (uint32_t)i >> 1, nscale, z);
-                R nz[24];
-#pragma unroll
-                for (int q = 0; q < 24; ++q) nz[q] = (R)z[q];
-                one(i, nz);
-                one(i + 1, nz + 12);
-            }
-            for (; i < n; ++i) {
+            for (; i < n; i += 2) {
                 float z[12];
-                philox_normals12<float>(&ns, (uint32_t)i, nscale, z);
                 R nz[12];
+                src.first((uint32_t)i >> 1, z);
 #pragma unroll
                 for (int q = 0; q < 12; ++q) nz[q] = (R)z[q];
                 one(i, nz);
+                if (i + 1 < n) {
+                    src.second((uint32_t)i >> 1, z);
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) nz[q] = (R)z[q];
+                    one(i + 1, nz);
+                }
             }
         } else {
 #pragma unroll kRefSubstepUnroll
@@ -682,7 +650,9 @@ STG_HD int env_step_pair_body(const StgSttStepArgs& a, int64_t eA, int64_t eB, E
                  make_stream(a.seed, a.env_offset + (uint64_t)eB, (uint32_t)a.state.episode[eB], (uint32_t)cb.step)}};
             double w[2][3] = {{ca.w[0], ca.w[1], ca.w[2]}, {cb.w[0], cb.w[1], cb.w[2]}};
             int g[2] = {ca.guard, cb.guard};
-            PhiloxSource<F2> src{{E[0].ns, E[1].ns}, mk2(thermal_nscale(ca.f, ca.plan.dt), thermal_nscale(cb.f, cb.plan.dt)), {}};
+            ThermalSource<F2> src;
+            const NoiseStream nss[2] = {E[0].ns, E[1].ns};
+            src.init(nss, mk2(thermal_nscale(ca.f, ca.plan.dt), thermal_nscale(cb.f, cb.plan.dt)));
             integrate_thermal<F2>(E, src, w, g);
             ca.w[0] = w[0][0]; ca.w[1] = w[0][1]; ca.w[2] = w[0][2]; ca.guard = g[0];
             cb.w[0] = w[1][0]; cb.w[1] = w[1][1]; cb.w[2] = w[1][2]; cb.guard = g[1];
@@ -791,13 +761,16 @@ STG_HD void integrate_grid(const double* f, double J, double& mx, double& my, do
     const float nscale = -1.3862943611198906f * (float)c.cth * (float)c.cth;
     ScaledState st{mx, my, mz, 1.0, 1.0, 1.0f};
     if (traj) { traj[0] = mx; traj[1] = my; traj[2] = mz; }
+    ThermalSource<float> src;
+    if (NOISE == 1 && !EULER) src.init(&ns, nscale);
     for (int i = 0; i < n; ++i) {
         const int64_t r = i < grid_rows ? i : grid_rows - 1;
         double nz[NS];
         if (NOISE == 1) {
             float z[12];
             if (EULER) philox_normals3(ns, (uint32_t)i, nscale, z);
-            else philox_normals12<float>(&ns, (uint32_t)i, nscale, z);
+            else if (i & 1) src.second((uint32_t)i >> 1, z);
+            else src.first((uint32_t)i >> 1, z);
 #pragma unroll
             for (int q = 0; q < NS; ++q) nz[q] = (double)z[q];
         } else if (NOISE == 2) {

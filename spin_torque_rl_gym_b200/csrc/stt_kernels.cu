@@ -27,14 +27,11 @@ namespace stg {
 #define STG_MINBLOCKS_DET 12    // no-noise variants: 80 registers, 24 warps/SM measured best (profiles/)
 #endif
 #ifndef STG_MINBLOCKS_NOISE
-#define STG_MINBLOCKS_NOISE 1   // FP64-stage thermal variants: let ptxas keep the 12 Gaussians + Philox state in registers
+#define STG_MINBLOCKS_NOISE 1   // FP64-stage thermal variants: let ptxas keep the 12 Gaussians + generator state in registers
 #endif
 #ifndef STG_MINBLOCKS_NOISE_F32
-// FP32 thermal variants: the substep loop is unrolled by four (STG_SUBSTEP_UNROLL, stt_env_core.cuh) so that the Philox rounds of
-// the following substeps can be scheduled under the dependent stage chain of the current one; unrolled, ptxas would take ~146
-// registers (14 warps/SM), so the kernel is held at 128 (16 warps/SM, no spill). 1M envs x 999 substeps: 14.17 ms plain; unroll 2:
-// 13.94 ms at 146 registers, 13.71 ms at 128; unroll 3 at 128: 13.87; unroll 4: 14.11 ms at 148 registers, 13.56 ms at 128;
-// unroll 8 at 128: 15.9 ms (instruction cache).
+// FP32 thermal variants (one env per thread): 106 registers at 8 CTAs (16 warps) per SM, no spills; 10 / 12 CTAs per SM (93 / 80
+// registers, the latter spilling) measured 9.50 / 9.35 ms against 9.31 per 1M-env x 999-substep step.
 #define STG_MINBLOCKS_NOISE_F32 8
 #endif
 constexpr int kBlock = STG_BLOCK;   // 64: 65,536 envs -> 1024 CTAs = 6.9 per SM, balanced to 1.2 % on 148 SMs
@@ -149,10 +146,12 @@ __device__ __forceinline__ void accumulate_stats(double* v, const EnvStepResult&
 #define STG_PAIR_MINBLOCKS 8
 #endif
 #ifndef STG_PAIR_THERMAL_MIN_ENVS
-#define STG_PAIR_THERMAL_MIN_ENVS (1 << 19)
+#define STG_PAIR_THERMAL_MIN_ENVS (1 << 18)
 #endif
 #ifndef STG_PAIR_MINBLOCKS_TH
-#define STG_PAIR_MINBLOCKS_TH 8
+// thermal pair kernel: 154 registers without spills at 6 CTAs (12 warps) per SM: 8.83 ms per 1M-env x 999-substep step; held at
+// 128 registers (8 CTAs) it spills 40 bytes: 9.21 ms; 5 CTAs (166 registers): 9.26 ms
+#define STG_PAIR_MINBLOCKS_TH 6
 #endif
 template <int NOISE>
 __global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : STG_PAIR_MINBLOCKS_TH) stt_env_step_pair_kernel(const __grid_constant__ StepArgs a) {
@@ -212,204 +211,8 @@ __global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : STG_
     }
 }
 
-#ifdef STG_THERMAL_WS
-// ---- warp-specialised thermal step: the noise is produced by other warps than the ones that integrate ----------------------
-// FP32 stages, e = z^, RK4, in-kernel noise stream (the headline configuration). One CTA = 4 warps = 64 K envs:
-//   one consumer warp      2K envs per thread as K packed pairs (FFMA2 / FMUL2 / FADD2): prologue, integrate_thermal, epilogue.
-//                          The K pairs are independent dependency chains, which the in-order issue of the warp interleaves.
-//   three producer warps   producer j evaluates Philox block 3g+j of substep pair g for the 2K envs of consumer thread u (its
-//                          lane), turns the words into packed Box-Muller pairs and stores them as float4 into a double-buffered
-//                          shared-memory ring (12 K float4 per consumer thread and substep pair)
-// Idea: a single instruction stream per env (stt_env_step_pair_kernel<1>) leaves the issue slots half empty - the dependent stage
-// chain (FMA pipe), the Philox rounds (FMA-heavy + ALU) and Box-Muller (quarter-rate XU) of ONE warp only overlap as far as the
-// static schedule interleaves them, at 4 warps per scheduler; split over warps, the hardware scheduler interleaves them. The
-// samples an env integrates are bit-identical to the other kernels. MEASURED (round 2, profiles/README.md): slower than the
-// two-envs-per-thread kernel (11.5 vs 10.4 ms per 1M-env step): the lone consumer warp of a scheduler issues one packed
-// instruction per ~3.5 cycles (dependent chain, 4.4-cycle FFMA2 latency) and everything else waits for it at the barriers; two
-// packs per consumer thread (K = 2) is not scalarised by the compiler. Kept compiled out (-DSTG_THERMAL_WS) as the record.
-// Hand-over: named barriers FULL[b] (the producer threads arrive, the 32 consumer threads wait) and EMPTY[b] (the reverse), b = g & 1.
-#ifndef STG_WS_PACKS
-#define STG_WS_PACKS 1
-#endif
-#ifndef STG_WS_MINBLOCKS
-#define STG_WS_MINBLOCKS 4
-#endif
-constexpr int kWsPacks = STG_WS_PACKS;
-constexpr int kWsLanes = 2 * kWsPacks;                 // envs per consumer thread
-constexpr int kWsEnvs = 32 * kWsLanes;                 // envs per CTA
-constexpr int kWsThreads = 128;
-typedef FN<kWsPacks> WsPack;
-struct WsEnvInfo {
-    uint32_t c0, c1, c2, c3;
-    float nscale;
-};
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-struct SmemNoiseSource {      // integrate_thermal's noise source in the consumer warp
-    const float4* buf;        // [2][12][kWsPacks][32]
-    int lane;
-    __device__ __forceinline__ void load6(const float4* p, WsPack* nz) const {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-#pragma unroll
-            for (int i = 0; i < kWsPacks; ++i) {
-                const float4 v = p[(k * kWsPacks + i) * 32];
-                nz[2 * k].p[i] = mk2(v.x, v.y);
-                nz[2 * k + 1].p[i] = mk2(v.z, v.w);
-            }
-        }
-    }
-    __device__ __forceinline__ void first(uint32_t g, WsPack* nz) const {
-        const int b = (int)(g & 1u);
-        named_bar_sync(1 + b, kWsThreads);                   // FULL[b]
-        load6(buf + b * 12 * kWsPacks * 32 + lane, nz);
-    }
-    __device__ __forceinline__ void second(uint32_t g, WsPack* nz) const {
-        const int b = (int)(g & 1u);
-        load6(buf + (b * 12 + 6) * kWsPacks * 32 + lane, nz);
-        named_bar_arrive(3 + b, kWsThreads);                 // EMPTY[b]
-    }
-};
-
-__global__ void __launch_bounds__(kWsThreads, STG_WS_MINBLOCKS) stt_env_step_ws_kernel(const __grid_constant__ StepArgs a) {
-    __shared__ __align__(16) float4 s_noise[2 * 12 * kWsPacks * 32];
-    __shared__ __align__(16) float s_obs[kWsEnvs * kObs];
-    __shared__ WsEnvInfo s_info[kWsEnvs];
-    __shared__ int s_run[2];                                  // fast_to (substeps every lane takes on the plain path), n_run
-    const int role = threadIdx.x >> 5;           // warp 0: consumer; warps 1..3: producers of Philox block role - 1
-    const bool consumer = role == 0;
-    const int tid = threadIdx.x & 31;            // lane: consumer thread `tid` owns envs kWsLanes tid .. kWsLanes tid + kWsLanes - 1
-    const int64_t base = (int64_t)blockIdx.x * kWsEnvs;
-    const bool sorted = (a.flags & STG_F_SORTED) != 0;
-    const bool want_fin = (a.flags & STG_F_AUTORESET) != 0 && a.out.final_obs != nullptr;
-
-    EnvStepCtx cx[kWsLanes];
-    ThermalEnv E[kWsLanes];
-    int64_t e[kWsLanes];
-    bool act[kWsLanes], thermal[kWsLanes];
-    if (consumer) {
-        int fast_to = 0x7fffffff, n_run = 0;
-#pragma unroll
-        for (int l = 0; l < kWsLanes; ++l) {
-            const int64_t slot = base + kWsLanes * tid + l;
-            act[l] = slot < a.n_envs;
-            thermal[l] = false;
-            e[l] = act[l] ? (sorted ? (int64_t)a.d_perm[slot] : slot) : 0;
-            WsEnvInfo info{0u, 0u, 0u, 0u, 0.0f};
-            E[l] = ThermalEnv{a.d_table[0].v, 0.0, 1.0, 0.0, 0.0, 0, NoiseStream{}};        // frozen lane
-            if (act[l]) {
-                env_step_prologue<float, true>(a, e[l], cx[l]);
-                thermal[l] = cx[l].valid && cx[l].f[FI_HTH] > 0.0;
-                if (thermal[l]) {
-                    const NoiseStream ns = make_stream(a.seed, a.env_offset + (uint64_t)e[l], (uint32_t)a.state.episode[e[l]],
-                                                       (uint32_t)cx[l].step);
-                    E[l] = ThermalEnv{cx[l].f, cx[l].J, cx[l].plan.dt, cx[l].T, cx[l].T, cx[l].plan.n, ns};
-                    info = WsEnvInfo{ns.c0, ns.c1, ns.c2, ns.c3, thermal_nscale(cx[l].f, cx[l].plan.dt)};
-                } else if (cx[l].valid) {
-                    env_step_integrate<float, true, 1, false>(a, e[l], cx[l]);      // parameter set without thermal field
-                }
-            }
-            s_info[kWsLanes * tid + l] = info;
-            const int safe = pulse_safe_substeps(E[l].n, E[l].dt, E[l].t_pulse, E[l].t_end);
-            fast_to = safe < fast_to ? safe : fast_to;
-            n_run = E[l].n > n_run ? E[l].n : n_run;
-        }
-        fast_to = __reduce_min_sync(0xffffffffu, fast_to);
-        n_run = __reduce_max_sync(0xffffffffu, n_run);
-        if (tid == 0) { s_run[0] = fast_to < 0 ? 0 : fast_to; s_run[1] = n_run; }
-    }
-    __syncthreads();
-    const int n_run = s_run[1];
-    const int g_end = (n_run + 1) / 2;
-    if (consumer) {
-        double w[kWsLanes][3];
-        int guard[kWsLanes];
-#pragma unroll
-        for (int l = 0; l < kWsLanes; ++l) {
-            w[l][0] = thermal[l] ? cx[l].w[0] : 0.0; w[l][1] = thermal[l] ? cx[l].w[1] : 0.0; w[l][2] = thermal[l] ? cx[l].w[2] : 1.0;
-            guard[l] = thermal[l] ? cx[l].guard : 0;
-        }
-        SmemNoiseSource src{s_noise, tid};
-        integrate_thermal<WsPack>(E, src, w, guard, nullptr, 0x7fffffff, s_run[0], n_run);
-#pragma unroll
-        for (int l = 0; l < kWsLanes; ++l)
-            if (thermal[l]) { cx[l].w[0] = w[l][0]; cx[l].w[1] = w[l][1]; cx[l].w[2] = w[l][2]; cx[l].guard = guard[l]; }
-    } else {
-        const int j = role - 1, u = tid;
-        NoiseStream ns[kWsLanes];
-        WsPack nscale;
-        const Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
-#pragma unroll
-        for (int l = 0; l < kWsLanes; ++l) {
-            const WsEnvInfo inf = s_info[kWsLanes * u + l];
-            ns[l] = NoiseStream{ph, inf.c0, inf.c1, inf.c2, inf.c3};
-            Ln<WsPack>::set(nscale, l, inf.nscale);
-        }
-        for (int g = 0; g < g_end; ++g) {
-            const int b = g & 1;
-            uint32_t wd[4][kWsLanes];
-            philox_block<kWsLanes>(ns, 3u * (uint32_t)g + (uint32_t)j, wd);
-            WsPack n0[4], n1[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) box_muller16<WsPack>(wd[q], nscale, n0[q], n1[q]);
-            if (g >= 2) named_bar_sync(3 + b, kWsThreads);           // EMPTY[b]: the consumers have read substep pair g - 2
-            float4* out = s_noise + (b * 12 + 4 * j) * kWsPacks * 32 + u;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                for (int i = 0; i < kWsPacks; ++i)
-                    out[(q * kWsPacks + i) * 32] = make_float4(n0[q].p[i].x, n0[q].p[i].y, n1[q].p[i].x, n1[q].p[i].y);
-            }
-            named_bar_arrive(1 + b, kWsThreads);                     // FULL[b]
-        }
-        // take the consumers' last EMPTY arrivals so that every barrier phase is complete at exit
-        for (int g = g_end > 2 ? g_end - 2 : 0; g < g_end; ++g) named_bar_sync(3 + (g & 1), kWsThreads);
-    }
-
-    EnvStepResult r[kWsLanes];
-    if (consumer) {
-#pragma unroll
-        for (int l = 0; l < kWsLanes; ++l) {
-            r[l].did_reset = false;
-            if (!act[l]) continue;
-            env_step_epilogue(a, e[l], cx[l], r[l]);
-            if (sorted) {
-                store_row(a.out.obs + e[l] * kObs, r[l].obs);
-            } else {
-#pragma unroll
-                for (int q = 0; q < kObs; ++q) s_obs[(kWsLanes * tid + l) * kObs + q] = r[l].obs[q];
-            }
-            if (want_fin && r[l].did_reset) store_row(a.out.final_obs + e[l] * kObs, r[l].final_obs);
-        }
-    }
-    if (!sorted) {
-        __syncthreads();
-        const int64_t rows = (a.n_envs - base) < kWsEnvs ? (a.n_envs - base) : kWsEnvs;
-        const int n4 = (int)(rows * kObs / 4);
-        float4* dst = reinterpret_cast<float4*>(a.out.obs + base * kObs);
-        const float4* srcp = reinterpret_cast<const float4*>(s_obs);
-        for (int q = threadIdx.x; q < n4; q += kWsThreads) dst[q] = srcp[q];
-    }
-    if (a.out.stats && consumer) {
-        double v[STG_NSTATS];
-#pragma unroll
-        for (int q = 0; q < STG_NSTATS; ++q) v[q] = 0.0;
-#pragma unroll
-        for (int l = 0; l < kWsLanes; ++l)
-            if (act[l]) accumulate_stats(v, r[l]);
-#pragma unroll
-        for (int q = 0; q < STG_NSTATS; ++q) {
-            const double sum = warp_sum(v[q]);
-            if (tid == 0 && sum != 0.0) atomicAdd(a.out.stats + (blockIdx.x % STG_STAT_REPLICAS) * STG_NSTATS + q, sum);
-        }
-    }
-}
-
-#endif  // STG_THERMAL_WS
+// (A warp-specialised variant of the thermal step - three producer warps evaluating the noise into a shared-memory ring for one
+// consumer warp - was measured in round 2 and removed: 11.5 ms against 10.4 ms for the kernel above; profiles/README.md.)
 
 // ---- second pass of stg_stt_step_f32: the envs the FP32 stages declined, compacted, with FP64 stages ---------------------
 // Grid-stride over the list d_redo[STG_REDO_HEADER ..] (count in d_redo[0], written by the first pass on the same stream).
@@ -519,8 +322,7 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
         if (err != cudaSuccess) return err;
         if (noise == 0 && !(a.flags & STG_F_NO_PAIR)) {
             // two envs per thread, Blackwell packed FP32x2 arithmetic (bit-identical to the one-env-per-thread kernels).
-            // Measured (profiles/README.md): +12 % without thermal noise. With the Philox stream the packed variant needs
-            // 201 registers and loses (the integer Philox rounds do not pack), so it is not dispatched there.
+            // Measured (profiles/README.md): +12 % without thermal noise.
             const unsigned grid = (unsigned)((a.n_envs + 2 * kBlock - 1) / (2 * kBlock));
             stt_env_step_pair_kernel<0><<<grid, kBlock, 0, s>>>(a);
             err = cudaGetLastError();
@@ -533,16 +335,11 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
     if (axis_z) {
         if (sizeof(R) == 4 && noise == 1 && !(a.flags & STG_F_NO_PAIR) && a.n_envs >= STG_PAIR_THERMAL_MIN_ENVS) {
             // two envs per thread on packed FP32x2 arithmetic, one noise stream per lane (bit-identical to one env per thread).
-            // Measured (profiles/README.md, 999 substeps): it only wins when the GPU is many waves deep - 10.40 vs 10.53 ms at
-            // 1,048,576 envs, equal at 524,288 - and loses below (1.59 vs 1.38 ms at 131,072 envs, 0.59 vs 0.31 ms up to 16,384:
-            // half as many threads, each twice as long), so smaller batches take the one-env-per-thread kernel.
-#ifdef STG_THERMAL_WS      // experiment, slower as measured (profiles/README.md): noise produced by separate warps of the CTA
-            const unsigned grid = (unsigned)((a.n_envs + kWsEnvs - 1) / kWsEnvs);
-            stt_env_step_ws_kernel<<<grid, kWsThreads, 0, s>>>(a);
-#else
+            // Measured (profiles/README.md, 999 substeps): 8.78 vs 9.27 ms at 1,048,576 envs, 2.26 vs 2.36 at 262,144; below
+            // that the one-env-per-thread kernel has twice as many threads to fill the GPU with (1.33 vs 1.21 ms at 131,072
+            // envs, 0.42 vs 0.26 ms up to 16,384), so smaller batches take it.
             const unsigned grid = (unsigned)((a.n_envs + 2 * kBlock - 1) / (2 * kBlock));
             stt_env_step_pair_kernel<1><<<grid, kBlock, 0, s>>>(a);
-#endif
             return cudaGetLastError();
         }
         if (noise == 0) return launch_step2<R, true, 0>(a, s);

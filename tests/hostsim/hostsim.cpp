@@ -138,16 +138,25 @@ extern "C" void hostsim_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c
     Philox ph{k0, k1};
     ph(c0, c1, c2, c3, out);
 }
+// the 12 samples of substep `sub` of an env-step's thermal stream (sequential: the draws before it are made and dropped)
 extern "C" void hostsim_normals12(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t step, uint32_t sub, float* out) {
     const float unit = -1.3862943611198906f;
     const NoiseStream ns = make_stream(seed, gid, episode, step);
-    philox_normals12<float>(&ns, sub, unit, out);
+    ThermalSource<float> src;
+    src.init(&ns, unit);
+    for (uint32_t i = 0; i <= sub; ++i) {
+        if (i & 1) src.second(i >> 1, out); else src.first(i >> 1, out);
+    }
 }
-// the 24 samples of the substep pair (2g, 2g+1): must equal the two single-substep draws
-extern "C" void hostsim_normals24(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t step, uint32_t g, float* out) {
-    const float unit = -1.3862943611198906f;
-    const NoiseStream ns = make_stream(seed, gid, episode, step);
-    philox_normals24<float>(&ns, g, unit, out);
+// xoshiro128++ known-answer access for tests: n outputs from the given state
+extern "C" void hostsim_xoshiro(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, int n, uint32_t* out) {
+    Xoshiro128pp g{s0, s1, s2, s3};
+    for (int i = 0; i < n; ++i) out[i] = g.next();
+}
+// the seed state of an env-step's stream
+extern "C" void hostsim_stream_seed(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t step, uint32_t* out) {
+    const Xoshiro128pp g = seed_xoshiro(make_stream(seed, gid, episode, step));
+    out[0] = g.s0; out[1] = g.s1; out[2] = g.s2; out[3] = g.s3;
 }
 
 extern "C" int hostsim_llgs_rk45(const StgRk45Args* a) {

@@ -209,13 +209,52 @@ def test_philox_known_answers():
     assert list(out) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
 
 
-def test_philox_normals_moments():
+def _xoshiro128pp_py(state, n):
+    """xoshiro128++ 1.0 restated from its published definition (Blackman & Vigna): result = rotl(s0 + s3, 7) + s0; t = s1 << 9;
+    s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t; s3 = rotl(s3, 11)."""
+    M = 0xffffffff
+    rotl = lambda x, k: ((x << k) | (x >> (32 - k))) & M
+    s0, s1, s2, s3 = state
+    out = []
+    for _ in range(n):
+        out.append((rotl((s0 + s3) & M, 7) + s0) & M)
+        t = (s1 << 9) & M
+        s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t
+        s3 = rotl(s3, 11)
+    return out
+
+
+def test_xoshiro_known_answers_and_stream_seeding():
+    """The thermal stream of the RK4 paths: xoshiro128++ (checked against an independent restatement of the published algorithm,
+    incl. the first output of state (1, 2, 3, 4): rotl(5, 7) + 1 = 641), seeded from block 0 of the env-step's Philox stream."""
+    import ctypes as C
+    from tests.hostsim.harness import lib
+    out = (C.c_uint32 * 64)()
+    for st in ((1, 2, 3, 4), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8), (0xffffffff, 0, 0x80000000, 7)):
+        lib().hostsim_xoshiro(*st, 64, out)
+        assert list(out) == _xoshiro128pp_py(st, 64)
+    lib().hostsim_xoshiro(1, 2, 3, 4, 1, out)
+    assert out[0] == 641
+    seed4, ph4 = (C.c_uint32 * 4)(), (C.c_uint32 * 4)()
+    for seed, gid, ep, step in ((1234, 5, 2, 3), (0xdeadbeefcafe, (1 << 33) | 17, 4, 9)):
+        lib().hostsim_stream_seed(C.c_uint64(seed), C.c_uint64(gid), ep, step, seed4)
+        lib().hostsim_philox(seed & 0xffffffff, seed >> 32, gid & 0xffffffff, ep, step, (gid >> 32) << 20, ph4)
+        assert list(seed4) == list(ph4)
+    # distinct (env, episode, step) -> unrelated states
+    seen = set()
+    for gid in range(64):
+        for step in range(4):
+            lib().hostsim_stream_seed(C.c_uint64(7), C.c_uint64(gid), 0, step, seed4)
+            seen.add(tuple(seed4))
+    assert len(seen) == 256
+
+
+def test_thermal_stream_normals_moments():
     import ctypes as C
     from tests.hostsim.harness import lib
     buf = (C.c_float * 12)()
-    buf24 = (C.c_float * 24)()
     xs = []
-    for g in range(6000):
+    for g in range(6000):                       # substeps 7 / 8 of 6000 different env-steps
         lib().hostsim_normals12(C.c_uint64(1234), C.c_uint64(g), 2, 3, 7 + (g & 1), buf)
         xs.append(np.array(buf[:]))
     x = np.concatenate(xs)
@@ -227,12 +266,18 @@ def test_philox_normals_moments():
     pairs = np.stack(xs)
     c = np.corrcoef(pairs.T)
     assert np.abs(c - np.eye(12)).max() < 0.07
-    # one draw of three Philox blocks serves substeps 2g and 2g+1: identical to the two single-substep draws
-    for g in (0, 5, 499):
-        lib().hostsim_normals24(C.c_uint64(99), C.c_uint64(1 << 33 | 17), 4, 9, g, buf24)
-        for half in (0, 1):
-            lib().hostsim_normals12(C.c_uint64(99), C.c_uint64(1 << 33 | 17), 4, 9, 2 * g + half, buf)
-            assert np.array_equal(np.array(buf[:]), np.array(buf24[12 * half:12 * half + 12]))
+    # along ONE stream: consecutive substeps are uncorrelated, moments hold, and the stream is a pure function of its identity
+    ys = []
+    for sub in range(1500):
+        lib().hostsim_normals12(C.c_uint64(99), C.c_uint64(1 << 33 | 17), 4, 9, sub, buf)
+        ys.append(np.array(buf[:]))
+    y = np.stack(ys)
+    assert abs(y.mean()) < 4 / np.sqrt(y.size) and abs(y.var() - 1) < 0.05
+    assert np.abs(np.corrcoef(y[:-1].T, y[1:].T)[:12, 12:]).max() < 0.12          # lag-1 cross-correlation of the 12 components
+    lib().hostsim_normals12(C.c_uint64(99), C.c_uint64(1 << 33 | 17), 4, 9, 1499, buf)
+    assert np.array_equal(np.array(buf[:]), ys[-1])
+    lib().hostsim_normals12(C.c_uint64(99), C.c_uint64(1 << 33 | 18), 4, 9, 1499, buf)
+    assert not np.array_equal(np.array(buf[:]), ys[-1])
 
 
 @pytest.mark.parametrize("thermal", [False, True])
