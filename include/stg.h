@@ -43,7 +43,9 @@ extern "C" {
 #define STG_INT_EULER 1
 
 /* step flags */
-#define STG_F_THERMAL_PHILOX 0x01u   /* thermal field from the in-kernel Philox4x32-10 stream                     */
+#define STG_F_THERMAL_PHILOX 0x01u   /* thermal field from the in-kernel stream: Philox4x32-10 keyed by seed, counter =   *
+                                      * (global env id, episode, step, block); the RK4 paths seed one xoshiro128++ state  *
+                                      * per env-step from block 0 of it (llgs_core.cuh, ThermalSource)                    */
 #define STG_F_THERMAL_INJECT 0x02u   /* thermal field from the caller's noise tensor (parity / debugging)          */
 #define STG_F_AUTORESET 0x04u        /* envs that terminate/truncate are reset in the same call (SB3 VecEnv rule)  */
 #define STG_F_EULER 0x08u            /* SimpleLLGSSolver(method='euler') instead of 'rk4'                          */
@@ -51,6 +53,9 @@ extern "C" {
 #define STG_F_AXIS_Z 0x20u           /* caller asserts stg_stt_all_axis_z(): kernels drop structurally-zero terms   */
 #define STG_F_NO_PAIR 0x80u          /* stg_stt_step_f32: one env per thread instead of the packed two-envs-per-thread FFMA2
                                         kernel (identical results; for comparisons)                                 */
+#define STG_F_PAIR_ALWAYS 0x200u     /* stg_stt_step_f32 with STG_F_THERMAL_PHILOX: take the two-envs-per-thread kernel at every batch
+                                        size (by default it is dispatched from 262,144 envs, where it is the faster one; identical
+                                        results per env either way)                                                  */
 #define STG_F_ARRAY_ONE_WARP 0x100u  /* stg_array_step_f64: force the one-warp-per-array kernel (the default for 8 <= devices <= 128
                                       * is four arrays per warp, eight lanes each; both are bit-identical) */
 #define STG_F_VECTORIZED_PLAN 0x40u  /* stg_stt_solve_*: n = max(10, int(t_end/max_step)) — VectorizedSolver.solve_batch's step

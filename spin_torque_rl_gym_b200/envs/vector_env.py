@@ -59,7 +59,7 @@ class SpinTorqueVectorEnv:
         param_index: Optional[Any] = None,
         sort_by_substeps: Union[str, bool] = "auto",
         collect_stats: bool = True,
-        pair_kernel: bool = True,
+        pair_kernel: Any = True,
         host_outputs: bool = False,
     ):
         torch = _lib.require_cuda()
@@ -101,7 +101,11 @@ class SpinTorqueVectorEnv:
         self.autoreset = bool(autoreset)
         self.env_offset = int(env_offset)
         self.collect_stats = bool(collect_stats)
-        self.pair_kernel = bool(pair_kernel)       # FP32 / e=z / RK4: two envs per thread on packed FFMA2 (same results)
+        # FP32 / e=z / RK4: two envs per thread on packed FFMA2 (same results per env). True: where it is the faster kernel (always
+        # without the thermal stream, from 262,144 envs with it); 'always': at every batch size; False: one env per thread
+        if pair_kernel not in (True, False, "always"):
+            raise ValueError("pair_kernel must be True, False or 'always'")
+        self.pair_kernel = pair_kernel
         # host_outputs: obs / final_obs / reward / terminated / truncated live in PINNED HOST memory and the kernels write
         # them there directly (posted PCIe writes while the kernel runs) - for consumers on the CPU (SB3, NumPy policies).
         # step() then returns CPU tensors and synchronises the stream before returning. Default: CUDA tensors, no sync.
@@ -362,6 +366,8 @@ class SpinTorqueVectorEnv:
             flags |= _lib.F_AUTORESET
         if not self.pair_kernel:
             flags |= _lib.F_NO_PAIR
+        elif self.pair_kernel == "always":
+            flags |= _lib.F_PAIR_ALWAYS
         a = self._step_args()
         a.d_noise, a.noise_stride, a.d_perm = None, 0, None
         if noise is not None:

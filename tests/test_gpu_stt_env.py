@@ -23,8 +23,13 @@ def _dtype(name):
 
 
 def _make(n, prec, cuda_device, **kw):
+    """prec 'f32-pair': FP32 stages through the two-envs-per-thread kernels at every batch size (the thermal one is otherwise
+    dispatched only from 262,144 envs - it is the bench's headline kernel)."""
     from spin_torque_rl_gym_b200 import SpinTorqueVectorEnv
     kw.setdefault("autoreset", False)
+    if prec == "f32-pair":
+        prec = "f32"
+        kw.setdefault("pair_kernel", "always")
     return SpinTorqueVectorEnv(num_envs=n, device=cuda_device, dtype=_dtype(prec), **kw)
 
 
@@ -245,7 +250,7 @@ def test_fp32_second_pass_equals_fp64_mode(pair, cuda_device):
     assert st32["steps"] == st64["steps"] == n * len(acts) and st32["substeps"] == st64["substeps"]
 
 
-@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("prec", ["f32", "f32-pair", "f64"])
 def test_philox_switching_statistics(prec, cuda_device):
     """In-kernel RNG: start on the equator (m_z = 0), no current, 100 substeps. The sign of m_z is decided by the noise:
     P(m_z > 0) must sit inside the binomial 95 % CI, and Var(m_z) must match the oracle's (same experiment with NumPy noise)
@@ -454,15 +459,15 @@ def test_device_mix_param_index(cuda_device):
 
 @pytest.mark.parametrize("thermal", [False, True])
 def test_packed_pair_kernel_is_bit_identical(thermal, cuda_device):
-    """FP32 / e=z / RK4 dispatches two-envs-per-thread FFMA2 kernels (no noise: stt_env_step_pair_kernel; in-kernel noise stream:
-    the warp-specialised stt_env_step_ws_kernel, whose samples come from other warps through shared memory). They must reproduce
-    the one-env-per-thread kernel (FP32 outputs bit for bit, FP64 bookkeeping to 1e-12) for ragged substep counts, odd batch size,
-    auto-reset, sorted and unsorted launches)."""
+    """FP32 / e=z / RK4 has two-envs-per-thread FFMA2 kernels (stt_env_step_pair_kernel<0> without noise, <1> with the in-kernel
+    thermal stream - the bench's headline kernel, forced here at a small batch with pair_kernel='always'). Every output must
+    equal the one-env-per-thread kernel's bit for bit - FP32 and FP64 alike (the FP64 bookkeeping is contraction-proof) - for
+    ragged substep counts, an odd batch size, auto-reset, sorted and unsorted launches."""
     torch = _torch()
     n, jm = 4099, 1.1e-6
     m0, tgt, acts = _random_setup(n, 13, tmax=2e-9)
     res = {}
-    for pair in (True, False):
+    for pair in ("always", False):
         for sort in (False, True):
             env = _make(n, "f32", cuda_device, max_current=jm, include_thermal_fluctuations=thermal, autoreset=True,
                         max_steps=2, rng_seed=4, pair_kernel=pair, sort_by_substeps=sort)
@@ -476,13 +481,30 @@ def test_packed_pair_kernel_is_bit_identical(thermal, cuda_device):
     ref = res[(False, False)]
     for key, val in res.items():
         for x, y in zip(val[:-1], ref[:-1]):
-            if key[0] is False or x.dtype != torch.float64:
-                assert torch.equal(x, y), key            # same kernel (sorted or not), and every FP32 / flag output
-            else:
-                # FP64 bookkeeping (master renormalisation, reward) is compiled in a different inlining context in the packed
-                # kernel: FMA contraction may differ in the last bit
-                assert torch.allclose(x, y, rtol=1e-12, atol=1e-13), key
+            assert torch.equal(x, y), key
         assert torch.allclose(val[-1], ref[-1], rtol=1e-12)          # statistics: same values, different summation order
+
+
+def test_headline_thermal_kernel_at_dispatch_size_equals_one_env_per_thread(cuda_device):
+    """262,144 envs x 999 substeps with the thermal stream: the default dispatch takes stt_env_step_pair_kernel<1> (the bench's
+    kernel), pair_kernel=False the one-env-per-thread kernel; same bits per env, and the state stays on the unit sphere."""
+    torch = _torch()
+    n, jm = 1 << 18, 1.1e-6
+    rng = np.random.default_rng(31)
+    act = torch.from_numpy(np.stack([rng.uniform(-jm, jm, n), np.full(n, 1e-9)], 1).astype(np.float32)).to(cuda_device)
+    outs = []
+    for pair in (True, False):
+        env = _make(n, "f32", cuda_device, max_current=jm, include_thermal_fluctuations=True, rng_seed=77, pair_kernel=pair,
+                    autoreset=True)
+        env.reset(seed=5)
+        for _ in range(2):
+            o, r, te, tr, info = env.step(act)
+        assert int(info["n_sub"].min()) == 999 == int(info["n_sub"].max())
+        m = env.magnetization
+        assert float((m.norm(dim=1) - 1).abs().max()) < 1e-12
+        outs.append((o.clone(), r.clone(), te.clone(), m.clone(), info["final_observation"].clone()))
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
 
 
 def test_reset_seed_reproducibility_and_masked_reset(cuda_device):
@@ -521,7 +543,7 @@ def test_reset_seed_reproducibility_and_masked_reset(cuda_device):
         _make(2, "f32", cuda_device).step(act[:2])            # step before reset
 
 
-@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("prec", ["f32", "f32-pair", "f64"])
 def test_thermal_switching_probability(prec, cuda_device):
     """North-star statistical parity: start exactly on the +z pole, drive with a destabilising current; whether (and when) the
     magnetisation switches is decided by the thermal kicks that seed the transverse component (the switching time goes with the
