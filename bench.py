@@ -47,11 +47,11 @@ FLOP_RK4 = 301
 FLOP_RK4_THERMAL_EXECUTED = 232
 # one launch of the headline kernel at 1,048,576 envs x 999 substeps under `ncu --set full` (profiles/, condensed CSV):
 # dram__bytes_read.sum + dram__bytes_write.sum and the pipe utilisations (pct of peak sustained active)
-# (profiles/r02_ncu_stt_env_step_pair_f32_thermal1_xoshiro.csv; 84.6 MB read + 115.2 MB written: the FP64 state planes and the
+# (profiles/r02_ncu_stt_env_step_pair_f32_thermal1_xoshiro.csv; 85.8 MB read + 116.2 MB written: the FP64 state planes and the
 # per-step diagnostics make it 1.3x the 150 B per env-step of SURVEY 8(d); 23 GB/s, irrelevant against the FP32 pipes)
-NCU_TRAFFIC_BYTES = 199.8e6
-NCU_PIPES = {"fma": 51.5, "fma_heavy": 51.2, "xu": 65.7, "alu": 43.3, "fp64": 1.2, "issue_slots_busy": 59.2,
-             "warp_instructions_per_env_substep": 181.7}
+NCU_TRAFFIC_BYTES = 202.0e6
+NCU_PIPES = {"fma": 52.0, "fma_heavy": 51.7, "xu": 66.6, "alu": 40.6, "fp64": 1.2, "issue_slots_busy": 58.2,
+             "warp_instructions_per_env_substep": 176.0}
 BYTES_PER_ENV_STEP = 150       # algorithmic HBM bytes per env-step
 FP32_LANES_PER_SM, N_SM = 128, 148
 
