@@ -13,9 +13,10 @@
 namespace stg {
 
 #ifndef STG_RK45_MINBLOCKS
-// Occupancy sweep on the configs[2] mix (262,144 trajectories x 114 attempts, B200): min blocks 1 (184 registers, 8 warps/SM)
-// 3.99 ms; 5: 3.34; 6: 3.41; 7: 3.23; 8 (128 registers + 72 B spill, 16 warps/SM): 3.04; 10: 3.17; 12: 3.47; 16: 4.02 ms.
-// The kernel waits on dependent FP64 chains (ncu: `wait` 2.1 stalls per issue at 1.9 warps per scheduler), so warps beat registers.
+// Occupancy sweep on the configs[2] mix (262,144 trajectories x 114 attempts, B200, end of round 2, solve incl. the sort): min
+// blocks 6 (164 registers, no spill) 1.91 ms; 7: 1.82; 8 (128 registers, 16 warps/SM): 1.80; 9 / 10 (96 registers, 208 B stack):
+// 1.88 / 1.87; 12 (80 registers): 1.95. (Round 1, before the kernel was trimmed: 1: 3.99, 8: 3.04, 16: 4.02 ms.)
+// The kernel waits on dependent FP64 chains (ncu: `wait` 2.7 stalls per issue at 3.6 warps per scheduler), so warps beat registers.
 #define STG_RK45_MINBLOCKS 8
 #endif
 template <bool SEG>      // SEG: piecewise-constant control tables (StgRk45Args.d_seg_*) instead of pulse + constant field
