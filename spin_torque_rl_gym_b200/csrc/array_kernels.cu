@@ -289,6 +289,35 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
     double* gp0 = a.d_pattern + arr0 * nd * 3;
     const double* gt0 = a.d_target + arr0 * nd * 3;
     if (VEC) {
+#ifndef STG_ARRAY_NO_BULK
+        // bulk asynchronous copies global -> shared (cp.async.bulk = UBLKCP, completion on an mbarrier): the 2 x narr tensors of
+        // 3 nd doubles never pass through registers, so the load costs the warp ten instructions instead of 48 LDG.128 + 48
+        // STS.128 and their MIO-queue / long-scoreboard stalls (16 % of the stall samples of the LDG / STS form, profiles/)
+        __shared__ __align__(8) uint64_t s_bar;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const uint32_t bytes = (uint32_t)(3 * nd * sizeof(double));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * (uint32_t)narr * bytes) : "memory");
+#pragma unroll
+            for (int ar = 0; ar < kGroupsPerWarp; ++ar) {
+                if (ar < narr) {
+                    const uint32_t dp = (uint32_t)__cvta_generic_to_shared(smem + ar * per);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dp), "l"(gp0 + ar * 3 * nd), "r"(bytes), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dp + bytes), "l"(gt0 + ar * 3 * nd), "r"(bytes), "r"(bar) : "memory");
+                }
+            }
+        }
+        __syncwarp();
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+        }
+#else
         const int n2 = 3 * nd / 2;                   // 16-byte words per array and tensor
         const double2* gp2 = reinterpret_cast<const double2*>(gp0);
         const double2* gt2 = reinterpret_cast<const double2*>(gt0);
@@ -301,6 +330,7 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
                 for (int q = lane; q < n2; q += 32) { sp[q] = gp2[ar * n2 + q]; st[q] = gt2[ar * n2 + q]; }
             }
         }
+#endif
     } else {
         for (int ar = 0; ar < narr; ++ar)
             for (int q = lane; q < 3 * nd; q += 32) {
@@ -406,6 +436,7 @@ __global__ void __launch_bounds__(32, kArray8MinBlocks) array_step_kernel8(const
     }
     const unsigned bulk_bits = __ballot_sync(0xffffffffu, valid && bulk_pattern && l8 == 0);   // bit 8*ar: whole pattern of array ar
     if (VEC) {
+        // (a bulk asynchronous copy shared -> global of these rows was measured: no gain, 25.4 us either way)
         const int n2 = 3 * nd / 2;
         double2* gp2 = reinterpret_cast<double2*>(gp0);
         double2* go2 = reinterpret_cast<double2*>(a.d_obs + arr0 * nd * 6);
@@ -493,8 +524,10 @@ extern "C" int stg_array_step_f64(const StgArrayStepArgs* args, void* stream) {
     const auto aligned = [](const void* q, uintptr_t n) { return (reinterpret_cast<uintptr_t>(q) & (n - 1)) == 0; };
     if (nd >= 8 && nd <= 128 && !(a.flags & STG_F_ARRAY_ONE_WARP) && aligned(a.d_obs, 8) &&
         (!a.d_final_obs || aligned(a.d_final_obs, 8))) {
-        const size_t smem8 = sizeof(double) * ((size_t)stg::array8_stride(nd) * stg::kGroupsPerWarp - 8);   // <= 28.2 KB; the
-        // last group needs no trailing pad (8x8: 14,528 B + 1 KB reserved per CTA; 14 CTAs fit the 233,472 B of an SM)
+        // <= 28.2 KB; the last group needs no trailing pad (8x8: 14,528 B + 1 KB reserved per CTA; 14 CTAs fit the 233,472 B of an
+        // SM). The pad is 0..15 doubles depending on nd (0 at 10x12), so it is computed, not assumed.
+        const int tail_pad = stg::array8_stride(nd) - (7 * nd + (nd & 1));
+        const size_t smem8 = sizeof(double) * ((size_t)stg::array8_stride(nd) * stg::kGroupsPerWarp - (size_t)tail_pad);
         const unsigned grid = (unsigned)((a.n_arrays + stg::kGroupsPerWarp - 1) / stg::kGroupsPerWarp);
         const bool vec = nd % 2 == 0 && aligned(a.d_pattern, 16) && aligned(a.d_target, 16) && aligned(a.d_obs, 16) &&
                          (!a.d_final_obs || aligned(a.d_final_obs, 16));

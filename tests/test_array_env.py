@@ -155,11 +155,13 @@ def test_cuda_array_env_batch_vs_oracle_and_full_size(cuda_device):
 def test_cuda_array_kernels_bit_identical(mode, cuda_device):
     """The default kernel (four arrays per warp, eight lanes each: NumPy's pairwise accumulators live in the lanes) and the
     one-warp-per-array kernel produce the same bits: state, observation, reward, energy, similarity, flags, statistics.
-    Grids cover a multiple of 8 (8x8), remainders (3x3 = 8+1, 4x5 = 16+4, 10x12 = 120), both fall-back sizes (2x3 < 8,
-    12x12 > 128) and batches that are not a multiple of 4; auto-reset on, so reset draws are compared too."""
+    Grids cover a multiple of 8 (8x8), remainders (3x3 = 8+1, 4x5 = 16+4, 10x12 = 120), the device counts whose shared-memory
+    stride needs no padding (2x4, 4x6, 10x12: the last group's scratch ends exactly at the allocation), both fall-back sizes
+    (2x3 < 8, 12x12 > 128) and batches that are not a multiple of 4; auto-reset on, so reset draws are compared too."""
     import torch
     from spin_torque_rl_gym_b200 import SpinTorqueArrayVectorEnv
-    for size, n in (((8, 8), 1003), ((3, 3), 257), ((4, 5), 130), ((10, 12), 66), ((2, 3), 33), ((12, 12), 9)):
+    for size, n in (((8, 8), 1003), ((3, 3), 257), ((4, 5), 130), ((10, 12), 66), ((2, 4), 35), ((4, 6), 21), ((2, 3), 33),
+                    ((12, 12), 9)):
         rng = np.random.default_rng(100 * ["individual", "row", "column", "global"].index(mode) + 10 * size[0] + size[1])
         envs = [SpinTorqueArrayVectorEnv(num_envs=n, array_size=size, action_mode=mode, device=cuda_device, max_steps=3,
                                          rng_seed=7, autoreset=True, one_warp_kernel=flag) for flag in (False, True)]
