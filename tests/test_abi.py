@@ -142,3 +142,12 @@ def test_no_cpu_fallback_in_product_path():
         from spin_torque_rl_gym_b200 import SpinTorqueVectorEnv
         with pytest.raises(_lib.StgError):
             SpinTorqueVectorEnv(num_envs=4)
+
+
+def test_integration_stub_names_the_current_abi_version():
+    """INTEGRATION.md's binding stub asserts an ABI version: it must be the one the header and the package carry."""
+    import re
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"stg_abi_version\(\) == (\d+)", text)
+    hdr = re.search(r"#define STG_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "stg.h")).read())
+    assert m and hdr and int(m.group(1)) == int(hdr.group(1)) == _lib.ABI_VERSION
