@@ -402,6 +402,9 @@ def main():
                 del e
             variant("substeps_per_s_thermal_off", n_local, include_thermal_fluctuations=False)
             variant("substeps_per_s_65536_envs", 65536)
+            # same workload with every word of the thermal stream from Philox4x32-10 (thermal_stream='philox': counter-based down
+            # to the substep; the headline uses the default stream, xoshiro128++ seeded per env-step from that Philox stream)
+            variant("substeps_per_s_all_philox_stream", n_local, thermal_stream="philox")
             variant("substeps_per_s_f64_thermal", n_local // 4, dtype=torch.float64)
             variant("substeps_per_s_f64_thermal_off", n_local // 4, dtype=torch.float64, include_thermal_fluctuations=False)
             try:       # BASELINE configs[2], configs[3] and the ragged-duration variant of configs[1] (tools/bench_extra.py)
@@ -518,8 +521,13 @@ def main():
                 "algorithmic_flop_per_substep": flop_sub, "executed_flop_per_substep": FLOP_RK4_THERMAL_EXECUTED if executed else None,
                 "executed_tflops": executed, "executed_frac": executed / fp32_peak_theory if executed else None,
                 "substeps_per_launch": n_local * 999, "kernel_ms": kernel_ms,
+                # the thermal stream of the headline: xoshiro128++ seeded per env-step from the env-step's Philox4x32-10 stream;
+                # the same workload with every word from Philox4x32-10 (thermal_stream='philox', measured in extras at N = 1)
+                "thermal_stream": "xoshiro128++ seeded per env-step from Philox4x32-10 (default)" if thermal else None,
+                "frac_with_all_philox_stream": (extras["substeps_per_s_all_philox_stream"] * flop_sub / 1e12 / fp32_peak_theory
+                                                if "substeps_per_s_all_philox_stream" in extras else None),
                 # pipe utilisation and DRAM traffic of one launch at this size from the ncu --set full capture of the shipped kernel
-                # (profiles/r02_ncu_stt_env_step_pair_f32_thermal1.csv)
+                # (profiles/r02_ncu_stt_env_step_pair_f32_thermal1_xoshiro.csv)
                 "pipes_pct_from_ncu": NCU_PIPES if headline else None,
                 "traffic": NCU_TRAFFIC_BYTES if headline else None,
                 "hbm": {"achieved_gbs": n_local * BYTES_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9,

@@ -56,6 +56,9 @@ extern "C" {
 #define STG_F_PAIR_ALWAYS 0x200u     /* stg_stt_step_f32 with STG_F_THERMAL_PHILOX: take the two-envs-per-thread kernel at every batch
                                         size (by default it is dispatched from 262,144 envs, where it is the faster one; identical
                                         results per env either way)                                                  */
+#define STG_F_STREAM_PHILOX10 0x400u  /* stg_stt_step_*, with STG_F_THERMAL_PHILOX and RK4: every word of the thermal stream from
+                                        Philox4x32-10 (counter-based down to the substep: three blocks per two substeps) instead of
+                                        the default Philox-seeded xoshiro128++ expansion; 10.4 against 8.6 ms per 1M-env step     */
 #define STG_F_ARRAY_ONE_WARP 0x100u  /* stg_array_step_f64: force the one-warp-per-array kernel (the default for 8 <= devices <= 128
                                       * is four arrays per warp, eight lanes each; both are bit-identical) */
 #define STG_F_VECTORIZED_PLAN 0x40u  /* stg_stt_solve_*: n = max(10, int(t_end/max_step)) — VectorizedSolver.solve_batch's step

@@ -21,6 +21,7 @@ F_VECTORIZED_PLAN = 0x40
 F_NO_PAIR = 0x80
 F_ARRAY_ONE_WARP = 0x100
 F_PAIR_ALWAYS = 0x200
+F_STREAM_PHILOX10 = 0x400
 DEV_STT, DEV_SOT, DEV_VCMA = 0, 1, 2
 NSTATS = 8
 STAT_REPLICAS = 256      # include/stg.h STG_STAT_REPLICAS: the step kernels spread their atomics over this many copies

@@ -637,8 +637,8 @@ STG_HD Xoshiro128pp seed_xoshiro(const NoiseStream& ns) {
 }
 // Noise source of the RK4 integrators, one stream per lane of the pack. first(g, nz) / second(g, nz): the 12 samples per lane
 // (already scaled) of substep 2g / 2g+1, called strictly in that order from g = 0 (a trailing odd substep calls first() only).
-#ifndef STG_THERMAL_PHILOX10
-template <typename P>
+// GEN 0: the xoshiro stream above (default). GEN 1 (STG_F_STREAM_PHILOX10): every word from Philox4x32-10, below.
+template <typename P, int GEN = 0>
 struct ThermalSource {
     Xoshiro128pp st[Ln<P>::N];
     P nscale;
@@ -661,12 +661,11 @@ struct ThermalSource {
     STG_HD void first(uint32_t, P* nz) { draw12(nz); }
     STG_HD void second(uint32_t, P* nz) { draw12(nz); }
 };
-#else
-// -DSTG_THERMAL_PHILOX10: the whole stream from Philox4x32-10 (counter-based down to the substep; the round-2 record of
-// profiles/README.md). One draw of three blocks serves a substep pair: blocks 3g and 3g+1 are evaluated for the first substep
-// (6 of their 8 words), the two remaining words are carried to the second, which adds block 3g+2.
+// GEN 1: the whole stream from Philox4x32-10, counter-based down to the substep (the stream of the first half of round 2; 10.44
+// against 8.64 ms per 1M-env step, profiles/README.md). One draw of three blocks serves a substep pair: blocks 3g and 3g+1 are
+// evaluated for the first substep (6 of their 8 words), the two remaining words are carried to the second, which adds block 3g+2.
 template <typename P>
-struct ThermalSource {
+struct ThermalSource<P, 1> {
     NoiseStream ns[Ln<P>::N];
     P nscale;
     uint32_t carry[2][Ln<P>::N];
@@ -695,7 +694,6 @@ struct ThermalSource {
         for (int k = 0; k < 4; ++k) box_muller16<P>(w[k], nscale, nz[4 + 2 * k], nz[5 + 2 * k]);
     }
 };
-#endif
 
 // constants of the fast path in pack form (hi/lo pairs, see StepConsts)
 template <typename P>

@@ -183,7 +183,8 @@ STG_HD void integrate_thermal(const ThermalEnv* E, SRC& src, double (*m)[3], int
 }
 
 // Integrate n substeps of size dt from (mx,my,mz); pulse of density J on while t <= t_pulse (envs/spin_torque_env.py:442-443).
-// NOISE: 0 none, 1 Philox stream `ns`, 2 injected tensor [n][S][3]. traj: optional [n+1][3] FP64 rows.
+// NOISE: 0 none, 1 in-kernel stream `ns` (Philox-seeded xoshiro128++), 2 injected tensor [n][S][3], 3 in-kernel stream with every
+// word from Philox4x32-10 (STG_F_STREAM_PHILOX10; env step only). traj: optional [n+1][3] FP64 rows.
 template <typename R, bool AXIS_Z, int NOISE, bool EULER>
 STG_HD void integrate(const double* f, double J, double& mx, double& my, double& mz, int n, double dt, double t_pulse,
                       double t_end, const NoiseStream& ns, const double* noise_row, double* traj,
@@ -193,16 +194,18 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
     // injected noise: substeps beyond the caller's tensor reuse its last row instead of reading out of bounds
     auto nrow_of = [&](int i) { return (int64_t)(i < noise_rows ? i : noise_rows - 1); };
     constexpr bool TH = NOISE != 0;
+    constexpr bool STREAM = NOISE == 1 || NOISE == 3;
+    constexpr int GEN = NOISE == 3 ? 1 : 0;
     constexpr bool FAST = sizeof(R) == 4 && AXIS_Z && !EULER;          // rk4_fast / rk4_thermal (llgs_core.cuh)
     constexpr bool SCALED = sizeof(R) == 4 && AXIS_Z && !TH;            // block-scaled transverse pair
-    constexpr bool TRACK = FAST && NOISE != 1;                          // with the Philox stream parity is statistical
+    constexpr bool TRACK = FAST && !STREAM;                             // with the in-kernel stream parity is statistical
     constexpr int NS = EULER ? 3 : 12;
     const int i_safe = pulse_safe_substeps(n, dt, t_pulse, t_end);
     if (traj) { traj[0] = mx; traj[1] = my; traj[2] = mz; }
 
-    if constexpr (FAST && NOISE == 1) {
+    if constexpr (FAST && STREAM) {
         ThermalEnv E{f, J, dt, t_pulse, t_end, n, ns};
-        ThermalSource<float> src;
+        ThermalSource<float, GEN> src;
         src.init(&ns, thermal_nscale(f, dt));
         double w[1][3] = {{mx, my, mz}};
         integrate_thermal<float>(&E, src, w, &guard, traj, traj_rows);
@@ -248,7 +251,7 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
             }
         };
         int i = 0;
-        if constexpr (NOISE == 1) {
+        if constexpr (STREAM) {
             // handled by integrate_thermal above
         } else if constexpr (NOISE == 2) {
             for (; i < n; ++i) {
@@ -292,8 +295,8 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
             }
         };
         int i = 0;
-        if constexpr (NOISE == 1 && !EULER) {
-            ThermalSource<float> src;
+        if constexpr (STREAM && !EULER) {
+            ThermalSource<float, GEN> src;
             src.init(&ns, nscale);
 #pragma unroll 1
             for (; i < n; i += 2) {
@@ -314,7 +317,7 @@ STG_HD void integrate(const double* f, double J, double& mx, double& my, double&
 #pragma unroll kRefSubstepUnroll
             for (; i < n; ++i) {
                 R nz[NS];
-                if (NOISE == 1) {       // Euler
+                if (STREAM) {       // Euler
                     float z[4];
                     philox_normals3(ns, (uint32_t)i, nscale, z);
                     nz[0] = (R)z[0]; nz[1] = (R)z[1]; nz[2] = (R)z[2];
@@ -650,7 +653,7 @@ STG_HD int env_step_pair_body(const StgSttStepArgs& a, int64_t eA, int64_t eB, E
                  make_stream(a.seed, a.env_offset + (uint64_t)eB, (uint32_t)a.state.episode[eB], (uint32_t)cb.step)}};
             double w[2][3] = {{ca.w[0], ca.w[1], ca.w[2]}, {cb.w[0], cb.w[1], cb.w[2]}};
             int g[2] = {ca.guard, cb.guard};
-            ThermalSource<F2> src;
+            ThermalSource<F2, NOISE == 3 ? 1 : 0> src;
             const NoiseStream nss[2] = {E[0].ns, E[1].ns};
             src.init(nss, mk2(thermal_nscale(ca.f, ca.plan.dt), thermal_nscale(cb.f, cb.plan.dt)));
             integrate_thermal<F2>(E, src, w, g);

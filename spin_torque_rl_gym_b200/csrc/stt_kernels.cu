@@ -154,7 +154,7 @@ __device__ __forceinline__ void accumulate_stats(double* v, const EnvStepResult&
 #define STG_PAIR_MINBLOCKS_TH 6
 #endif
 template <int NOISE>
-__global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : STG_PAIR_MINBLOCKS_TH) stt_env_step_pair_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(kBlock, NOISE == 0 ? STG_PAIR_MINBLOCKS : (NOISE == 3 ? 8 : STG_PAIR_MINBLOCKS_TH)) stt_env_step_pair_kernel(const __grid_constant__ StepArgs a) {
     __shared__ __align__(16) float s_obs[2 * kBlock * kObs];
     __shared__ uint8_t s_skip[2 * kBlock];
     const int64_t base = (int64_t)blockIdx.x * (2 * kBlock);
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kBlock) stt_solve_grid_kernel(const __grid_con
 template <typename R, bool AXIS_Z, int NOISE>
 static cudaError_t launch_step2(const StepArgs& a, cudaStream_t s) {
     const unsigned grid = (unsigned)((a.n_envs + kBlock - 1) / kBlock);
-    if constexpr (sizeof(R) == 8) {      // Euler always runs FP64 stages (launch_step)
+    if constexpr (sizeof(R) == 8 && NOISE != 3) {      // Euler always runs FP64 stages (launch_step), noise from Philox blocks
         if (a.flags & STG_F_EULER) {
             stt_env_step_kernel<R, AXIS_Z, NOISE, true><<<grid, kBlock, 0, s>>>(a);
             return cudaGetLastError();
@@ -315,7 +315,9 @@ static cudaError_t launch_redo(const StepArgs& a, cudaStream_t s) {
 // 1e-4 contract there either, so Euler runs FP64 stages through both entry points as well.
 template <typename R>
 static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
-    const int noise = (a.flags & STG_F_THERMAL_INJECT) ? 2 : ((a.flags & STG_F_THERMAL_PHILOX) ? 1 : 0);
+    // 3: the in-kernel stream with every word from Philox4x32-10 (Euler draws from Philox blocks in either case)
+    const int noise = (a.flags & STG_F_THERMAL_INJECT) ? 2 : ((a.flags & STG_F_THERMAL_PHILOX)
+                      ? (((a.flags & STG_F_STREAM_PHILOX10) && !(a.flags & STG_F_EULER)) ? 3 : 1) : 0);
     if (sizeof(R) == 4 && (a.flags & STG_F_EULER)) return launch_step<double>(a, axis_z, s);
     if (step_uses_redo(a, sizeof(R) == 4, axis_z)) {
         cudaError_t err = cudaMemsetAsync(a.d_redo, 0, sizeof(int32_t) * STG_REDO_HEADER, s);
@@ -333,22 +335,25 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
         return noise == 0 ? launch_redo<0>(a, s) : launch_redo<2>(a, s);
     }
     if (axis_z) {
-        if (sizeof(R) == 4 && noise == 1 && !(a.flags & STG_F_NO_PAIR) &&
+        if (sizeof(R) == 4 && (noise == 1 || noise == 3) && !(a.flags & STG_F_NO_PAIR) &&
             (a.n_envs >= STG_PAIR_THERMAL_MIN_ENVS || (a.flags & STG_F_PAIR_ALWAYS))) {
             // two envs per thread on packed FP32x2 arithmetic, one noise stream per lane (bit-identical to one env per thread).
             // Measured (profiles/README.md, 999 substeps): 8.78 vs 9.27 ms at 1,048,576 envs, 2.26 vs 2.36 at 262,144; below
             // that the one-env-per-thread kernel has twice as many threads to fill the GPU with (1.33 vs 1.21 ms at 131,072
             // envs, 0.42 vs 0.26 ms up to 16,384), so smaller batches take it.
             const unsigned grid = (unsigned)((a.n_envs + 2 * kBlock - 1) / (2 * kBlock));
-            stt_env_step_pair_kernel<1><<<grid, kBlock, 0, s>>>(a);
+            if (noise == 3) stt_env_step_pair_kernel<3><<<grid, kBlock, 0, s>>>(a);
+            else stt_env_step_pair_kernel<1><<<grid, kBlock, 0, s>>>(a);
             return cudaGetLastError();
         }
         if (noise == 0) return launch_step2<R, true, 0>(a, s);
         if (noise == 1) return launch_step2<R, true, 1>(a, s);
+        if (noise == 3) return launch_step2<R, true, 3>(a, s);
         return launch_step2<R, true, 2>(a, s);
     }
     if (noise == 0) return launch_step2<double, false, 0>(a, s);
     if (noise == 1) return launch_step2<double, false, 1>(a, s);
+    if (noise == 3) return launch_step2<double, false, 3>(a, s);
     return launch_step2<double, false, 2>(a, s);
 }
 

@@ -61,6 +61,7 @@ class SpinTorqueVectorEnv:
         collect_stats: bool = True,
         pair_kernel: Any = True,
         host_outputs: bool = False,
+        thermal_stream: str = "xoshiro",
     ):
         torch = _lib.require_cuda()
         self._torch = torch
@@ -103,6 +104,12 @@ class SpinTorqueVectorEnv:
         self.collect_stats = bool(collect_stats)
         # FP32 / e=z / RK4: two envs per thread on packed FFMA2 (same results per env). True: where it is the faster kernel (always
         # without the thermal stream, from 262,144 envs with it); 'always': at every batch size; False: one env per thread
+        # in-kernel thermal stream of the RK4 paths. 'xoshiro' (default): one xoshiro128++ state per env-step, seeded from block 0
+        # of the env-step's Philox4x32-10 stream; 'philox': every word from Philox4x32-10 (counter-based down to the substep,
+        # ~20 % slower). Both are pure functions of (rng_seed, global env id, episode, step).
+        if thermal_stream not in ("xoshiro", "philox"):
+            raise ValueError("thermal_stream must be 'xoshiro' or 'philox'")
+        self.thermal_stream = thermal_stream
         if pair_kernel not in (True, False, "always"):
             raise ValueError("pair_kernel must be True, False or 'always'")
         self.pair_kernel = pair_kernel
@@ -381,6 +388,8 @@ class SpinTorqueVectorEnv:
             a.noise_stride = nz.shape[1]
         elif self.include_thermal and self.temperature > 0:
             flags |= _lib.F_THERMAL_PHILOX
+            if self.thermal_stream == "philox":
+                flags |= _lib.F_STREAM_PHILOX10
         stream = self._stream()
         with _lib.device_guard(torch, self.device):
             # 'auto': the counting sort costs three tiny launches; ragged pulse durations run ~2x faster sorted

@@ -46,7 +46,7 @@ class HostSimEnv:
     def __init__(self, num_envs, device_type="stt_mram", device_params=None, target_states=None, max_steps=100,
                  max_current=2e6, max_duration=5e-9, temperature=300.0, include_thermal_fluctuations=True,
                  success_threshold=0.9, energy_penalty_weight=0.1, f64=True, integrator="rk4", rng_seed=0,
-                 env_offset=0, autoreset=False, force_general=False, pair=True):
+                 env_offset=0, autoreset=False, force_general=False, pair=True, thermal_stream="xoshiro"):
         N = self.N = int(num_envs)
         if device_params is None:
             device_params = P.env_default_device_params(device_type)
@@ -61,6 +61,7 @@ class HostSimEnv:
         self.thermal = include_thermal_fluctuations and temperature > 0
         self.seed, self.env_offset, self.autoreset = rng_seed, env_offset, autoreset
         self.pair = pair
+        self.thermal_stream = thermal_stream
         tt = np.array([[0, 0, 1.0], [0, 0, -1.0]]) if target_states is None else \
             np.array([np.asarray(t, float) / np.linalg.norm(t) for t in target_states])
         self.target_table = np.ascontiguousarray(tt)
@@ -115,6 +116,7 @@ class HostSimEnv:
             flags |= _lib.F_THERMAL_INJECT; a.d_noise = _p(noise); a.noise_stride = noise.shape[1]
         elif self.thermal:
             flags |= _lib.F_THERMAL_PHILOX
+            if self.thermal_stream == "philox": flags |= _lib.F_STREAM_PHILOX10
         if perm is not None:
             perm = np.ascontiguousarray(perm, np.int32); flags |= _lib.F_SORTED; a.d_perm = _p(perm)
         a.d_table = _p(self.table); a.state = self._state(); a.d_action = _p(act)

@@ -34,8 +34,8 @@ static void step_all(const StgSttStepArgs& a) {
         const int64_t e = (a.flags & STG_F_SORTED) ? a.d_perm[s] : s;
         EnvStepResult r;
         bool done;
-        if (a.flags & STG_F_EULER)
-            done = env_step_body<R, AXIS_Z, NOISE, true>(a, e, r);
+        if ((a.flags & STG_F_EULER) && NOISE != 3)
+            done = env_step_body<R, AXIS_Z, NOISE == 3 ? 1 : NOISE, true>(a, e, r);
         else
             done = env_step_body<R, AXIS_Z, NOISE, false>(a, e, r);
         if (done) store_rows(a, e, r);
@@ -45,6 +45,7 @@ static void step_all(const StgSttStepArgs& a) {
 template <typename R, bool AXIS_Z>
 static void step_noise(const StgSttStepArgs& a) {
     if (a.flags & STG_F_THERMAL_INJECT) step_all<R, AXIS_Z, 2>(a);
+    else if ((a.flags & STG_F_THERMAL_PHILOX) && (a.flags & STG_F_STREAM_PHILOX10) && !(a.flags & STG_F_EULER)) step_all<R, AXIS_Z, 3>(a);
     else if (a.flags & STG_F_THERMAL_PHILOX) step_all<R, AXIS_Z, 1>(a);
     else step_all<R, AXIS_Z, 0>(a);
 }
@@ -79,7 +80,9 @@ extern "C" int hostsim_stt_step(const StgSttStepArgs* a, int f64) {
     if (a->flags & STG_F_EULER) f64 = 1;      // as launch_step<> dispatches: Euler always runs FP64 stages
     FtzScope ftz(!f64);
     if (!f64 && (a->flags & STG_F_AXIS_Z) && !(a->flags & (STG_F_THERMAL_INJECT | STG_F_EULER | STG_F_NO_PAIR))) {
-        if (a->flags & STG_F_THERMAL_PHILOX) step_pairs<1>(*a); else step_pairs<0>(*a);      // as launch_step<> dispatches
+        if ((a->flags & STG_F_THERMAL_PHILOX) && (a->flags & STG_F_STREAM_PHILOX10)) step_pairs<3>(*a);      // as launch_step<> dispatches
+        else if (a->flags & STG_F_THERMAL_PHILOX) step_pairs<1>(*a);
+        else step_pairs<0>(*a);
         return 0;
     }
     const bool z = (a->flags & STG_F_AXIS_Z) != 0;
@@ -139,14 +142,22 @@ extern "C" void hostsim_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c
     ph(c0, c1, c2, c3, out);
 }
 // the 12 samples of substep `sub` of an env-step's thermal stream (sequential: the draws before it are made and dropped)
-extern "C" void hostsim_normals12(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t step, uint32_t sub, float* out) {
+template <int GEN>
+static void normals12(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t step, uint32_t sub, float* out) {
     const float unit = -1.3862943611198906f;
     const NoiseStream ns = make_stream(seed, gid, episode, step);
-    ThermalSource<float> src;
+    ThermalSource<float, GEN> src;
     src.init(&ns, unit);
     for (uint32_t i = 0; i <= sub; ++i) {
         if (i & 1) src.second(i >> 1, out); else src.first(i >> 1, out);
     }
+}
+extern "C" void hostsim_normals12(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t step, uint32_t sub, float* out) {
+    normals12<0>(seed, gid, episode, step, sub, out);
+}
+// the same for the all-Philox stream (STG_F_STREAM_PHILOX10)
+extern "C" void hostsim_normals12_philox(uint64_t seed, uint64_t gid, uint32_t episode, uint32_t step, uint32_t sub, float* out) {
+    normals12<1>(seed, gid, episode, step, sub, out);
 }
 // xoshiro128++ known-answer access for tests: n outputs from the given state
 extern "C" void hostsim_xoshiro(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, int n, uint32_t* out) {

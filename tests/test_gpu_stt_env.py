@@ -30,6 +30,10 @@ def _make(n, prec, cuda_device, **kw):
     if prec == "f32-pair":
         prec = "f32"
         kw.setdefault("pair_kernel", "always")
+    if prec == "f32-pair-philox":           # ... and with every word of the stream from Philox4x32-10
+        prec = "f32"
+        kw.setdefault("pair_kernel", "always")
+        kw.setdefault("thermal_stream", "philox")
     return SpinTorqueVectorEnv(num_envs=n, device=cuda_device, dtype=_dtype(prec), **kw)
 
 
@@ -250,7 +254,7 @@ def test_fp32_second_pass_equals_fp64_mode(pair, cuda_device):
     assert st32["steps"] == st64["steps"] == n * len(acts) and st32["substeps"] == st64["substeps"]
 
 
-@pytest.mark.parametrize("prec", ["f32", "f32-pair", "f64"])
+@pytest.mark.parametrize("prec", ["f32", "f32-pair", "f32-pair-philox", "f64"])
 def test_philox_switching_statistics(prec, cuda_device):
     """In-kernel RNG: start on the equator (m_z = 0), no current, 100 substeps. The sign of m_z is decided by the noise:
     P(m_z > 0) must sit inside the binomial 95 % CI, and Var(m_z) must match the oracle's (same experiment with NumPy noise)
@@ -457,7 +461,7 @@ def test_device_mix_param_index(cuda_device):
         assert int(i1["status"].max()) == 0 and float((m_after - m0n[sel]).__abs__().max()) > 1e-6
 
 
-@pytest.mark.parametrize("thermal", [False, True])
+@pytest.mark.parametrize("thermal", [False, True, "philox"])
 def test_packed_pair_kernel_is_bit_identical(thermal, cuda_device):
     """FP32 / e=z / RK4 has two-envs-per-thread FFMA2 kernels (stt_env_step_pair_kernel<0> without noise, <1> with the in-kernel
     thermal stream - the bench's headline kernel, forced here at a small batch with pair_kernel='always'). Every output must
@@ -469,8 +473,9 @@ def test_packed_pair_kernel_is_bit_identical(thermal, cuda_device):
     res = {}
     for pair in ("always", False):
         for sort in (False, True):
-            env = _make(n, "f32", cuda_device, max_current=jm, include_thermal_fluctuations=thermal, autoreset=True,
-                        max_steps=2, rng_seed=4, pair_kernel=pair, sort_by_substeps=sort)
+            env = _make(n, "f32", cuda_device, max_current=jm, include_thermal_fluctuations=bool(thermal), autoreset=True,
+                        max_steps=2, rng_seed=4, pair_kernel=pair, sort_by_substeps=sort,
+                        thermal_stream="philox" if thermal == "philox" else "xoshiro")
             env.reset(options={"initial_state": m0, "target_state": tgt})
             out = []
             for a in acts + acts[:1]:
@@ -543,7 +548,7 @@ def test_reset_seed_reproducibility_and_masked_reset(cuda_device):
         _make(2, "f32", cuda_device).step(act[:2])            # step before reset
 
 
-@pytest.mark.parametrize("prec", ["f32", "f32-pair", "f64"])
+@pytest.mark.parametrize("prec", ["f32", "f32-pair", "f32-pair-philox", "f64"])
 def test_thermal_switching_probability(prec, cuda_device):
     """North-star statistical parity: start exactly on the +z pole, drive with a destabilising current; whether (and when) the
     magnetisation switches is decided by the thermal kicks that seed the transverse component (the switching time goes with the

@@ -280,7 +280,42 @@ def test_thermal_stream_normals_moments():
     assert not np.array_equal(np.array(buf[:]), ys[-1])
 
 
-@pytest.mark.parametrize("thermal", [False, True])
+def test_all_philox_stream_normals_and_block_layout():
+    """thermal_stream='philox' (STG_F_STREAM_PHILOX10): substep pair (2g, 2g+1) consumes Philox blocks 3g, 3g+1, 3g+2 of the
+    env-step's counter space, one 16 + 16 bit word per Box-Muller pair; moments as for the default stream."""
+    import ctypes as C
+    from tests.hostsim.harness import lib
+    buf = (C.c_float * 12)()
+    xs = []
+    for g in range(4000):
+        lib().hostsim_normals12_philox(C.c_uint64(1234), C.c_uint64(g), 2, 3, 7 + (g & 1), buf)
+        xs.append(np.array(buf[:]))
+    x = np.concatenate(xs)
+    assert abs(x.mean()) < 4 / np.sqrt(x.size) and abs(x.var() - 1) < 0.03 and abs((x ** 4).mean() - 3) < 0.2
+    assert np.abs(x).max() < 4.86
+    # words -> samples: the first pair of substep 0 comes from word 0 of block 0
+    seed, gid, ep, step = 99, (1 << 33) | 17, 4, 9
+    ph = (C.c_uint32 * 4)()
+    lib().hostsim_philox(seed & 0xffffffff, seed >> 32, gid & 0xffffffff, ep, step, ((gid >> 32) << 20) + 0, ph)
+    lib().hostsim_normals12_philox(C.c_uint64(seed), C.c_uint64(gid), ep, step, 0, buf)
+    w = ph[0]
+    u = ((w >> 16) + 0.5) / 65536.0
+    r, ang = np.sqrt(-2.0 * np.log(u)), 2 * np.pi * (w & 0xffff) / 65536.0
+    assert abs(buf[0] - r * np.cos(ang)) < 2e-3 and abs(buf[1] - r * np.sin(ang)) < 2e-3
+    # substep 1 starts with the two words carried from block 1 (words 2, 3)
+    lib().hostsim_philox(seed & 0xffffffff, seed >> 32, gid & 0xffffffff, ep, step, ((gid >> 32) << 20) + 1, ph)
+    lib().hostsim_normals12_philox(C.c_uint64(seed), C.c_uint64(gid), ep, step, 1, buf)
+    w = ph[2]
+    u = ((w >> 16) + 0.5) / 65536.0
+    r, ang = np.sqrt(-2.0 * np.log(u)), 2 * np.pi * (w & 0xffff) / 65536.0
+    assert abs(buf[0] - r * np.cos(ang)) < 2e-3 and abs(buf[1] - r * np.sin(ang)) < 2e-3
+    # and it is a different stream from the default one
+    b2 = (C.c_float * 12)()
+    lib().hostsim_normals12(C.c_uint64(seed), C.c_uint64(gid), ep, step, 1, b2)
+    assert not np.array_equal(np.array(buf[:]), np.array(b2[:]))
+
+
+@pytest.mark.parametrize("thermal", [False, True, "philox"])
 def test_pair_path_is_bit_identical_to_scalar_path(thermal):
     """Two envs per thread (FP32x2 pack) vs one env per thread: same IEEE operations per component, so bit-identical results,
     for ragged substep counts (partners finish at different substeps), odd batch sizes and a permuted launch."""
@@ -293,8 +328,8 @@ def test_pair_path_is_bit_identical_to_scalar_path(thermal):
     perm = rng.permutation(n).astype(np.int32)
     outs = []
     for pair in (True, False):
-        h = HostSimEnv(n, max_current=jm, include_thermal_fluctuations=thermal, f64=False, rng_seed=9, pair=pair,
-                       autoreset=True, max_steps=2)
+        h = HostSimEnv(n, max_current=jm, include_thermal_fluctuations=bool(thermal), f64=False, rng_seed=9, pair=pair,
+                       autoreset=True, max_steps=2, thermal_stream="philox" if thermal == "philox" else "xoshiro")
         h.reset(m0, tgt)
         res = []
         for s in range(3):
