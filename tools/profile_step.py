@@ -21,6 +21,8 @@ ap.add_argument("--dtype", default="f32")
 ap.add_argument("--tilted", action="store_true")
 ap.add_argument("--pulse", type=float, default=1e-9)
 ap.add_argument("--no-pair", action="store_true")
+ap.add_argument("--pair-always", action="store_true", help="two envs per thread at any batch size (STG_F_PAIR_ALWAYS)")
+ap.add_argument("--stream", default="xoshiro", choices=["xoshiro", "philox"])
 ap.add_argument("--no-sort", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -29,7 +31,7 @@ if a.tilted:
     p["easy_axis"] = np.array([0.2, -0.1, 1.0])
 env = SpinTorqueVectorEnv(num_envs=a.envs, device=dev, dtype=torch.float32 if a.dtype == "f32" else torch.float64,
                           device_params=p, max_current=1.1e-6, include_thermal_fluctuations=bool(a.thermal), rng_seed=1,
-                          pair_kernel=not a.no_pair, sort_by_substeps=False if a.no_sort else 'auto')
+                          pair_kernel=("always" if a.pair_always else not a.no_pair), thermal_stream=a.stream, sort_by_substeps=False if a.no_sort else 'auto')
 env.reset(seed=1)
 rng = np.random.default_rng(0)
 act = np.stack([rng.uniform(-1.1e-6, 1.1e-6, a.envs), np.full(a.envs, a.pulse)], 1).astype(np.float32)
