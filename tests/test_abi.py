@@ -151,3 +151,12 @@ def test_integration_stub_names_the_current_abi_version():
     m = re.search(r"stg_abi_version\(\) == (\d+)", text)
     hdr = re.search(r"#define STG_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "stg.h")).read())
     assert m and hdr and int(m.group(1)) == int(hdr.group(1)) == _lib.ABI_VERSION
+
+
+def test_flag_constants_of_the_binding_equal_the_header():
+    hdr = open(os.path.join(ROOT, "include", "stg.h")).read()
+    flags = re.findall(r"#define (STG_F_\w+) (0x[0-9a-fA-F]+)u", hdr)
+    assert len(flags) >= 11
+    for name, val in flags:
+        assert getattr(_lib, name[len("STG_"):]) == int(val, 16), name
+    assert len({int(v, 16) for _, v in flags}) == len(flags)          # no two flags share a bit
