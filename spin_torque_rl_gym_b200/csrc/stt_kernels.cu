@@ -335,8 +335,10 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
         return noise == 0 ? launch_redo<0>(a, s) : launch_redo<2>(a, s);
     }
     if (axis_z) {
+        // (all-Philox stream: the packed kernel only draws level at 524,288 envs - 5.24 vs 5.23 ms, 2.70 vs 2.65 at 262,144)
+        const int64_t pair_min_envs = noise == 3 ? 2 * (int64_t)STG_PAIR_THERMAL_MIN_ENVS : (int64_t)STG_PAIR_THERMAL_MIN_ENVS;
         if (sizeof(R) == 4 && (noise == 1 || noise == 3) && !(a.flags & STG_F_NO_PAIR) &&
-            (a.n_envs >= STG_PAIR_THERMAL_MIN_ENVS || (a.flags & STG_F_PAIR_ALWAYS))) {
+            (a.n_envs >= pair_min_envs || (a.flags & STG_F_PAIR_ALWAYS))) {
             // two envs per thread on packed FP32x2 arithmetic, one noise stream per lane (bit-identical to one env per thread).
             // Measured (profiles/README.md, 999 substeps): 8.78 vs 9.27 ms at 1,048,576 envs, 2.26 vs 2.36 at 262,144; below
             // that the one-env-per-thread kernel has twice as many threads to fill the GPU with (1.33 vs 1.21 ms at 131,072
