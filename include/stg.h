@@ -244,6 +244,10 @@ typedef struct StgSttSolveArgs {
 } StgSttSolveArgs;
 
 int stg_abi_version(void);
+/* 1 if stg_stt_step_f32 (STG_F_AXIS_Z, RK4, STG_F_THERMAL_PHILOX) takes the two-envs-per-thread kernel for n_envs envs and these
+ * flags on a GPU with sm_count SMs (<= 0: the current device), else 0. Both kernels give the same bits per env; this is the
+ * dispatch rule of stt_kernels.cu made visible to tests and tools. */
+int stg_stt_thermal_pair_dispatch(int64_t n_envs, uint32_t flags, int sm_count);
 const char* stg_error_string(int code);
 
 /* Host-side: fold n raw parameter sets into kernel constants (pure CPU, no CUDA call). Replaces the per-RHS-call

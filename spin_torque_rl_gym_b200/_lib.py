@@ -153,6 +153,7 @@ class StgEnergyParams(C.Structure):
 # every symbol include/stg.h declares: (name, restype, argtypes)
 SYMBOLS = {
     "stg_abi_version": (C.c_int, []),
+    "stg_stt_thermal_pair_dispatch": (C.c_int, [C.c_int64, C.c_uint32, C.c_int]),
     "stg_error_string": (C.c_char_p, [C.c_int]),
     "stg_stt_fold": (C.c_int, [C.POINTER(StgSttParams), C.c_int32, C.POINTER(StgSttFolded)]),
     "stg_stt_all_axis_z": (C.c_int, [C.POINTER(StgSttFolded), C.c_int32]),

@@ -313,6 +313,41 @@ static cudaError_t launch_redo(const StepArgs& a, cudaStream_t s) {
 // components to 24 bits is a systematic rate error the 1e-4 contract does not survive over thousands of substeps.
 // The explicit Euler map amplifies rounding errors chaotically (0.35 rad per substep, renormalised): FP32 stages do not hold the
 // 1e-4 contract there either, so Euler runs FP64 stages through both entry points as well.
+// Does the thermal FP32 step (axis z, RK4, in-kernel stream) of n_envs envs take the two-envs-per-thread kernel? (exported as
+// stg_stt_thermal_pair_dispatch for tests and tools)
+//   * STG_F_NO_PAIR / STG_F_PAIR_ALWAYS decide by themselves;
+//   * from STG_PAIR_THERMAL_MIN_ENVS envs (262,144; all-Philox stream: 524,288, where the packed kernel only draws level - 5.24 vs
+//     5.23 ms, 2.70 vs 2.65 at 262,144) the GPU is several waves deep and the packed kernel's throughput wins (8.55 vs 9.22 ms
+//     at 1,048,576 envs, 2.21 vs 2.35 at 262,144);
+//   * batches of at most one wave of the packed kernel: every CTA is two warps and an SM has four schedulers, so with k CTAs per
+//     SM the busiest scheduler runs ceil(k / 2) warps and the step time is a staircase in that count (measured, 999 substeps,
+//     one env per thread: 0.25 / 0.375 / 0.56 / 0.72 / 0.90 / 1.05 / 1.22 ms for 1 .. 7 warps; two envs per thread: 0.415 / 0.70 /
+//     0.99 / 1.30 ms for 1 .. 4). The packed kernel has half as many CTAs, each ~1.75x as long: it wins (by 3 - 6 %) exactly
+//     when it halves the busiest scheduler's warp count and that count is at least 2 - e.g. 65,536 envs (BASELINE configs[1]):
+//     7 CTAs per SM = 4 warps against 4 CTAs = 2 warps, 0.70 vs 0.72 ms; 95,000 .. 113,664 envs: 0.99 vs 1.05 - and loses
+//     otherwise (76,000 .. 94,000 envs: 0.99 vs 0.90; 131,072: 1.30 vs 1.21). profiles/README.md.
+static bool thermal_pair_dispatch(int64_t n_envs, uint32_t flags, int sms) {
+    if (flags & STG_F_NO_PAIR) return false;
+    if (flags & STG_F_PAIR_ALWAYS) return true;
+    const bool all_philox = (flags & STG_F_STREAM_PHILOX10) != 0;
+    if (n_envs >= (all_philox ? 2 : 1) * (int64_t)STG_PAIR_THERMAL_MIN_ENVS) return true;
+    if (all_philox || kBlock != 64 || sms <= 0) return false;
+    const int64_t k_s = ((n_envs + kBlock - 1) / kBlock + sms - 1) / sms;
+    const int64_t k_p = ((n_envs + 2 * kBlock - 1) / (2 * kBlock) + sms - 1) / sms;
+    const int64_t w_s = (k_s + 1) / 2, w_p = (k_p + 1) / 2;
+    return k_p <= STG_PAIR_MINBLOCKS_TH && w_p >= 2 && w_s == 2 * w_p;
+}
+static int sm_count() {      // of the current device (every GPU of a node is the same part); 148 on B200
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+            n = v;
+        else
+            return 148;
+    }
+    return n;
+}
 template <typename R>
 static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
     // 3: the in-kernel stream with every word from Philox4x32-10 (Euler draws from Philox blocks in either case)
@@ -335,10 +370,7 @@ static cudaError_t launch_step(const StepArgs& a, bool axis_z, cudaStream_t s) {
         return noise == 0 ? launch_redo<0>(a, s) : launch_redo<2>(a, s);
     }
     if (axis_z) {
-        // (all-Philox stream: the packed kernel only draws level at 524,288 envs - 5.24 vs 5.23 ms, 2.70 vs 2.65 at 262,144)
-        const int64_t pair_min_envs = noise == 3 ? 2 * (int64_t)STG_PAIR_THERMAL_MIN_ENVS : (int64_t)STG_PAIR_THERMAL_MIN_ENVS;
-        if (sizeof(R) == 4 && (noise == 1 || noise == 3) && !(a.flags & STG_F_NO_PAIR) &&
-            (a.n_envs >= pair_min_envs || (a.flags & STG_F_PAIR_ALWAYS))) {
+        if (sizeof(R) == 4 && (noise == 1 || noise == 3) && thermal_pair_dispatch(a.n_envs, a.flags, sm_count())) {
             // two envs per thread on packed FP32x2 arithmetic, one noise stream per lane (bit-identical to one env per thread).
             // Measured (profiles/README.md, 999 substeps): 8.78 vs 9.27 ms at 1,048,576 envs, 2.26 vs 2.36 at 262,144; below
             // that the one-env-per-thread kernel has twice as many threads to fill the GPU with (1.33 vs 1.21 ms at 131,072
@@ -403,6 +435,9 @@ static cudaError_t launch_solve(const SolveArgs& a, uint32_t flags, bool axis_z,
 using namespace stg;
 
 extern "C" int stg_abi_version(void) { return STG_ABI_VERSION; }
+extern "C" int stg_stt_thermal_pair_dispatch(int64_t n_envs, uint32_t flags, int sm_count) {
+    return stg::thermal_pair_dispatch(n_envs, flags, sm_count > 0 ? sm_count : stg::sm_count()) ? 1 : 0;
+}
 
 extern "C" const char* stg_error_string(int code) {
     switch (code) {

@@ -160,3 +160,17 @@ def test_flag_constants_of_the_binding_equal_the_header():
     for name, val in flags:
         assert getattr(_lib, name[len("STG_"):]) == int(val, 16), name
     assert len({int(v, 16) for _, v in flags}) == len(flags)          # no two flags share a bit
+
+
+def test_thermal_pair_kernel_dispatch_rule():
+    """stg_stt_thermal_pair_dispatch on 148 SMs (B200): the packed kernel from 262,144 envs (all-Philox stream: 524,288), and in
+    the one-wave window exactly where it halves the busiest scheduler's warp count (measured table in profiles/README.md)."""
+    lib = _lib.load()
+    f = _lib.F_THERMAL_PHILOX | _lib.F_AXIS_Z
+    want = {1024: 0, 32768: 0, 49152: 0, 56832: 0, 57000: 1, 65536: 1, 75776: 1, 76000: 0, 90000: 0, 95000: 1, 113664: 1,
+            114000: 0, 131072: 0, 196608: 0, 262143: 0, 262144: 1, 1 << 20: 1}
+    for n, w in want.items():
+        assert lib.stg_stt_thermal_pair_dispatch(n, f, 148) == w, n
+        assert lib.stg_stt_thermal_pair_dispatch(n, f | _lib.F_NO_PAIR, 148) == 0
+        assert lib.stg_stt_thermal_pair_dispatch(n, f | _lib.F_PAIR_ALWAYS, 148) == 1
+        assert lib.stg_stt_thermal_pair_dispatch(n, f | _lib.F_STREAM_PHILOX10, 148) == (1 if n >= (1 << 19) else 0)
